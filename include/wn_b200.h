@@ -1,0 +1,145 @@
+/*
+ * wn_b200.h -- C ABI of libwn_b200.so: the B200 (sm_100a) WaveNet autoregressive sample loop.
+ *
+ * The reference (hccho2/Tacotron-Wavenet-Vocoder-Korean) has no FFI: the path sits behind Python
+ * class / CLI signatures.  Each entry point below names the reference interface it stands in for
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions: plain C types only, no torch / C++ types cross the boundary.  Every call returns
+ * WN_OK (0) or a negative error code; wn_last_error(h) gives the message.  No C++ exception crosses
+ * the ABI.  "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors' data_ptr())
+ * and only borrowed for the duration of the stream-ordered call; the library owns its packed weight
+ * images, mailboxes and dilation-queue rings.  A handle is re-entrant per stream: calls on one handle
+ * must be stream-ordered by the caller; different handles are independent.  There is no CPU fallback:
+ * every compute entry point fails with WN_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef WN_B200_H
+#define WN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WN_OK 0
+#define WN_ERR_ARG (-1)        /* bad argument / unsupported configuration */
+#define WN_ERR_STATE (-2)      /* call order (e.g. generate before finalize, missing weights) */
+#define WN_ERR_CUDA (-3)       /* CUDA runtime error, no device, launch failure */
+#define WN_ERR_TIMEOUT (-4)    /* the persistent kernel aborted on its in-kernel watchdog */
+
+#define WN_MAX_LAYERS 256
+#define WN_MAX_UPSAMPLE 8
+#define WN_MAX_BATCH 32
+
+/* Construction arguments of wavenet.model.WaveNetModel.__init__ (wavenet/model.py:8-10), train_mode=False.
+ * force_M / force_Mt = 0 lets the library pick the layer / tail split (tests pin them to cover
+ * every evaluation plan). */
+typedef struct wn_config {
+    int32_t batch;                     /* batch_size: utterances generated together (<= WN_MAX_BATCH) */
+    int32_t n_layers;                  /* len(dilations) */
+    int32_t filter_width;              /* must be 2 (hparams.py:59) */
+    int32_t residual_channels;
+    int32_t dilation_channels;
+    int32_t skip_channels;
+    int32_t quantization_channels;
+    int32_t out_channels;
+    int32_t use_biases;
+    int32_t scalar_input;
+    int32_t initial_filter_width;
+    int32_t gc_channels;               /* global_condition_channels or 0 */
+    int32_t gc_cardinality;            /* global_condition_cardinality or 0 */
+    int32_t lc_channels;               /* local_condition_channels or 0 */
+    int32_t n_upsample;
+    int32_t upsample_factor[WN_MAX_UPSAMPLE];
+    int32_t dilations[WN_MAX_LAYERS];
+    int32_t force_M;
+    int32_t force_Mt;
+} wn_config;
+
+/* Floating-point evaluation order implemented by the kernel (DESIGN.md "Pinned arithmetic").
+ * Field meaning is identical to oracle/wn_oracle.c's orc_plan. */
+typedef struct wn_plan {
+    int32_t M, Mt, t_cur, t_old, t_lc, t_gc, t_dense, t_skip, t_post1, t_post2, t_causal;
+} wn_plan;
+
+typedef struct wn_info {
+    int32_t grid;                      /* CTAs of the persistent kernel (1 per SM) */
+    int32_t threads;                   /* threads per CTA */
+    int32_t M, Mt;
+    int32_t smem_bytes_layer, smem_bytes_tail, smem_bytes_sampler;
+    int32_t sm_count;
+    int64_t p_hot;                     /* weights touched per step, gc folded into biases */
+    int64_t weights_in_smem;           /* floats resident in shared memory over the whole grid */
+    int64_t weights_in_global;         /* floats that overflowed to L2/HBM */
+    int64_t kernel_launches;           /* kernels launched by this handle so far */
+} wn_info;
+
+typedef struct wn_handle wn_handle;
+
+/* WaveNetModel(...) constructor, wavenet/model.py:8-30. */
+int wn_create(const wn_config *cfg, wn_handle **out);
+void wn_destroy(wn_handle *h);
+const char *wn_last_error(const wn_handle *h);      /* h may be NULL: last create error */
+
+/* tf.train.Saver.restore of the non-queue variables (generate.py:157-161, utils/__init__.py:75-90).
+ * `name` is the TF variable name, `data` a HOST pointer to n floats in TF layout. */
+int wn_set_weight(wn_handle *h, const char *name, const float *data, int64_t n);
+/* Packs the weights into per-SM shared-memory images and uploads them.  Must follow the last
+ * wn_set_weight and precede any compute call. */
+int wn_finalize(wn_handle *h);
+
+int wn_get_plan(const wn_handle *h, wn_plan *plan);
+int wn_get_info(const wn_handle *h, wn_info *info);
+
+/* WaveNetModel.calculate_receptive_field, wavenet/model.py:31-39. */
+int wn_receptive_field(int filter_width, const int32_t *dilations, int n, int scalar_input,
+                       int initial_filter_width);
+
+/* WaveNetModel.create_upsample, wavenet/model.py:102-111 (evaluated once per utterance, generate.py:155,200).
+ * mel_dev (rows, t_mel, lc_channels) -> out_dev (rows, t_mel*prod(upsample_factor), lc_channels). */
+int wn_upsample(wn_handle *h, const float *mel_dev, int rows, int t_mel, float *out_dev, void *stream);
+
+/* The hot loop of generate.py:202-233 over sess.run(predict_proba_incremental) (wavenet/model.py:215-245)
+ * including the sample draw (wavenet/mixture.py:84-114 or generate.py:219-231), as ONE persistent kernel. */
+typedef struct wn_generate_args {
+    int32_t rows;                 /* utterances in this call, 1..cfg.batch */
+    int32_t T;                    /* network steps per row (max over rows when T_row != NULL) */
+    const int32_t *T_row;         /* HOST, optional per-row step counts (<= T) */
+    int32_t n_forced;             /* >= 1: x_in(t) = forced[row][t] for t < n_forced, else the sample drawn at t-1
+                                     (1 = free running from an initial sample, generate.py:184-192;
+                                      len(seed) = priming, generate.py:177-180; T = teacher forcing) */
+    const float *forced_dev;      /* (rows, n_forced) fp32; mu-law ids are stored as floats (generate.py:190) */
+    const float *lc_dev;          /* (rows, t_lc, lc_channels) upsampled local condition, or NULL */
+    int32_t t_lc;
+    int32_t lc_shift;             /* step t pushes row t - lc_shift into the lc queue (zeros if out of range) */
+    const int32_t *gc_ids;        /* HOST (rows) speaker ids or NULL */
+    const void *uniforms_dev;     /* scalar_input: (rows, T, out_channels/3 + 1) fp32 in (1e-5, 1-1e-5)
+                                     one-hot:      (rows, T) fp64 in [0,1) */
+    float temperature;            /* generate.py:51; only the mu-law path uses it */
+    float *out_samples_dev;       /* (rows, T) fp32 */
+    float *out_logits_dev;        /* optional (rows, T, out_dim) raw conv2 output, or NULL */
+} wn_generate_args;
+
+/* Stream-ordered and asynchronous: returns after the launch. */
+int wn_generate(wn_handle *h, const wn_generate_args *args, void *stream);
+
+/* Synchronises `stream` and reports WN_ERR_TIMEOUT if the kernel's watchdog aborted the last launch. */
+int wn_sync_check(wn_handle *h, void *stream);
+
+/* Same, through HOST buffers: mel in, waveform out, host<->device copies inside (the call a
+ * generate.py user effectively makes: np.load(mel) ... save_wav).  mel_host (rows, t_mel, lc_channels) is
+ * upsampled on the device (args->lc_dev is then ignored), or NULL.  Pointer fields of `args` named
+ * *_dev are HOST pointers here.  Synchronous; includes the watchdog check. */
+int wn_generate_host(wn_handle *h, const wn_generate_args *args, const float *mel_host, int t_mel);
+
+/* wavenet.ops.mu_law_encode / mu_law_decode, wavenet/ops.py:22-47, element-wise on device buffers. */
+int wn_mu_law_encode(const float *audio_dev, int64_t n, int quantization_channels, int32_t *out_dev, void *stream);
+int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, int quantization,
+                     float *out_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,97 @@
+"""ctypes binding of libwn_b200.so (include/wn_b200.h).  There is no fallback: if the CUDA
+library is missing or no sm_100 device is usable, every compute entry point raises."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwn_b200.so")
+
+WN_MAX_LAYERS = 256
+WN_MAX_UPSAMPLE = 8
+WN_MAX_BATCH = 32
+
+
+class WnConfig(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("n_layers", C.c_int32), ("filter_width", C.c_int32),
+        ("residual_channels", C.c_int32), ("dilation_channels", C.c_int32), ("skip_channels", C.c_int32),
+        ("quantization_channels", C.c_int32), ("out_channels", C.c_int32),
+        ("use_biases", C.c_int32), ("scalar_input", C.c_int32), ("initial_filter_width", C.c_int32),
+        ("gc_channels", C.c_int32), ("gc_cardinality", C.c_int32), ("lc_channels", C.c_int32),
+        ("n_upsample", C.c_int32), ("upsample_factor", C.c_int32 * WN_MAX_UPSAMPLE),
+        ("dilations", C.c_int32 * WN_MAX_LAYERS),
+        ("force_M", C.c_int32), ("force_Mt", C.c_int32),
+    ]
+
+
+class WnPlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("M", "Mt", "t_cur", "t_old", "t_lc", "t_gc", "t_dense", "t_skip", "t_post1", "t_post2", "t_causal")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class WnInfo(C.Structure):
+    _fields_ = [("grid", C.c_int32), ("threads", C.c_int32), ("M", C.c_int32), ("Mt", C.c_int32),
+                ("smem_bytes_layer", C.c_int32), ("smem_bytes_tail", C.c_int32), ("smem_bytes_sampler", C.c_int32),
+                ("sm_count", C.c_int32), ("p_hot", C.c_int64), ("weights_in_smem", C.c_int64),
+                ("weights_in_global", C.c_int64), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class WnGenerateArgs(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("T", C.c_int32), ("T_row", C.POINTER(C.c_int32)),
+                ("n_forced", C.c_int32), ("forced_dev", C.c_void_p), ("lc_dev", C.c_void_p),
+                ("t_lc", C.c_int32), ("lc_shift", C.c_int32), ("gc_ids", C.POINTER(C.c_int32)),
+                ("uniforms_dev", C.c_void_p), ("temperature", C.c_float),
+                ("out_samples_dev", C.c_void_p), ("out_logits_dev", C.c_void_p)]
+
+
+EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_get_plan",
+           "wn_get_info", "wn_receptive_field", "wn_upsample", "wn_generate", "wn_sync_check",
+           "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode"]
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libwn_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc")]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout)
+    if out.returncode != 0:
+        raise RuntimeError("building libwn_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        H = C.c_void_p
+        L.wn_create.argtypes = [C.POINTER(WnConfig), C.POINTER(H)]
+        L.wn_destroy.argtypes = [H]
+        L.wn_destroy.restype = None
+        L.wn_last_error.argtypes = [H]
+        L.wn_last_error.restype = C.c_char_p
+        L.wn_set_weight.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
+        L.wn_finalize.argtypes = [H]
+        L.wn_get_plan.argtypes = [H, C.POINTER(WnPlan)]
+        L.wn_get_info.argtypes = [H, C.POINTER(WnInfo)]
+        L.wn_receptive_field.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.wn_upsample.argtypes = [H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.wn_generate.argtypes = [H, C.POINTER(WnGenerateArgs), C.c_void_p]
+        L.wn_sync_check.argtypes = [H, C.c_void_p]
+        L.wn_generate_host.argtypes = [H, C.POINTER(WnGenerateArgs), C.c_void_p, C.c_int]
+        L.wn_mu_law_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.wn_mu_law_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib

@@ -1,0 +1,663 @@
+// wn_api.cu -- host side of libwn_b200.so: the C ABI declared in include/wn_b200.h.
+//
+// Responsibilities: hold the TF-named weights (generate.py:157-161), choose the CTA topology and the
+// evaluation plan, pack every matrix into the per-CTA thread-major shared-memory images, own the
+// mailboxes / dilation-queue rings, and launch the persistent kernel cooperatively.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include "wn_params.h"
+
+// single translation unit: the device code is compiled together with its launch sites
+#include "wn_kernel.cu"
+
+namespace {
+
+constexpr int kMaxDynSmem = 232448 - 2048;   // 227 KB opt-in limit minus static/reserved slack
+
+std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; bytes = 0; if (e != cudaSuccess) return e; }
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct wn_handle {
+    wn_config cfg;
+    std::map<std::string, std::vector<float>> w;
+    bool finalized = false;
+    std::string err;
+    int out_dim = 0;
+    int sm_count = 0;
+    wn_plan plan{};
+    wn_info info{};
+    WnParams base{};            // everything except the per-call fields
+    int smem_layer = 0, smem_tail = 0, smem_samp = 0, smem_launch = 0;
+    DevBuf layer_img, tail_img, samp_img, gc_table, wc_onehot, upk, mbox, ring, ring_off, status;
+    DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
+    DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
+    size_t mbox_bytes = 0, ring_bytes = 0;
+    std::vector<int> up_off;   // float offsets of the upsample kernels inside `upk`
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(wn_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) return fail(h, WN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+int align4(int v) { return (v + 3) & ~3; }
+int align32(int v) { return (v + 31) & ~31; }
+
+// evaluation-plan choice: as many k-chunks per column as there are idle threads (keeps the fma chains
+// short), power of two, chunk length >= 4.
+int choose_t(int ncols, int K, int cap)
+{
+    int t = 1;
+    while (t * 2 <= cap && (long)ncols * (t * 2) <= WN_NT && K % (t * 2) == 0 && K / (t * 2) >= 4) t *= 2;
+    return t;
+}
+
+WnMat make_mat(int K, int ncols, int t)
+{
+    WnMat m{};
+    m.K = K; m.ncols = ncols; m.t = t; m.ch = K / t;
+    m.V = (m.ch % 4 == 0) ? 4 : 1;
+    m.gpp = WN_NT / t;
+    m.npass = (ncols + m.gpp - 1) / m.gpp;
+    if (m.V == 4) m.xstride = ((m.ch / 4) % 2 == 1) ? m.ch : m.ch + 4;
+    else m.xstride = (m.ch % 2 == 1) ? m.ch : m.ch + 1;
+    m.xlen = align4(t * m.xstride);
+    m.in_smem = 1;
+    return m;
+}
+
+int mat_floats(const WnMat &m) { return m.npass * m.ch * WN_NT; }
+
+// pack W (accessed through get(k, col)) into the thread-major layout described in wn_params.h
+template <class Get>
+void pack_mat(const WnMat &m, float *dst, Get get)
+{
+    for (int pass = 0; pass < m.npass; ++pass)
+        for (int tid = 0; tid < WN_NT; ++tid) {
+            int col = pass * m.gpp + tid / m.t;
+            int chunk = tid % m.t;
+            for (int i = 0; i < m.ch; ++i) {
+                float v = (col < m.ncols) ? get(chunk * m.ch + i, col) : 0.0f;
+                size_t idx;
+                if (m.V == 4) idx = (((size_t)pass * (m.ch / 4) + i / 4) * WN_NT + tid) * 4 + (i % 4);
+                else idx = ((size_t)pass * m.ch + i) * WN_NT + tid;
+                dst[idx] = v;
+            }
+        }
+}
+
+const std::vector<float> *find_w(wn_handle *h, const std::string &name)
+{
+    auto it = h->w.find(name);
+    return it == h->w.end() ? nullptr : &it->second;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char *wn_last_error(const wn_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int wn_receptive_field(int filter_width, const int32_t *dilations, int n, int scalar_input, int initial_filter_width)
+{
+    long s = 0;
+    for (int i = 0; i < n; ++i) s += dilations[i];
+    long rf = (long)(filter_width - 1) * s + 1;
+    rf += scalar_input ? initial_filter_width - 1 : filter_width - 1;
+    return (int)rf;
+}
+
+int wn_create(const wn_config *cfg, wn_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, WN_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->filter_width != 2) return fail(nullptr, WN_ERR_ARG, "filter_width must be 2 (got %d)", cfg->filter_width);
+    if (cfg->batch < 1 || cfg->batch > WN_MAX_BATCH) return fail(nullptr, WN_ERR_ARG, "batch must be in 1..%d", WN_MAX_BATCH);
+    if (cfg->n_layers < 1 || cfg->n_layers > WN_MAX_LAYERS) return fail(nullptr, WN_ERR_ARG, "n_layers out of range");
+    if (cfg->residual_channels < 1 || cfg->residual_channels > WN_NT) return fail(nullptr, WN_ERR_ARG, "residual_channels must be <= %d", WN_NT);
+    if (cfg->dilation_channels < 1 || cfg->dilation_channels > WN_NT || cfg->skip_channels < 1)
+        return fail(nullptr, WN_ERR_ARG, "dilation_channels must be in 1..%d, skip_channels >= 1", WN_NT);
+    if (cfg->n_upsample < 0 || cfg->n_upsample > WN_MAX_UPSAMPLE) return fail(nullptr, WN_ERR_ARG, "too many upsample stages");
+    for (int i = 0; i < cfg->n_layers; ++i)
+        if (cfg->dilations[i] < 1) return fail(nullptr, WN_ERR_ARG, "dilation %d < 1", i);
+    int out_dim = cfg->scalar_input ? cfg->out_channels : cfg->quantization_channels;
+    if (cfg->scalar_input) {
+        if (out_dim % 3 != 0 || out_dim / 3 > 32 || out_dim < 3) return fail(nullptr, WN_ERR_ARG, "out_channels must be 3*nr_mix, nr_mix <= 32");
+        if (cfg->initial_filter_width < 1 || cfg->initial_filter_width > WN_NT) return fail(nullptr, WN_ERR_ARG, "initial_filter_width out of range");
+    } else {
+        if (!is_pow2(out_dim) || out_dim < 32 || out_dim > WN_NT) return fail(nullptr, WN_ERR_ARG, "quantization_channels must be a power of two in 32..%d", WN_NT);
+    }
+    if (cfg->gc_channels && cfg->gc_cardinality < 1) return fail(nullptr, WN_ERR_ARG, "gc_cardinality required with gc_channels");
+    if (cfg->lc_channels > WN_NT || cfg->gc_channels > WN_NT) return fail(nullptr, WN_ERR_ARG, "conditioning channels must be <= %d", WN_NT);
+    wn_handle *h = new wn_handle();
+    h->cfg = *cfg;
+    h->out_dim = out_dim;
+    *out = h;
+    return WN_OK;
+}
+
+void wn_destroy(wn_handle *h)
+{
+    if (!h) return;
+    DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
+                      &h->ring_off, &h->status, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
+                      &h->h_out, &h->h_logits};
+    for (DevBuf *b : bufs) b->release();
+    delete h;
+}
+
+int wn_set_weight(wn_handle *h, const char *name, const float *data, int64_t n)
+{
+    if (!h || !name || !data || n <= 0) return fail(h, WN_ERR_ARG, "wn_set_weight: bad argument");
+    h->w[name] = std::vector<float>(data, data + n);
+    h->finalized = false;
+    return WN_OK;
+}
+
+int wn_finalize(wn_handle *h)
+{
+    if (!h) return WN_ERR_ARG;
+    const wn_config &c = h->cfg;
+    const int N = c.batch, L = c.n_layers, R = c.residual_channels, D = c.dilation_channels, S = c.skip_channels;
+    const int G = c.gc_channels, C = c.lc_channels, O = h->out_dim, Q = c.quantization_channels, ifw = c.initial_filter_width;
+    h->info = wn_info{};
+
+    int dev = 0;
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDevice(&dev));
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(h, WN_ERR_CUDA, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) return fail(h, WN_ERR_CUDA, "device does not support cooperative launch");
+    h->sm_count = prop.multiProcessorCount;
+
+    // ---- required weights, in TF layout --------------------------------------------------------
+    auto need = [&](const std::string &nm, size_t n, const std::vector<float> **out) -> int {
+        const std::vector<float> *v = find_w(h, nm);
+        if (!v) return fail(h, WN_ERR_STATE, "missing weight %s", nm.c_str());
+        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
+        *out = v;
+        return WN_OK;
+    };
+    std::vector<float> zeros((size_t)std::max(std::max(S, D), std::max(R, O)) + 8, 0.0f);
+    auto opt = [&](const std::string &nm, size_t n, const float **out) -> int {
+        const std::vector<float> *v = find_w(h, nm);
+        if (!v) { *out = zeros.data(); return WN_OK; }
+        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
+        *out = v->data();
+        return WN_OK;
+    };
+
+    // ---- topology --------------------------------------------------------------------------------
+    int M = c.force_M ? c.force_M : std::min(4, std::max(1, D / 32));
+    int Mt = c.force_Mt ? c.force_Mt : std::min(16, std::max(1, S / 32));
+    if (!is_pow2(M) || M > 4 || D % M) return fail(h, WN_ERR_ARG, "layer split M=%d invalid for D=%d (power of two <= 4 dividing D)", M, D);
+    if (!is_pow2(Mt) || Mt > 32 || S % Mt) return fail(h, WN_ERR_ARG, "tail split Mt=%d invalid for S=%d", Mt, S);
+    if (!c.force_M) while (M > 1 && L * M + Mt + 1 > h->sm_count) M >>= 1;
+    if (!c.force_Mt) while (Mt > 1 && L * M + Mt + 1 > h->sm_count) Mt >>= 1;
+    const int grid = L * M + Mt + 1;
+    if (grid > h->sm_count) return fail(h, WN_ERR_ARG, "%d layers x M=%d + %d tail + 1 sampler = %d CTAs exceed the %d SMs", L, M, Mt, grid, h->sm_count);
+    const int Dm = D / M, Sm = S / M, St = S / Mt;
+    if (2 * Dm > WN_NT) return fail(h, WN_ERR_ARG, "2*D/M = %d filter/gate columns exceed %d threads", 2 * Dm, WN_NT);
+    if (St > WN_NT) return fail(h, WN_ERR_ARG, "S/Mt = %d exceeds %d threads", St, WN_NT);
+
+    WnParams &p = h->base;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.L = L; p.R = R; p.D = D; p.S = S; p.O = O; p.Q = Q; p.G = G; p.C = C; p.ifw = ifw;
+    p.scalar_input = c.scalar_input; p.nr_mix = c.scalar_input ? O / 3 : 0;
+    p.M = M; p.Mt = Mt; p.Dm = Dm; p.Sm = Sm; p.St = St; p.grid = grid;
+    for (int i = 0; i < L; ++i) p.dil[i] = c.dilations[i];
+
+    // ---- evaluation plan ----------------------------------------------------------------------------
+    const int t_fg = choose_t(2 * Dm, R, 16);            // <= 16 so filter/gate partner columns share a warp
+    p.cur = make_mat(R, 2 * Dm, t_fg);
+    p.old = make_mat(R, 2 * Dm, t_fg);
+    p.lc = make_mat(C ? C : 4, 2 * Dm, C ? choose_t(2 * Dm, C, 32) : 1);
+    p.gc = make_mat(G ? G : 4, 2 * Dm, G ? choose_t(2 * Dm, G, 32) : 1);
+    p.dense = make_mat(Dm, R, choose_t(R, Dm, 32));
+    p.skip = make_mat(D, Sm, choose_t(Sm, D, 32));
+    p.post1 = make_mat(S, St, choose_t(St, S, 32));
+    p.post2 = make_mat(St, O, choose_t(O, St, 32));
+    p.causal = make_mat(c.scalar_input ? ifw : 4, R, c.scalar_input ? choose_t(R, ifw, 32) : 1);
+    if (p.cur.npass != 1 || p.old.npass != 1) return fail(h, WN_ERR_ARG, "internal: filter/gate must be single pass");
+    h->plan = wn_plan{M, Mt, p.cur.t, p.old.t, p.lc.t, p.gc.t, p.dense.t, p.skip.t, p.post1.t, p.post2.t, p.causal.t};
+
+    // ---- layer images ---------------------------------------------------------------------------------
+    // image = [bfg | bd | bs | cur | dense | skip | old | lc | gc]; the resident prefix is what fits.
+    {
+        int off = 0;
+        p.off_bfg = off; off += align4(2 * Dm);
+        p.off_bd = off; off += align4(R);
+        p.off_bs = off; off += align4(Sm);
+        WnMat *order[6] = {&p.cur, &p.dense, &p.skip, &p.old, &p.lc, &p.gc};
+        bool present[6] = {true, true, true, true, C > 0, G > 0};
+        // scratch
+        int so = 0;
+        p.ls.xs_cur = so; so += p.cur.xlen;
+        p.ls.xs_old = so; so += p.old.xlen;
+        p.ls.lcs = so; so += p.lc.xlen;
+        p.ls.xraw = so; so += align4(R);
+        p.ls.zs_dense = so; so += p.dense.xlen;
+        p.ls.zs_skip = so; so += p.skip.xlen;
+        p.ls.gvec = so; so += p.gc.xlen;
+        p.ls.bfgN = so; so += align4(N * 2 * Dm);
+        p.ls.pre = so; so += align4(N * 2 * Dm);
+        p.ls.total_floats = so;
+        const int cap = kMaxDynSmem / 4 - so;
+        int resident = off;
+        bool spill = false;
+        for (int i = 0; i < 6; ++i) {
+            WnMat &m = *order[i];
+            m.off = off;
+            int n = present[i] ? mat_floats(m) : 0;
+            if (!present[i]) { m.in_smem = 1; continue; }
+            if (!spill && off + n <= cap) { m.in_smem = 1; resident = off + n; }
+            else { m.in_smem = 0; spill = true; h->info.weights_in_global += (int64_t)n * L * M; }
+            off += n;
+        }
+        if (resident > cap) return fail(h, WN_ERR_ARG, "per-CTA vectors do not fit shared memory");
+        p.layer_img_floats = align32(off);
+        p.layer_smem_floats = align4(resident);
+        h->smem_layer = (p.layer_smem_floats + so) * 4;
+    }
+    std::vector<float> limg((size_t)p.layer_img_floats * L * M, 0.0f);
+    for (int l = 0; l < L; ++l) {
+        std::string pre = "wavenet/dilated_stack/layer" + std::to_string(l) + "/dilation_layer/";
+        const std::vector<float> *wf, *wg, *wd, *ws, *gcf = nullptr, *gcg = nullptr, *lcf = nullptr, *lcg = nullptr;
+        int rc;
+        if ((rc = need(pre + "conv_filter/kernel", (size_t)2 * R * D, &wf))) return rc;
+        if ((rc = need(pre + "conv_gate/kernel", (size_t)2 * R * D, &wg))) return rc;
+        if ((rc = need(pre + "dense/kernel", (size_t)D * R, &wd))) return rc;
+        if ((rc = need(pre + "skip/kernel", (size_t)D * S, &ws))) return rc;
+        if (G) { if ((rc = need(pre + "gc_filter/kernel", (size_t)G * D, &gcf))) return rc; if ((rc = need(pre + "gc_gate/kernel", (size_t)G * D, &gcg))) return rc; }
+        if (C) { if ((rc = need(pre + "lc_filter/kernel", (size_t)C * D, &lcf))) return rc; if ((rc = need(pre + "lc_gate/kernel", (size_t)C * D, &lcg))) return rc; }
+        const float *bf, *bg, *bd, *bs;
+        if ((rc = opt(pre + "conv_filter/bias", D, &bf))) return rc;
+        if ((rc = opt(pre + "conv_gate/bias", D, &bg))) return rc;
+        if ((rc = opt(pre + "dense/bias", R, &bd))) return rc;
+        if ((rc = opt(pre + "skip/bias", S, &bs))) return rc;
+        for (int m = 0; m < M; ++m) {
+            float *img = limg.data() + (size_t)(l * M + m) * p.layer_img_floats;
+            for (int j = 0; j < Dm; ++j) { img[p.off_bfg + 2 * j] = bf[m * Dm + j]; img[p.off_bfg + 2 * j + 1] = bg[m * Dm + j]; }
+            for (int r = 0; r < R; ++r) img[p.off_bd + r] = bd[r];
+            for (int s = 0; s < Sm; ++s) img[p.off_bs + s] = bs[m * Sm + s];
+            // column c = 2*j + (0: filter, 1: gate) for gated channel m*Dm + j
+            auto fgcol = [&](const std::vector<float> *f, const std::vector<float> *g, size_t base, int k, int col) {
+                const std::vector<float> *src = (col & 1) ? g : f;
+                return (*src)[base + (size_t)k * D + (m * Dm + (col >> 1))];
+            };
+            pack_mat(p.cur, img + p.cur.off, [&](int k, int col) { return fgcol(wf, wg, (size_t)R * D, k, col); });   // tap 1 = current
+            pack_mat(p.old, img + p.old.off, [&](int k, int col) { return fgcol(wf, wg, 0, k, col); });               // tap 0 = dilated
+            if (C) pack_mat(p.lc, img + p.lc.off, [&](int k, int col) { return fgcol(lcf, lcg, 0, k, col); });
+            if (G) pack_mat(p.gc, img + p.gc.off, [&](int k, int col) { return fgcol(gcf, gcg, 0, k, col); });
+            pack_mat(p.dense, img + p.dense.off, [&](int k, int r) { return (*wd)[(size_t)(m * Dm + k) * R + r]; });
+            pack_mat(p.skip, img + p.skip.off, [&](int k, int s) { return (*ws)[(size_t)k * S + (m * Sm + s)]; });
+        }
+    }
+
+    // ---- tail images -------------------------------------------------------------------------------------
+    {
+        int off = 0;
+        p.off_b1 = off; off += align4(St);
+        int so = 0;
+        p.ts.as1 = so; so += p.post1.xlen;
+        p.ts.c1s = so; so += p.post2.xlen;
+        p.ts.total_floats = so;
+        const int cap = kMaxDynSmem / 4 - so;
+        p.post1.off = off; off += mat_floats(p.post1);
+        p.post2.off = off; off += mat_floats(p.post2);
+        int resident = off;
+        if (off > cap) {   // spill conv2 first, then conv1
+            p.post2.in_smem = 0; resident = p.post2.off;
+            h->info.weights_in_global += (int64_t)mat_floats(p.post2) * Mt;
+            if (resident > cap) { p.post1.in_smem = 0; resident = p.post1.off; h->info.weights_in_global += (int64_t)mat_floats(p.post1) * Mt; }
+        }
+        p.tail_img_floats = align32(off);
+        p.tail_smem_floats = align4(resident);
+        h->smem_tail = (p.tail_smem_floats + so) * 4;
+    }
+    std::vector<float> timg((size_t)p.tail_img_floats * Mt, 0.0f);
+    const float *b2v;
+    {
+        const std::vector<float> *w1, *w2;
+        int rc;
+        if ((rc = need("wavenet/conv1d_1/kernel", (size_t)S * S, &w1))) return rc;
+        if ((rc = need("wavenet/conv1d_2/kernel", (size_t)S * O, &w2))) return rc;
+        const float *b1;
+        if ((rc = opt("wavenet/conv1d_1/bias", S, &b1))) return rc;
+        if ((rc = opt("wavenet/conv1d_2/bias", O, &b2v))) return rc;
+        for (int mt = 0; mt < Mt; ++mt) {
+            float *img = timg.data() + (size_t)mt * p.tail_img_floats;
+            for (int s = 0; s < St; ++s) img[p.off_b1 + s] = b1[mt * St + s];
+            pack_mat(p.post1, img + p.post1.off, [&](int k, int col) { return (*w1)[(size_t)k * S + (mt * St + col)]; });
+            pack_mat(p.post2, img + p.post2.off, [&](int k, int o) { return (*w2)[(size_t)(mt * St + k) * O + o]; });
+        }
+    }
+
+    // ---- sampler image ----------------------------------------------------------------------------------
+    std::vector<float> simg;
+    {
+        int off = 0;
+        p.off_b2 = off; off += align4(O);
+        p.causal.off = off;
+        if (c.scalar_input) off += mat_floats(p.causal);
+        int so = 0;
+        p.ss.c2s = so; so += align4(std::max(O, WN_NT));
+        p.ss.cq = so; so += align4(N * std::max(ifw, 1));
+        p.ss.cqx = so; so += p.causal.xlen;
+        p.ss.ids = so; so += align4(2 * N);
+        p.ss.qs = so; so += WN_NT;
+        so = (so + 1) & ~1;
+        p.ss.cdf = so; so += 2 * WN_NT;
+        p.ss.red = so; so += 2 * 16;
+        p.ss.misc = so; so += 32;
+        p.ss.total_floats = so;
+        if ((off + so) * 4 > kMaxDynSmem) return fail(h, WN_ERR_ARG, "sampler image does not fit shared memory");
+        p.samp_img_floats = align32(off);
+        p.samp_smem_floats = align4(off);
+        h->smem_samp = (p.samp_smem_floats + so) * 4;
+        simg.assign((size_t)p.samp_img_floats, 0.0f);
+        for (int o = 0; o < O; ++o) simg[p.off_b2 + o] = b2v[o];
+        const std::vector<float> *wc;
+        int rc;
+        if (c.scalar_input) {
+            if ((rc = need("wavenet/conv1d/kernel", (size_t)ifw * R, &wc))) return rc;
+            pack_mat(p.causal, simg.data() + p.causal.off, [&](int k, int r) { return (*wc)[(size_t)k * R + r]; });
+        } else {
+            if ((rc = need("wavenet/conv1d/kernel", (size_t)2 * Q * R, &wc))) return rc;
+            CUDA_TRY(h, h->wc_onehot.ensure(wc->size() * 4));
+            CUDA_TRY(h, cudaMemcpy(h->wc_onehot.p, wc->data(), wc->size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+
+    // ---- conditioning tables / upsample kernels --------------------------------------------------------
+    if (G) {
+        const std::vector<float> *gt;
+        int rc;
+        if ((rc = need("wavenet/gc_embedding", (size_t)c.gc_cardinality * G, &gt))) return rc;
+        CUDA_TRY(h, h->gc_table.ensure(gt->size() * 4));
+        CUDA_TRY(h, cudaMemcpy(h->gc_table.p, gt->data(), gt->size() * 4, cudaMemcpyHostToDevice));
+    }
+    h->up_off.clear();
+    if (C && c.n_upsample) {
+        std::vector<float> all;
+        for (int i = 0; i < c.n_upsample; ++i) {
+            const std::vector<float> *k;
+            int rc;
+            if ((rc = need("wavenet/upsample" + std::to_string(i) + "/kernel", (size_t)c.upsample_factor[i] * 2, &k))) return rc;
+            h->up_off.push_back((int)all.size());
+            all.insert(all.end(), k->begin(), k->end());
+        }
+        CUDA_TRY(h, h->upk.ensure(all.size() * 4));
+        CUDA_TRY(h, cudaMemcpy(h->upk.p, all.data(), all.size() * 4, cudaMemcpyHostToDevice));
+    }
+
+    // ---- upload images, allocate mailboxes and rings ---------------------------------------------------
+    CUDA_TRY(h, h->layer_img.ensure(limg.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->layer_img.p, limg.data(), limg.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, h->tail_img.ensure(timg.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->tail_img.p, timg.data(), timg.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, h->samp_img.ensure(simg.size() * 4));
+    CUDA_TRY(h, cudaMemcpy(h->samp_img.p, simg.data(), simg.size() * 4, cudaMemcpyHostToDevice));
+
+    const size_t n_x = (size_t)N * L * M * R, n_z = (size_t)N * L * M * Dm, n_acc = (size_t)N * L * M * Sm, n_c2 = (size_t)N * Mt * O;
+    h->mbox_bytes = (n_x + n_z + n_acc + n_c2) * 8;
+    CUDA_TRY(h, h->mbox.ensure(h->mbox_bytes));
+    std::vector<long long> roff(L);
+    size_t rtot = 0;
+    for (int l = 0; l < L; ++l) { roff[l] = (long long)rtot; rtot += (size_t)M * N * c.dilations[l] * R; }
+    h->ring_bytes = rtot * 4;
+    CUDA_TRY(h, h->ring.ensure(std::max<size_t>(h->ring_bytes, 16)));
+    CUDA_TRY(h, h->ring_off.ensure(L * sizeof(long long)));
+    CUDA_TRY(h, cudaMemcpy(h->ring_off.p, roff.data(), L * sizeof(long long), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, h->status.ensure(16));
+
+    p.layer_img = (const float *)h->layer_img.p;
+    p.tail_img = (const float *)h->tail_img.p;
+    p.samp_img = (const float *)h->samp_img.p;
+    p.gc_table = (const float *)h->gc_table.p;
+    p.wc_onehot = (const float *)h->wc_onehot.p;
+    p.mb_x = (unsigned long long *)h->mbox.p;
+    p.mb_z = p.mb_x + n_x;
+    p.mb_acc = p.mb_z + n_z;
+    p.mb_c2 = p.mb_acc + n_acc;
+    p.ring = (float *)h->ring.p;
+    p.ring_off = (const long long *)h->ring_off.p;
+    p.status = (int32_t *)h->status.p;
+
+    h->smem_launch = std::max(h->smem_layer, std::max(h->smem_tail, h->smem_samp));
+    CUDA_TRY(h, cudaFuncSetAttribute(wn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
+    int occ = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel, WN_NT, h->smem_launch));
+    if ((long)occ * h->sm_count < grid) return fail(h, WN_ERR_CUDA, "cannot co-schedule %d CTAs (occupancy %d x %d SMs)", grid, occ, h->sm_count);
+
+    // ---- info ----------------------------------------------------------------------------------------------
+    wn_info &inf = h->info;
+    inf.grid = grid; inf.threads = WN_NT; inf.M = M; inf.Mt = Mt; inf.sm_count = h->sm_count;
+    inf.smem_bytes_layer = h->smem_layer; inf.smem_bytes_tail = h->smem_tail; inf.smem_bytes_sampler = h->smem_samp;
+    int64_t per_layer = 2LL * 2 * R * D + 2LL * D + 2LL * C * D + (int64_t)D * R + R + (int64_t)D * S + S;
+    int64_t causal = c.scalar_input ? (int64_t)ifw * R : 2LL * R;
+    inf.p_hot = per_layer * L + causal + (int64_t)S * S + S + (int64_t)S * O + O;
+    inf.weights_in_smem = ((int64_t)p.layer_smem_floats * L * M + (int64_t)p.tail_smem_floats * Mt + p.samp_smem_floats);
+    h->finalized = true;
+    return WN_OK;
+}
+
+int wn_get_plan(const wn_handle *h, wn_plan *plan)
+{
+    if (!h || !plan) return WN_ERR_ARG;
+    if (!h->finalized) return WN_ERR_STATE;
+    *plan = h->plan;
+    return WN_OK;
+}
+
+int wn_get_info(const wn_handle *h, wn_info *info)
+{
+    if (!h || !info) return WN_ERR_ARG;
+    if (!h->finalized) return WN_ERR_STATE;
+    *info = h->info;
+    info->kernel_launches = h->launches;
+    return WN_OK;
+}
+
+int wn_upsample(wn_handle *h, const float *mel_dev, int rows, int t_mel, float *out_dev, void *stream)
+{
+    if (!h) return WN_ERR_ARG;
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "wn_upsample before wn_finalize");
+    const wn_config &c = h->cfg;
+    if (!c.lc_channels || !c.n_upsample) return fail(h, WN_ERR_STATE, "model has no local-condition upsampling network");
+    if (!mel_dev || !out_dev || rows < 1 || t_mel < 1) return fail(h, WN_ERR_ARG, "wn_upsample: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = c.lc_channels;
+    long long rows_in = (long long)rows * t_mel;
+    size_t tmp_floats = 0;
+    {
+        long long r = rows_in;
+        for (int i = 0; i + 1 < c.n_upsample; ++i) { r *= c.upsample_factor[i]; tmp_floats = std::max<size_t>(tmp_floats, (size_t)r * C); }
+    }
+    if (tmp_floats) { CUDA_TRY(h, h->up_tmp0.ensure(tmp_floats * 4)); CUDA_TRY(h, h->up_tmp1.ensure(tmp_floats * 4)); }
+    const float *src = mel_dev;
+    for (int i = 0; i < c.n_upsample; ++i) {
+        const int F = c.upsample_factor[i];
+        float *dst = (i + 1 == c.n_upsample) ? out_dev : (float *)((i & 1) ? h->up_tmp1.p : h->up_tmp0.p);
+        long long total = rows_in * F * C;
+        int blocks = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+        wn_upsample_stage_kernel<<<blocks, 256, 0, st>>>(src, dst, (const float *)h->upk.p + h->up_off[i], rows_in, F, C);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches++;
+        src = dst;
+        rows_in *= F;
+    }
+    return WN_OK;
+}
+
+int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
+{
+    if (!h || !a) return WN_ERR_ARG;
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "wn_generate before wn_finalize");
+    const wn_config &c = h->cfg;
+    if (a->rows < 1 || a->rows > c.batch) return fail(h, WN_ERR_ARG, "rows=%d outside 1..batch_size=%d", a->rows, c.batch);
+    if (a->T < 0) return fail(h, WN_ERR_ARG, "T must be >= 0");
+    if (a->T == 0) return WN_OK;
+    if (a->n_forced < 1 || !a->forced_dev) return fail(h, WN_ERR_ARG, "n_forced must be >= 1 (forced[row][0] is the initial sample)");
+    if (!a->uniforms_dev || !a->out_samples_dev) return fail(h, WN_ERR_ARG, "uniforms_dev / out_samples_dev required");
+    if (c.gc_channels && !a->gc_ids) return fail(h, WN_ERR_ARG, "gc_ids required: the model is globally conditioned (generate.py:72-77)");
+    if (!c.scalar_input && !(a->temperature > 0.0f)) return fail(h, WN_ERR_ARG, "temperature must be > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    WnParams p = h->base;
+    p.N = a->rows;
+    p.T = a->T;
+    p.n_forced = a->n_forced;
+    p.t_lc = a->lc_dev ? a->t_lc : 0;
+    p.lc_shift = a->lc_shift;
+    p.temperature = a->temperature;
+    for (int b = 0; b < a->rows; ++b) {
+        int tr = a->T_row ? a->T_row[b] : a->T;
+        if (tr < 0 || tr > a->T) return fail(h, WN_ERR_ARG, "T_row[%d]=%d outside 0..T", b, tr);
+        p.T_row[b] = tr;
+        int gid = a->gc_ids ? a->gc_ids[b] : 0;
+        if (c.gc_channels && (gid < 0 || gid >= c.gc_cardinality)) return fail(h, WN_ERR_ARG, "gc_ids[%d]=%d outside 0..%d", b, gid, c.gc_cardinality - 1);
+        p.gc_id[b] = gid;
+    }
+    p.forced = a->forced_dev;
+    p.lc_up = c.lc_channels ? a->lc_dev : nullptr;
+    p.uniforms = a->uniforms_dev;
+    p.out_samples = a->out_samples_dev;
+    p.out_logits = a->out_logits_dev;
+    // The mailbox / ring strides were laid out for cfg.batch rows; a smaller `rows` only uses a prefix
+    // of each [N] dimension, so the kernel must index with the allocation's N.  Keep N = cfg.batch in
+    // the strides by running the kernel with N = batch and T_row = 0 for the unused rows.
+    p.N = c.batch;
+    for (int b = a->rows; b < c.batch; ++b) { p.T_row[b] = 0; p.gc_id[b] = 0; }
+
+    CUDA_TRY(h, cudaMemsetAsync(h->mbox.p, 0, h->mbox_bytes, st));
+    if (h->ring_bytes) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 16, st));
+    void *args[] = {&p};
+    CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)wn_persistent_kernel, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
+    h->launches++;
+    return WN_OK;
+}
+
+int wn_sync_check(wn_handle *h, void *stream)
+{
+    if (!h) return WN_ERR_ARG;
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "not finalized");
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+    int32_t st[4] = {0, 0, 0, 0};
+    CUDA_TRY(h, cudaMemcpy(st, h->status.p, 16, cudaMemcpyDeviceToHost));
+    if (st[0] != 0) return fail(h, WN_ERR_TIMEOUT, "persistent kernel aborted on its watchdog (CTA %d, thread %d)", st[1], st[2]);
+    return WN_OK;
+}
+
+int wn_generate_host(wn_handle *h, const wn_generate_args *a, const float *mel_host, int t_mel)
+{
+    if (!h || !a) return WN_ERR_ARG;
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "wn_generate_host before wn_finalize");
+    const wn_config &c = h->cfg;
+    const int rows = a->rows;
+    if (rows < 1 || rows > c.batch) return fail(h, WN_ERR_ARG, "rows=%d outside 1..batch_size=%d", rows, c.batch);
+    wn_generate_args d = *a;
+    int T = a->T;
+    cudaStream_t st = 0;
+    if (mel_host) {
+        if (!c.lc_channels || !c.n_upsample) return fail(h, WN_ERR_STATE, "mel given but the model has no local conditioning");
+        long f = 1;
+        for (int i = 0; i < c.n_upsample; ++i) f *= c.upsample_factor[i];
+        const int t_up = (int)(t_mel * f);
+        size_t mel_bytes = (size_t)rows * t_mel * c.lc_channels * 4;
+        CUDA_TRY(h, h->h_mel.ensure(mel_bytes));
+        CUDA_TRY(h, h->h_lc.ensure((size_t)rows * t_up * c.lc_channels * 4));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_mel.p, mel_host, mel_bytes, cudaMemcpyHostToDevice, st));
+        int rc = wn_upsample(h, (const float *)h->h_mel.p, rows, t_mel, (float *)h->h_lc.p, st);
+        if (rc) return rc;
+        d.lc_dev = (const float *)h->h_lc.p;
+        d.t_lc = t_up;
+    } else if (a->lc_dev) {
+        size_t b = (size_t)rows * a->t_lc * c.lc_channels * 4;
+        CUDA_TRY(h, h->h_lc.ensure(b));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_lc.p, a->lc_dev, b, cudaMemcpyHostToDevice, st));
+        d.lc_dev = (const float *)h->h_lc.p;
+    }
+    if (T < 1) return fail(h, WN_ERR_ARG, "T must be >= 1");
+    size_t fb = (size_t)rows * a->n_forced * 4;
+    size_t ub = c.scalar_input ? (size_t)rows * T * (h->out_dim / 3 + 1) * 4 : (size_t)rows * T * 8;
+    size_t ob = (size_t)rows * T * 4;
+    if (a->n_forced < 1 || !a->forced_dev || !a->uniforms_dev || !a->out_samples_dev) return fail(h, WN_ERR_ARG, "forced / uniforms / out_samples required");
+    CUDA_TRY(h, h->h_forced.ensure(fb));
+    CUDA_TRY(h, h->h_unif.ensure(ub));
+    CUDA_TRY(h, h->h_out.ensure(ob));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_forced.p, a->forced_dev, fb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_unif.p, a->uniforms_dev, ub, cudaMemcpyHostToDevice, st));
+    d.forced_dev = (const float *)h->h_forced.p;
+    d.uniforms_dev = h->h_unif.p;
+    d.out_samples_dev = (float *)h->h_out.p;
+    if (a->out_logits_dev) {
+        CUDA_TRY(h, h->h_logits.ensure(ob * h->out_dim));
+        d.out_logits_dev = (float *)h->h_logits.p;
+    }
+    int rc = wn_generate(h, &d, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(a->out_samples_dev, h->h_out.p, ob, cudaMemcpyDeviceToHost, st));
+    if (a->out_logits_dev) CUDA_TRY(h, cudaMemcpyAsync(a->out_logits_dev, h->h_logits.p, ob * h->out_dim, cudaMemcpyDeviceToHost, st));
+    return wn_sync_check(h, st);
+}
+
+int wn_mu_law_encode(const float *audio_dev, int64_t n, int quantization_channels, int32_t *out_dev, void *stream)
+{
+    if (!audio_dev || !out_dev || n < 0) return WN_ERR_ARG;
+    if (n == 0) return WN_OK;
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    wn_mu_law_encode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(audio_dev, n, (float)(quantization_channels - 1), out_dev);
+    return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+
+int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, int quantization, float *out_dev, void *stream)
+{
+    if (!in_dev || !out_dev || n < 0) return WN_ERR_ARG;
+    if (n == 0) return WN_OK;
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    wn_mu_law_decode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_dev, n, (float)(quantization_channels - 1), quantization, out_dev);
+    return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// wn_params.h -- structures shared by the host API (wn_api.cu) and the device code (wn_kernel.cu).
+#pragma once
+#include <stdint.h>
+#include "../../include/wn_b200.h"
+
+#define WN_NT 256                 // threads per CTA (8 warps), every role
+
+// A matrix packed "thread-major" for one CTA: ncols dot products of length K.
+// Thread tid handles column (pass*gpp + tid/t) and the contiguous k-chunk (tid % t) of length ch = K/t.
+// Packed layout (V = 4):  w[((pass*(ch/4) + i4)*WN_NT + tid)*4 + j] = W[chunk*ch + 4*i4 + j][col]
+//               (V = 1):  w[(pass*ch + i)*WN_NT + tid]              = W[chunk*ch + i][col]
+// so that every warp-wide load is one fully coalesced, bank-conflict-free 512 B / 128 B access.
+// The input vector is kept in shared memory with chunk c starting at c*xstride (xstride >= ch chosen
+// so the t chunk starts fall in distinct banks).
+struct WnMat {
+    int32_t off;        // float offset of the packed matrix inside the CTA image
+    int32_t K, ncols;
+    int32_t t, ch, V;
+    int32_t gpp;        // column groups per pass = WN_NT / t
+    int32_t npass;
+    int32_t xstride;
+    int32_t xlen;       // t * xstride: floats of the padded input vector
+    int32_t in_smem;    // 1: resident in shared memory, 0: read from the global image (overflow)
+    int32_t pad_;
+};
+
+// Shared-memory float offsets of the per-role scratch vectors (after the resident image prefix).
+struct WnLayerSmem {
+    int32_t xs_cur, xs_old, lcs, xraw, zs_dense, zs_skip, gvec, bfgN, pre, total_floats;
+};
+struct WnTailSmem {
+    int32_t as1, c1s, total_floats;
+};
+struct WnSamplerSmem {
+    int32_t c2s, cq, cqx, ids, qs, cdf /* doubles, 8B aligned */, red, misc, total_floats;
+};
+
+struct WnParams {
+    // model dims
+    int32_t N, L, R, D, S, O, Q, G, C, ifw, scalar_input, nr_mix;
+    // topology
+    int32_t M, Mt, Dm, Sm, St;           // Dm = D/M, Sm = S/M, St = S/Mt
+    int32_t grid;
+    // run
+    int32_t T, n_forced, t_lc, lc_shift;
+    float temperature;
+    int32_t T_row[WN_MAX_BATCH];
+    int32_t gc_id[WN_MAX_BATCH];
+    int32_t dil[WN_MAX_LAYERS];
+    // layer CTA image
+    WnMat cur, old, lc, gc, dense, skip;
+    int32_t off_bfg, off_bd, off_bs;
+    int32_t layer_img_floats, layer_smem_floats;   // image size (stride) and resident prefix
+    WnLayerSmem ls;
+    // tail CTA image
+    WnMat post1, post2;
+    int32_t off_b1;
+    int32_t tail_img_floats, tail_smem_floats;
+    WnTailSmem ts;
+    // sampler CTA image
+    WnMat causal;
+    int32_t off_b2;
+    int32_t samp_img_floats, samp_smem_floats;
+    WnSamplerSmem ss;
+    // device pointers
+    const float *layer_img, *tail_img, *samp_img;
+    const float *gc_table;         // (card, G)
+    const float *wc_onehot;        // (2, Q, R) causal kernel for one-hot input, read by row
+    unsigned long long *mb_x;      // [N][L][M][R]    partial inputs of layer l
+    unsigned long long *mb_z;      // [N][L][M][Dm]   gated activations, exchanged between the M siblings
+    unsigned long long *mb_acc;    // [N][L][M][Sm]   running skip sum after layer l
+    unsigned long long *mb_c2;     // [N][Mt][O]      partial conv2 outputs
+    float *ring;                   // private dilation-queue rings
+    const long long *ring_off;     // [L] float offset of layer l's ring block; block = [M][N][d][R]
+    const float *forced;
+    const float *lc_up;
+    const void *uniforms;
+    float *out_samples;
+    float *out_logits;
+    int32_t *status;               // [0] abort flag, [1] cta that raised it, [2] code
+};

@@ -1,0 +1,278 @@
+"""WaveNetModel with the reference's construction signature (wavenet/model.py:8-10) whose
+generation path runs as one persistent sm_100a kernel through libwn_b200.so.
+
+Tensors are torch CUDA tensors; weights are exchanged as a dict keyed by the reference's TF
+variable names.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class WaveNetModel(object):
+    def __init__(self, batch_size, dilations, filter_width, residual_channels, dilation_channels, skip_channels,
+                 quantization_channels=2 ** 8, out_channels=30, use_biases=False, scalar_input=False,
+                 initial_filter_width=32, global_condition_channels=None, global_condition_cardinality=None,
+                 local_condition_channels=80, upsample_factor=None, train_mode=True, device=None,
+                 force_M=0, force_Mt=0):
+        self.batch_size = batch_size
+        self.dilations = list(dilations)
+        self.filter_width = filter_width
+        self.residual_channels = residual_channels
+        self.dilation_channels = dilation_channels
+        self.quantization_channels = quantization_channels
+        self.use_biases = use_biases
+        self.skip_channels = skip_channels
+        self.scalar_input = scalar_input
+        self.initial_filter_width = initial_filter_width
+        self.global_condition_channels = global_condition_channels
+        self.global_condition_cardinality = global_condition_cardinality
+        self.local_condition_channels = local_condition_channels
+        self.upsample_factor = list(upsample_factor) if upsample_factor else None
+        self.train_mode = train_mode
+        self.receptive_field = WaveNetModel.calculate_receptive_field(
+            self.filter_width, self.dilations, self.scalar_input, self.initial_filter_width)
+        self.out_channels = out_channels
+        self.out_dim = out_channels if scalar_input else quantization_channels
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
+            if torch.cuda.is_available() else None
+
+        cfg = _lib.WnConfig()
+        cfg.batch = batch_size
+        cfg.n_layers = len(self.dilations)
+        cfg.filter_width = filter_width
+        cfg.residual_channels = residual_channels
+        cfg.dilation_channels = dilation_channels
+        cfg.skip_channels = skip_channels
+        cfg.quantization_channels = quantization_channels
+        cfg.out_channels = out_channels
+        cfg.use_biases = int(bool(use_biases))
+        cfg.scalar_input = int(bool(scalar_input))
+        cfg.initial_filter_width = initial_filter_width
+        cfg.gc_channels = global_condition_channels or 0
+        cfg.gc_cardinality = global_condition_cardinality or 0
+        cfg.lc_channels = local_condition_channels or 0
+        uf = self.upsample_factor or []
+        cfg.n_upsample = len(uf)
+        if len(uf) > _lib.WN_MAX_UPSAMPLE or len(self.dilations) > _lib.WN_MAX_LAYERS:
+            raise ValueError("too many upsample stages / layers")
+        for i, f in enumerate(uf):
+            cfg.upsample_factor[i] = f
+        for i, d in enumerate(self.dilations):
+            cfg.dilations[i] = d
+        cfg.force_M = force_M
+        cfg.force_Mt = force_Mt
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        rc = _lib.lib().wn_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise ValueError(_lib.lib().wn_last_error(None).decode())
+        self._finalized = False
+        self._inc = None            # state of the eager predict_proba_incremental emulation
+        # attribute the reference's generate.py runs through sess.run before the loop (generate.py:163);
+        # the kernel zeroes its queues at every launch, so this is a no-op kept for drop-in callers.
+        self.queue_initializer = lambda: None
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().wn_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def _err(self):
+        return _lib.lib().wn_last_error(self._h).decode()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("libwn_b200: %s (code %d)" % (self._err(), rc))
+
+    def _dev_guard(self):
+        if self.device is None or not torch.cuda.is_available():
+            raise RuntimeError("no CUDA device: the B200 WaveNet path has no CPU fallback")
+        return torch.cuda.device(self.device)
+
+    @staticmethod
+    def calculate_receptive_field(filter_width, dilations, scalar_input, initial_filter_width):
+        """wavenet/model.py:31-39."""
+        d = np.ascontiguousarray(dilations, dtype=np.int32)
+        return int(_lib.lib().wn_receptive_field(filter_width, d.ctypes.data_as(C.c_void_p), len(d),
+                                                 int(bool(scalar_input)), initial_filter_width))
+
+    def load_state_dict(self, state):
+        """Restore of the non-queue variables (generate.py:157-161): {tf_variable_name: array}."""
+        with self._dev_guard():
+            for name, arr in state.items():
+                if 'queue' in name or 'ExponentialMovingAverage' in name or name.startswith('optimizer'):
+                    continue       # generate.py:157 restores only the raw, non-queue variables
+                a = np.ascontiguousarray(arr.detach().cpu().numpy() if isinstance(arr, torch.Tensor) else arr,
+                                         dtype=np.float32)
+                self._check(_lib.lib().wn_set_weight(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+            self._check(_lib.lib().wn_finalize(self._h))
+        self._finalized = True
+        return self
+
+    def plan(self):
+        p = _lib.WnPlan()
+        self._check(_lib.lib().wn_get_plan(self._h, C.byref(p)))
+        return p.as_dict()
+
+    def info(self):
+        i = _lib.WnInfo()
+        self._check(_lib.lib().wn_get_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ reference methods
+    def create_upsample(self, local_condition_batch):
+        """wavenet/model.py:102-111: (N, T_mel, C) -> (N, T_mel*prod(upsample_factor), C)."""
+        with self._dev_guard():
+            mel = torch.as_tensor(local_condition_batch, dtype=torch.float32, device=self.device).contiguous()
+            n, tm, c = mel.shape
+            f = int(np.prod(self.upsample_factor))
+            out = torch.empty((n, tm * f, c), dtype=torch.float32, device=self.device)
+            self._check(_lib.lib().wn_upsample(self._h, C.c_void_p(mel.data_ptr()), n, tm,
+                                               C.c_void_p(out.data_ptr()), self._stream()))
+            return out
+
+    def generate(self, T, forced, uniforms, lc_up=None, lc_shift=0, gc_ids=None, temperature=1.0,
+                 want_logits=False, T_row=None, sync=True):
+        """The fused generate.py:202-233 loop.  All tensor arguments live on the GPU (moved if not).
+
+        forced   (rows, n_forced>=1): x_in(t) for t < n_forced; afterwards the drawn sample feeds back.
+        uniforms (rows, T, nr_mix+1) fp32 [scalar input] or (rows, T) fp64 [mu-law].
+        lc_up    (rows, T_lc, C) upsampled local condition or None; lc_shift as in include/wn_b200.h.
+        Returns samples (rows, T) fp32 [and logits (rows, T, out_dim)]."""
+        if not self._finalized:
+            raise RuntimeError("load_state_dict() must be called before generate()")
+        with self._dev_guard():
+            dev = self.device
+            forced = torch.as_tensor(forced, dtype=torch.float32, device=dev)
+            rows = forced.shape[0]
+            forced = forced.reshape(rows, -1).contiguous()
+            if self.scalar_input:
+                uniforms = torch.as_tensor(uniforms, dtype=torch.float32, device=dev).contiguous()
+                if tuple(uniforms.shape) != (rows, T, self.out_channels // 3 + 1):
+                    raise ValueError("uniforms must be (rows, T, %d)" % (self.out_channels // 3 + 1))
+            else:
+                uniforms = torch.as_tensor(uniforms, dtype=torch.float64, device=dev).contiguous()
+                if tuple(uniforms.shape) != (rows, T):
+                    raise ValueError("uniforms must be (rows, T) float64")
+            a = _lib.WnGenerateArgs()
+            a.rows, a.T, a.n_forced = rows, int(T), forced.shape[1]
+            a.forced_dev = forced.data_ptr()
+            keep = [forced, uniforms]
+            if lc_up is not None:
+                lc_up = torch.as_tensor(lc_up, dtype=torch.float32, device=dev).contiguous()
+                a.lc_dev, a.t_lc = lc_up.data_ptr(), lc_up.shape[1]
+                keep.append(lc_up)
+            a.lc_shift = int(lc_shift)
+            if gc_ids is not None:
+                g = (C.c_int32 * rows)(*[int(v) for v in gc_ids])
+                a.gc_ids = C.cast(g, C.POINTER(C.c_int32))
+                keep.append(g)
+            if T_row is not None:
+                tr = (C.c_int32 * rows)(*[int(v) for v in T_row])
+                a.T_row = C.cast(tr, C.POINTER(C.c_int32))
+                keep.append(tr)
+            a.uniforms_dev = uniforms.data_ptr()
+            a.temperature = float(temperature)
+            out = torch.empty((rows, T), dtype=torch.float32, device=dev)
+            a.out_samples_dev = out.data_ptr()
+            logits = None
+            if want_logits:
+                logits = torch.empty((rows, T, self.out_dim), dtype=torch.float32, device=dev)
+                a.out_logits_dev = logits.data_ptr()
+            self._check(_lib.lib().wn_generate(self._h, C.byref(a), self._stream()))
+            if sync:
+                self._check(_lib.lib().wn_sync_check(self._h, self._stream()))
+            self._keep = keep
+            return (out, logits) if want_logits else out
+
+    def sync_check(self):
+        self._check(_lib.lib().wn_sync_check(self._h, self._stream()))
+
+    def generate_host(self, T, forced, uniforms, mel=None, lc_shift=0, gc_ids=None, temperature=1.0):
+        """Host-buffer entry point (wn_generate_host): numpy in, numpy out, copies inside."""
+        if not self._finalized:
+            raise RuntimeError("load_state_dict() must be called before generate_host()")
+        with self._dev_guard():
+            forced = np.ascontiguousarray(forced, dtype=np.float32)
+            rows = forced.shape[0]
+            forced = forced.reshape(rows, -1)
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float32 if self.scalar_input else np.float64)
+            a = _lib.WnGenerateArgs()
+            a.rows, a.T, a.n_forced = rows, int(T), forced.shape[1]
+            a.forced_dev = forced.ctypes.data
+            a.lc_shift = int(lc_shift)
+            g = None
+            if gc_ids is not None:
+                g = (C.c_int32 * rows)(*[int(v) for v in gc_ids])
+                a.gc_ids = C.cast(g, C.POINTER(C.c_int32))
+            a.uniforms_dev = uniforms.ctypes.data
+            a.temperature = float(temperature)
+            out = np.empty((rows, T), np.float32)
+            a.out_samples_dev = out.ctypes.data
+            mel_p, t_mel = None, 0
+            if mel is not None:
+                mel = np.ascontiguousarray(mel, dtype=np.float32)
+                mel_p, t_mel = mel.ctypes.data_as(C.c_void_p), mel.shape[1]
+            self._check(_lib.lib().wn_generate_host(self._h, C.byref(a), mel_p, t_mel))
+            return out
+
+    def predict_proba_incremental(self, waveform, upsampled_local_condition=None, global_condition=None,
+                                  name='wavenet', uniforms=None):
+        """Eager stand-in for the graph node of wavenet/model.py:215-245: feed ONE step, get the
+        softmax probabilities (N, Q) or, for scalar input, a sample (N, 1).
+
+        The reference evaluates this node once per audio sample through sess.run, with the queues as
+        TF variables.  Here the state is the history of fed inputs: every call replays the history
+        teacher-forced through the persistent kernel and returns the last step, which is O(T^2) and
+        meant for checking/short runs only -- `generate()` is the fused production path."""
+        dev = self.device
+        w = torch.as_tensor(waveform, dtype=torch.float32, device=dev).reshape(self.batch_size, -1)[:, -1:]
+        if self._inc is None:
+            self._inc = {"x": [], "lc": [], "u": []}
+        st = self._inc
+        st["x"].append(w)
+        if self.local_condition_channels:
+            if upsampled_local_condition is None:
+                raise ValueError("upsampled_local_condition is required (model.py:125)")
+            st["lc"].append(torch.as_tensor(upsampled_local_condition, dtype=torch.float32, device=dev)
+                            .reshape(self.batch_size, 1, self.local_condition_channels))
+        T = len(st["x"])
+        nr1 = self.out_channels // 3 + 1
+        if self.scalar_input:
+            u = uniforms if uniforms is not None else torch.empty(self.batch_size, 1, nr1, device=dev).uniform_(1e-5, 1 - 1e-5)
+            st["u"].append(torch.as_tensor(u, dtype=torch.float32, device=dev).reshape(self.batch_size, 1, nr1))
+            uni = torch.cat(st["u"], dim=1)
+        else:
+            uni = torch.full((self.batch_size, T), 0.5, dtype=torch.float64, device=dev)
+        lc = torch.cat(st["lc"], dim=1) if st["lc"] else None
+        gc = None
+        if self.global_condition_channels:
+            gc = [int(v) for v in (global_condition if global_condition is not None else [0] * self.batch_size)]
+        samples, logits = self.generate(T, torch.cat(st["x"], dim=1), uni, lc_up=lc, lc_shift=0, gc_ids=gc,
+                                        want_logits=True)
+        if self.scalar_input:
+            return samples[:, -1:]
+        return torch.softmax(logits[:, -1, :].to(torch.float64), dim=-1).to(torch.float32)
+
+    def reset_incremental(self):
+        """Counterpart of sess.run(net.queue_initializer), generate.py:163."""
+        self._inc = None
+
+    def add_loss(self, *_a, **_k):
+        raise NotImplementedError("training (wavenet/model.py:247-312) is outside the generation hot path "
+                                  "(SURVEY.md section 8f, next-3)")
+
+    def add_optimizer(self, *_a, **_k):
+        raise NotImplementedError("training (wavenet/model.py:314-346) is outside the generation hot path "
+                                  "(SURVEY.md section 8f, next-3)")
