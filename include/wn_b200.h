@@ -90,6 +90,10 @@ int wn_set_weight(wn_handle *h, const char *name, const float *data, int64_t n);
  * wn_set_weight and precede any compute call. */
 int wn_finalize(wn_handle *h);
 
+/* Topology / evaluation plan / shared-memory budget the library would choose for `cfg` on a device with
+ * sm_count SMs (0 = 148, a B200).  Pure host function: no device needed. */
+int wn_plan_config(const wn_config *cfg, int sm_count, wn_plan *plan, wn_info *info);
+
 int wn_get_plan(const wn_handle *h, wn_plan *plan);
 int wn_get_info(const wn_handle *h, wn_info *info);
 

@@ -28,7 +28,7 @@
  *
  * Floating point evaluation order.  TF/Eigen's summation order inside conv1d is
  * not specified, so any order is an equally faithful restatement.  Every dot
- * product here goes through dot_plan(), whose order is selected by an orc_plan:
+ * product here goes through mv_plan(), whose order is selected by an orc_plan:
  * plan = all ones is the natural left-to-right order; a device kernel that wants
  * bit-exact comparison reports the plan it implements and the test passes it in.
  */
@@ -37,6 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <pthread.h>
 #include "wn_math_ref.h"
 
 #define ORC_MAX_LAYERS 256
@@ -62,7 +63,7 @@ typedef struct {
     int32_t dilations[ORC_MAX_LAYERS];
 } orc_config;
 
-/* Evaluation-order plan, see dot_plan(). */
+/* Evaluation-order plan, see mv_plan(). */
 typedef struct {
     int32_t M;         /* dense (residual 1x1): K=D cut in M slices added in order   */
     int32_t Mt;        /* post2: K=S cut in Mt slices added in order                 */
@@ -99,27 +100,33 @@ typedef struct {
 } orc_model;
 
 /* ------------------------------------------------------------------------- */
-/* dot_plan: sum_k w[k*stride]*x[k], k<K, evaluated as t contiguous chunks of
- * K/t; each chunk is an fma chain in increasing k starting from +0; the t
- * chunk sums are combined by an xor-butterfly with ascending offsets
- * (1,2,4,...,t/2):  a[c] = a[c] + a[c^off].  t must be a power of two dividing K. */
-static float dot_plan(const float *w, int stride, const float *x, int K, int t)
+/* mv_plan: out[o] = sum_k W[k*stride + o] * x[k] for o < ncols, k < K.  Every column is evaluated
+ * as t contiguous chunks of K/t; each chunk is an fma chain in increasing k starting from +0; the t
+ * chunk sums are combined by an xor-butterfly with ascending offsets (1,2,4,...,t/2):
+ * a[c] = a[c] + a[c^off].  t must be a power of two dividing K.  The loops run k-outer / column-inner
+ * so the compiler can vectorise across columns; each column's operation sequence is unchanged.
+ * scratch: t*ncols floats. */
+static void mv_plan(const float *W, int stride, int ncols, const float *x, int K, int t, float *out, float *scratch)
 {
-    float a[64];
     int ch = K / t;
     for (int c = 0; c < t; ++c) {
-        float s = 0.0f;
-        const float *wp = w + (size_t)c * ch * stride;
-        const float *xp = x + c * ch;
-        for (int i = 0; i < ch; ++i) s = fmaf(wp[(size_t)i * stride], xp[i], s);
-        a[c] = s;
+        float *restrict a = scratch + (size_t)c * ncols;
+        for (int o = 0; o < ncols; ++o) a[o] = 0.0f;
+        for (int i = 0; i < ch; ++i) {
+            int k = c * ch + i;
+            const float xk = x[k];
+            const float *restrict w = W + (size_t)k * stride;
+            for (int o = 0; o < ncols; ++o) a[o] = fmaf(w[o], xk, a[o]);
+        }
     }
-    for (int off = 1; off < t; off <<= 1) {
-        float b[64];
-        for (int c = 0; c < t; ++c) b[c] = a[c] + a[c ^ off];
-        memcpy(a, b, sizeof(float) * t);
-    }
-    return a[0];
+    for (int off = 1; off < t; off <<= 1)
+        for (int c = 0; c < t; ++c)
+            if ((c & off) == 0) {
+                float *restrict a = scratch + (size_t)c * ncols;
+                float *restrict b = scratch + (size_t)(c ^ off) * ncols;
+                for (int o = 0; o < ncols; ++o) { float v = a[o] + b[o]; a[o] = v; b[o] = v; }
+            }
+    for (int o = 0; o < ncols; ++o) out[o] = scratch[o];
 }
 
 /* ascending xor-butterfly sum of n (power of two) doubles; used for the softmax
@@ -398,6 +405,166 @@ static int mulaw_draw(const float *c2, int Q, float temperature, double u, float
     return cnt;
 }
 
+typedef struct {
+    orc_model *m; orc_plan p; int T, n_forced; const float *forced; const float *lc_up; int t_lc, lc_shift;
+    const int32_t *gc_ids; const void *uniforms; float temperature; float *out_samples, *out_logits;
+    int next_row; pthread_mutex_t mu;
+} gen_ctx;
+
+static void run_row(gen_ctx *g_, int b)
+{
+    orc_model *m = g_->m;
+    const orc_config *c = &m->cfg;
+    const orc_plan p = g_->p;
+    const int L = c->n_layers, R = c->residual_channels, D = c->dilation_channels;
+    const int S = c->skip_channels, G = c->gc_channels, C = c->lc_channels, O = m->out_dim;
+    const int ifw = c->initial_filter_width, Q = c->quantization_channels;
+    const int T = g_->T, n_forced = g_->n_forced, t_lc = g_->t_lc, lc_shift = g_->lc_shift;
+    const float *forced = g_->forced, *lc_up = g_->lc_up;
+    const int32_t *gc_ids = g_->gc_ids;
+    const void *uniforms = g_->uniforms;
+    const float temperature = g_->temperature;
+    float *out_samples = g_->out_samples, *out_logits = g_->out_logits;
+    const int nr_mix = O / 3;
+    int maxc = S; if (D > maxc) maxc = D; if (R > maxc) maxc = R; if (O > maxc) maxc = O;
+    {
+        float *x = (float *)malloc(sizeof(float) * R), *xn = (float *)malloc(sizeof(float) * R);
+        float *z = (float *)malloc(sizeof(float) * D);
+        float *f = (float *)malloc(sizeof(float) * D), *g = (float *)malloc(sizeof(float) * D);
+        float *acc = (float *)malloc(sizeof(float) * S), *c1 = (float *)malloc(sizeof(float) * S);
+        float *c2 = (float *)malloc(sizeof(float) * O);
+        float *tmp = (float *)malloc(sizeof(float) * maxc);
+        float *scratch = (float *)malloc(sizeof(float) * 64 * (size_t)maxc);
+        float *gvec = (float *)calloc(G ? G : 1, sizeof(float));
+        float *zero_lc = (float *)calloc(C ? C : 1, sizeof(float));
+        row_state st;
+        st.cq = (float *)calloc(ifw, sizeof(float));
+        st.id_prev = -1; st.id_cur = -1;        /* zero one-hot rows (queue_initializer) */
+        st.lc_prev = (float *)calloc(C ? C : 1, sizeof(float));
+        st.ring = (float **)malloc(sizeof(float *) * L);
+        for (int l = 0; l < L; ++l) st.ring[l] = (float *)calloc((size_t)c->dilations[l] * R, sizeof(float));
+        st.biasf = (float *)malloc(sizeof(float) * L * D);
+        st.biasg = (float *)malloc(sizeof(float) * L * D);
+        if (G) memcpy(gvec, m->gc_table + (size_t)gc_ids[b] * G, sizeof(float) * G);
+        for (int l = 0; l < L; ++l) {
+            /* global conditioning is constant per row: fold it into the biases once (model.py:71-73) */
+            for (int o = 0; o < D; ++o) { st.biasf[l * D + o] = m->layers[l].bf[o]; st.biasg[l * D + o] = m->layers[l].bg[o]; }
+            if (G) {
+                mv_plan(m->layers[l].gcf, D, D, gvec, G, p.t_gc, tmp, scratch);
+                for (int o = 0; o < D; ++o) st.biasf[l * D + o] = st.biasf[l * D + o] + tmp[o];
+                mv_plan(m->layers[l].gcg, D, D, gvec, G, p.t_gc, tmp, scratch);
+                for (int o = 0; o < D; ++o) st.biasg[l * D + o] = st.biasg[l * D + o] + tmp[o];
+            }
+        }
+
+        float prev_sample = 0.0f;
+        for (int t = 0; t < T; ++t) {
+            float x_in = (t < n_forced) ? forced[(size_t)b * n_forced + t] : prev_sample;
+            /* --- causal queue + causal conv (model.py:122,131) --- */
+            if (c->scalar_input) {
+                memmove(st.cq, st.cq + 1, sizeof(float) * (ifw - 1));
+                st.cq[ifw - 1] = x_in;
+                mv_plan(m->wc, R, R, st.cq, ifw, p.t_causal, x, scratch);
+            } else {
+                st.id_prev = st.id_cur;
+                st.id_cur = (int)x_in;
+                for (int r = 0; r < R; ++r) {
+                    float a = (st.id_prev >= 0) ? m->wc[((size_t)0 * Q + st.id_prev) * R + r] : 0.0f;
+                    float bb = (st.id_cur >= 0 && st.id_cur < Q) ? m->wc[((size_t)1 * Q + st.id_cur) * R + r] : 0.0f;
+                    x[r] = a + bb;
+                }
+            }
+            const float *lc_use = st.lc_prev;     /* lq[0] */
+            /* --- dilated stack (model.py:141-149, 66-101) --- */
+            for (int l = 0; l < L; ++l) {
+                const orc_layer *ly = &m->layers[l];
+                int d = c->dilations[l];
+                float *slot = st.ring[l] + (size_t)(t % d) * R;   /* holds x_l(t-d) */
+                /* f = ((bias(+gc) + W0.old) (+ Wlc.lc)) + W1.cur, same for g (model.py:68-83) */
+                memcpy(f, st.biasf + l * D, sizeof(float) * D);
+                memcpy(g, st.biasg + l * D, sizeof(float) * D);
+                mv_plan(ly->wf, D, D, slot, R, p.t_old, tmp, scratch);
+                for (int o = 0; o < D; ++o) f[o] = f[o] + tmp[o];
+                mv_plan(ly->wg, D, D, slot, R, p.t_old, tmp, scratch);
+                for (int o = 0; o < D; ++o) g[o] = g[o] + tmp[o];
+                if (C) {
+                    mv_plan(ly->lcf, D, D, lc_use, C, p.t_lc, tmp, scratch);
+                    for (int o = 0; o < D; ++o) f[o] = f[o] + tmp[o];
+                    mv_plan(ly->lcg, D, D, lc_use, C, p.t_lc, tmp, scratch);
+                    for (int o = 0; o < D; ++o) g[o] = g[o] + tmp[o];
+                }
+                mv_plan(ly->wf + (size_t)R * D, D, D, x, R, p.t_cur, tmp, scratch);
+                for (int o = 0; o < D; ++o) f[o] = f[o] + tmp[o];
+                mv_plan(ly->wg + (size_t)R * D, D, D, x, R, p.t_cur, tmp, scratch);
+                for (int o = 0; o < D; ++o) g[o] = g[o] + tmp[o];
+                for (int o = 0; o < D; ++o) z[o] = orc_tanh32(f[o]) * orc_sigmoid32(g[o]);   /* model.py:86 */
+                memcpy(slot, x, sizeof(float) * R);                /* queue push, model.py:145 */
+                mv_plan(ly->ws, S, S, z, D, p.t_skip, tmp, scratch);
+                for (int s = 0; s < S; ++s) {
+                    float v = ly->bs[s] + tmp[s];
+                    acc[s] = (l == 0) ? v : acc[s] + v;             /* sum(outputs), model.py:157 */
+                }
+                int dm = D / p.M;
+                for (int r = 0; r < R; ++r) xn[r] = x[r] + ly->bd[r];
+                for (int mm = 0; mm < p.M; ++mm) {
+                    mv_plan(ly->wd + (size_t)mm * dm * R, R, R, z + mm * dm, dm, p.t_dense, tmp, scratch);
+                    for (int r = 0; r < R; ++r) xn[r] = xn[r] + tmp[r];
+                }
+                memcpy(x, xn, sizeof(float) * R);
+            }
+            /* --- postprocessing (model.py:150-165) --- */
+            for (int s = 0; s < S; ++s) acc[s] = relu32(acc[s]);
+            mv_plan(m->w1, S, S, acc, S, p.t_post1, tmp, scratch);
+            for (int s = 0; s < S; ++s) c1[s] = relu32(m->b1[s] + tmp[s]);
+            int sm = S / p.Mt;
+            for (int o = 0; o < O; ++o) c2[o] = m->b2[o];
+            for (int mm = 0; mm < p.Mt; ++mm) {
+                mv_plan(m->w2 + (size_t)mm * sm * O, O, O, c1 + mm * sm, sm, p.t_post2, tmp, scratch);
+                for (int o = 0; o < O; ++o) c2[o] = c2[o] + tmp[o];
+            }
+            if (out_logits) memcpy(out_logits + ((size_t)b * T + t) * O, c2, sizeof(float) * O);
+            /* --- head + draw --- */
+            float sample;
+            if (c->scalar_input) {
+                const float *u = (const float *)uniforms + ((size_t)b * T + t) * (nr_mix + 1);
+                sample = mol_draw(c2, nr_mix, u);
+            } else {
+                double u = ((const double *)uniforms)[(size_t)b * T + t];
+                sample = (float)mulaw_draw(c2, Q, temperature, u, NULL);
+            }
+            out_samples[(size_t)b * T + t] = sample;
+            prev_sample = sample;
+            /* --- lc queue push (model.py:125): the row for this step becomes lq[0] next step --- */
+            if (C) {
+                long idx = (long)t - lc_shift;
+                const float *row = (lc_up && idx >= 0 && idx < t_lc) ? lc_up + ((size_t)b * t_lc + idx) * C : zero_lc;
+                memcpy(st.lc_prev, row, sizeof(float) * C);
+            }
+        }
+        for (int l = 0; l < L; ++l) free(st.ring[l]);
+        free(st.ring); free(st.cq); free(st.lc_prev); free(st.biasf); free(st.biasg);
+        free(x); free(xn); free(z); free(f); free(g); free(acc); free(c1); free(c2); free(tmp); free(scratch);
+        free(gvec); free(zero_lc);
+    }
+}
+
+static void *row_worker(void *arg)
+{
+    gen_ctx *g_ = (gen_ctx *)arg;
+    for (;;) {
+        pthread_mutex_lock(&g_->mu);
+        int b = g_->next_row++;
+        pthread_mutex_unlock(&g_->mu);
+        if (b >= g_->m->cfg.batch) break;
+        run_row(g_, b);
+    }
+    return NULL;
+}
+
+static int g_threads = 1;
+/* number of host threads orc_generate spreads the (independent) batch rows over */
+void orc_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
 /* One generate.py-style run for the whole batch.
  *   T            number of network steps per row
  *   n_forced     x_in(t) = forced[b][t] for t < n_forced, else the sample drawn at t-1.
@@ -425,117 +592,23 @@ int orc_generate(orc_model *m, const orc_plan *plan, int T, int n_forced, const 
     if (!is_pow2(p.M) || D % p.M || !is_pow2(p.Mt) || S % p.Mt) { snprintf(m->err, sizeof m->err, "bad plan M/Mt"); return -1; }
     if (n_forced < 1) { snprintf(m->err, sizeof m->err, "n_forced must be >= 1"); return -1; }
     if (!c->scalar_input && !is_pow2(Q)) { snprintf(m->err, sizeof m->err, "Q must be a power of two"); return -1; }
-    const int nr_mix = O / 3;
 
-    float *x = (float *)malloc(sizeof(float) * R), *xn = (float *)malloc(sizeof(float) * R);
-    float *z = (float *)malloc(sizeof(float) * D);
-    float *acc = (float *)malloc(sizeof(float) * S), *c1 = (float *)malloc(sizeof(float) * S);
-    float *c2 = (float *)malloc(sizeof(float) * O);
-    float *gvec = (float *)calloc(G ? G : 1, sizeof(float));
-    float *zero_lc = (float *)calloc(C ? C : 1, sizeof(float));
-
-    for (int b = 0; b < N; ++b) {
-        row_state st;
-        st.cq = (float *)calloc(ifw, sizeof(float));
-        st.id_prev = -1; st.id_cur = -1;        /* zero one-hot rows (queue_initializer) */
-        st.lc_prev = (float *)calloc(C ? C : 1, sizeof(float));
-        st.ring = (float **)malloc(sizeof(float *) * L);
-        for (int l = 0; l < L; ++l) st.ring[l] = (float *)calloc((size_t)c->dilations[l] * R, sizeof(float));
-        st.biasf = (float *)malloc(sizeof(float) * L * D);
-        st.biasg = (float *)malloc(sizeof(float) * L * D);
-        if (G) memcpy(gvec, m->gc_table + (size_t)gc_ids[b] * G, sizeof(float) * G);
-        for (int l = 0; l < L; ++l)
-            for (int o = 0; o < D; ++o) {
-                float bf = m->layers[l].bf[o], bg = m->layers[l].bg[o];
-                if (G) {
-                    bf = bf + dot_plan(m->layers[l].gcf + o, D, gvec, G, p.t_gc);
-                    bg = bg + dot_plan(m->layers[l].gcg + o, D, gvec, G, p.t_gc);
-                }
-                st.biasf[l * D + o] = bf; st.biasg[l * D + o] = bg;
-            }
-
-        float prev_sample = 0.0f;
-        for (int t = 0; t < T; ++t) {
-            float x_in = (t < n_forced) ? forced[(size_t)b * n_forced + t] : prev_sample;
-            /* --- causal queue + causal conv (model.py:122,131) --- */
-            if (c->scalar_input) {
-                memmove(st.cq, st.cq + 1, sizeof(float) * (ifw - 1));
-                st.cq[ifw - 1] = x_in;
-                for (int r = 0; r < R; ++r) x[r] = dot_plan(m->wc + r, R, st.cq, ifw, p.t_causal);
-            } else {
-                st.id_prev = st.id_cur;
-                st.id_cur = (int)x_in;
-                for (int r = 0; r < R; ++r) {
-                    float a = (st.id_prev >= 0) ? m->wc[((size_t)0 * Q + st.id_prev) * R + r] : 0.0f;
-                    float bb = (st.id_cur >= 0 && st.id_cur < Q) ? m->wc[((size_t)1 * Q + st.id_cur) * R + r] : 0.0f;
-                    x[r] = a + bb;
-                }
-            }
-            const float *lc_use = st.lc_prev;     /* lq[0] */
-            /* --- dilated stack (model.py:141-149, 66-101) --- */
-            for (int l = 0; l < L; ++l) {
-                const orc_layer *ly = &m->layers[l];
-                int d = c->dilations[l];
-                float *slot = st.ring[l] + (size_t)(t % d) * R;   /* holds x_l(t-d) */
-                for (int o = 0; o < D; ++o) {
-                    float f = st.biasf[l * D + o], g = st.biasg[l * D + o];
-                    f = f + dot_plan(ly->wf + o, D, slot, R, p.t_old);
-                    g = g + dot_plan(ly->wg + o, D, slot, R, p.t_old);
-                    if (C) {
-                        f = f + dot_plan(ly->lcf + o, D, lc_use, C, p.t_lc);
-                        g = g + dot_plan(ly->lcg + o, D, lc_use, C, p.t_lc);
-                    }
-                    f = f + dot_plan(ly->wf + (size_t)R * D + o, D, x, R, p.t_cur);
-                    g = g + dot_plan(ly->wg + (size_t)R * D + o, D, x, R, p.t_cur);
-                    z[o] = orc_tanh32(f) * orc_sigmoid32(g);
-                }
-                memcpy(slot, x, sizeof(float) * R);                /* queue push */
-                for (int s = 0; s < S; ++s) {
-                    float v = ly->bs[s] + dot_plan(ly->ws + s, S, z, D, p.t_skip);
-                    acc[s] = (l == 0) ? v : acc[s] + v;             /* sum(outputs), model.py:157 */
-                }
-                int dm = D / p.M;
-                for (int r = 0; r < R; ++r) {
-                    float v = x[r] + ly->bd[r];
-                    for (int mm = 0; mm < p.M; ++mm)
-                        v = v + dot_plan(ly->wd + (size_t)mm * dm * R + r, R, z + mm * dm, dm, p.t_dense);
-                    xn[r] = v;
-                }
-                memcpy(x, xn, sizeof(float) * R);
-            }
-            /* --- postprocessing (model.py:150-165) --- */
-            for (int s = 0; s < S; ++s) acc[s] = relu32(acc[s]);
-            for (int s = 0; s < S; ++s) c1[s] = relu32(m->b1[s] + dot_plan(m->w1 + s, S, acc, S, p.t_post1));
-            int sm = S / p.Mt;
-            for (int o = 0; o < O; ++o) {
-                float v = m->b2[o];
-                for (int mm = 0; mm < p.Mt; ++mm)
-                    v = v + dot_plan(m->w2 + (size_t)mm * sm * O + o, O, c1 + mm * sm, sm, p.t_post2);
-                c2[o] = v;
-            }
-            if (out_logits) memcpy(out_logits + ((size_t)b * T + t) * O, c2, sizeof(float) * O);
-            /* --- head + draw --- */
-            float sample;
-            if (c->scalar_input) {
-                const float *u = (const float *)uniforms + ((size_t)b * T + t) * (nr_mix + 1);
-                sample = mol_draw(c2, nr_mix, u);
-            } else {
-                double u = ((const double *)uniforms)[(size_t)b * T + t];
-                sample = (float)mulaw_draw(c2, Q, temperature, u, NULL);
-            }
-            out_samples[(size_t)b * T + t] = sample;
-            prev_sample = sample;
-            /* --- lc queue push (model.py:125): the row for this step becomes lq[0] next step --- */
-            if (C) {
-                long idx = (long)t - lc_shift;
-                const float *row = (lc_up && idx >= 0 && idx < t_lc) ? lc_up + ((size_t)b * t_lc + idx) * C : zero_lc;
-                memcpy(st.lc_prev, row, sizeof(float) * C);
-            }
-        }
-        for (int l = 0; l < L; ++l) free(st.ring[l]);
-        free(st.ring); free(st.cq); free(st.lc_prev); free(st.biasf); free(st.biasg);
+    gen_ctx g_;
+    g_.m = m; g_.p = p; g_.T = T; g_.n_forced = n_forced; g_.forced = forced; g_.lc_up = lc_up; g_.t_lc = t_lc;
+    g_.lc_shift = lc_shift; g_.gc_ids = gc_ids; g_.uniforms = uniforms; g_.temperature = temperature;
+    g_.out_samples = out_samples; g_.out_logits = out_logits; g_.next_row = 0;
+    pthread_mutex_init(&g_.mu, NULL);
+    int nt = g_threads < N ? g_threads : N;
+    if (nt <= 1) {
+        for (int b = 0; b < N; ++b) run_row(&g_, b);
+    } else {
+        pthread_t th[256];
+        if (nt > 256) nt = 256;
+        for (int i = 0; i < nt; ++i) pthread_create(&th[i], NULL, row_worker, &g_);
+        for (int i = 0; i < nt; ++i) pthread_join(th[i], NULL);
     }
-    free(x); free(xn); free(z); free(acc); free(c1); free(c2); free(gvec); free(zero_lc);
+    pthread_mutex_destroy(&g_.mu);
+    (void)L; (void)R; (void)G; (void)C; (void)ifw;
     return 0;
 }
 

@@ -51,7 +51,7 @@ class WnGenerateArgs(C.Structure):
                 ("out_samples_dev", C.c_void_p), ("out_logits_dev", C.c_void_p)]
 
 
-EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_get_plan",
+EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_plan_config", "wn_get_plan",
            "wn_get_info", "wn_receptive_field", "wn_upsample", "wn_generate", "wn_sync_check",
            "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode"]
 
@@ -84,6 +84,7 @@ def lib():
         L.wn_last_error.restype = C.c_char_p
         L.wn_set_weight.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
         L.wn_finalize.argtypes = [H]
+        L.wn_plan_config.argtypes = [C.POINTER(WnConfig), C.c_int, C.POINTER(WnPlan), C.POINTER(WnInfo)]
         L.wn_get_plan.argtypes = [H, C.POINTER(WnPlan)]
         L.wn_get_info.argtypes = [H, C.POINTER(WnInfo)]
         L.wn_receptive_field.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]

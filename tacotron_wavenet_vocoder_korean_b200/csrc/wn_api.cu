@@ -193,48 +193,24 @@ int wn_set_weight(wn_handle *h, const char *name, const float *data, int64_t n)
     return WN_OK;
 }
 
-int wn_finalize(wn_handle *h)
+// Topology, evaluation plan and shared-memory layout: a pure function of (config, SM count), no CUDA calls.
+static int plan_layout(wn_handle *h, int sm_count)
 {
-    if (!h) return WN_ERR_ARG;
     const wn_config &c = h->cfg;
     const int N = c.batch, L = c.n_layers, R = c.residual_channels, D = c.dilation_channels, S = c.skip_channels;
     const int G = c.gc_channels, C = c.lc_channels, O = h->out_dim, Q = c.quantization_channels, ifw = c.initial_filter_width;
     h->info = wn_info{};
-
-    int dev = 0;
-    cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDevice(&dev));
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10) return fail(h, WN_ERR_CUDA, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major, prop.minor);
-    if (!prop.cooperativeLaunch) return fail(h, WN_ERR_CUDA, "device does not support cooperative launch");
-    h->sm_count = prop.multiProcessorCount;
-
-    // ---- required weights, in TF layout --------------------------------------------------------
-    auto need = [&](const std::string &nm, size_t n, const std::vector<float> **out) -> int {
-        const std::vector<float> *v = find_w(h, nm);
-        if (!v) return fail(h, WN_ERR_STATE, "missing weight %s", nm.c_str());
-        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
-        *out = v;
-        return WN_OK;
-    };
-    std::vector<float> zeros((size_t)std::max(std::max(S, D), std::max(R, O)) + 8, 0.0f);
-    auto opt = [&](const std::string &nm, size_t n, const float **out) -> int {
-        const std::vector<float> *v = find_w(h, nm);
-        if (!v) { *out = zeros.data(); return WN_OK; }
-        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
-        *out = v->data();
-        return WN_OK;
-    };
+    h->sm_count = sm_count;
 
     // ---- topology --------------------------------------------------------------------------------
     int M = c.force_M ? c.force_M : std::min(4, std::max(1, D / 32));
     int Mt = c.force_Mt ? c.force_Mt : std::min(16, std::max(1, S / 32));
     if (!is_pow2(M) || M > 4 || D % M) return fail(h, WN_ERR_ARG, "layer split M=%d invalid for D=%d (power of two <= 4 dividing D)", M, D);
     if (!is_pow2(Mt) || Mt > 32 || S % Mt) return fail(h, WN_ERR_ARG, "tail split Mt=%d invalid for S=%d", Mt, S);
-    if (!c.force_M) while (M > 1 && L * M + Mt + 1 > h->sm_count) M >>= 1;
-    if (!c.force_Mt) while (Mt > 1 && L * M + Mt + 1 > h->sm_count) Mt >>= 1;
+    if (!c.force_M) while (M > 1 && L * M + Mt + 1 > sm_count) M >>= 1;
+    if (!c.force_Mt) while (Mt > 1 && L * M + Mt + 1 > sm_count) Mt >>= 1;
     const int grid = L * M + Mt + 1;
-    if (grid > h->sm_count) return fail(h, WN_ERR_ARG, "%d layers x M=%d + %d tail + 1 sampler = %d CTAs exceed the %d SMs", L, M, Mt, grid, h->sm_count);
+    if (grid > sm_count) return fail(h, WN_ERR_ARG, "%d layers x M=%d + %d tail + 1 sampler = %d CTAs exceed the %d SMs", L, M, Mt, grid, sm_count);
     const int Dm = D / M, Sm = S / M, St = S / Mt;
     if (2 * Dm > WN_NT) return fail(h, WN_ERR_ARG, "2*D/M = %d filter/gate columns exceed %d threads", 2 * Dm, WN_NT);
     if (St > WN_NT) return fail(h, WN_ERR_ARG, "S/Mt = %d exceeds %d threads", St, WN_NT);
@@ -260,8 +236,7 @@ int wn_finalize(wn_handle *h)
     if (p.cur.npass != 1 || p.old.npass != 1) return fail(h, WN_ERR_ARG, "internal: filter/gate must be single pass");
     h->plan = wn_plan{M, Mt, p.cur.t, p.old.t, p.lc.t, p.gc.t, p.dense.t, p.skip.t, p.post1.t, p.post2.t, p.causal.t};
 
-    // ---- layer images ---------------------------------------------------------------------------------
-    // image = [bfg | bd | bs | cur | dense | skip | old | lc | gc]; the resident prefix is what fits.
+    // ---- layer image = [bfg | bd | bs | cur | dense | skip | old | lc | gc]; the resident prefix is what fits
     {
         int off = 0;
         p.off_bfg = off; off += align4(2 * Dm);
@@ -269,7 +244,6 @@ int wn_finalize(wn_handle *h)
         p.off_bs = off; off += align4(Sm);
         WnMat *order[6] = {&p.cur, &p.dense, &p.skip, &p.old, &p.lc, &p.gc};
         bool present[6] = {true, true, true, true, C > 0, G > 0};
-        // scratch
         int so = 0;
         p.ls.xs_cur = so; so += p.cur.xlen;
         p.ls.xs_old = so; so += p.old.xlen;
@@ -298,6 +272,112 @@ int wn_finalize(wn_handle *h)
         p.layer_smem_floats = align4(resident);
         h->smem_layer = (p.layer_smem_floats + so) * 4;
     }
+    // ---- tail image = [b1 | post1 | post2]
+    {
+        int off = 0;
+        p.off_b1 = off; off += align4(St);
+        int so = 0;
+        p.ts.as1 = so; so += p.post1.xlen;
+        p.ts.c1s = so; so += p.post2.xlen;
+        p.ts.total_floats = so;
+        const int cap = kMaxDynSmem / 4 - so;
+        p.post1.off = off; off += mat_floats(p.post1);
+        p.post2.off = off; off += mat_floats(p.post2);
+        int resident = off;
+        if (off > cap) {   // spill conv2 first, then conv1
+            p.post2.in_smem = 0; resident = p.post2.off;
+            h->info.weights_in_global += (int64_t)mat_floats(p.post2) * Mt;
+            if (resident > cap) { p.post1.in_smem = 0; resident = p.post1.off; h->info.weights_in_global += (int64_t)mat_floats(p.post1) * Mt; }
+        }
+        p.tail_img_floats = align32(off);
+        p.tail_smem_floats = align4(resident);
+        h->smem_tail = (p.tail_smem_floats + so) * 4;
+    }
+    // ---- sampler image = [b2 | causal]
+    {
+        int off = 0;
+        p.off_b2 = off; off += align4(O);
+        p.causal.off = off;
+        if (c.scalar_input) off += mat_floats(p.causal);
+        int so = 0;
+        p.ss.c2s = so; so += align4(std::max(O, WN_NT));
+        p.ss.cq = so; so += align4(N * std::max(ifw, 1));
+        p.ss.cqx = so; so += p.causal.xlen;
+        p.ss.ids = so; so += align4(2 * N);
+        p.ss.qs = so; so += WN_NT;
+        so = (so + 1) & ~1;
+        p.ss.cdf = so; so += 2 * WN_NT;
+        p.ss.red = so; so += 2 * 16;
+        p.ss.misc = so; so += 32;
+        p.ss.total_floats = so;
+        if ((off + so) * 4 > kMaxDynSmem) return fail(h, WN_ERR_ARG, "sampler image does not fit shared memory");
+        p.samp_img_floats = align32(off);
+        p.samp_smem_floats = align4(off);
+        h->smem_samp = (p.samp_smem_floats + so) * 4;
+    }
+    h->smem_launch = std::max(h->smem_layer, std::max(h->smem_tail, h->smem_samp));
+
+    wn_info &inf = h->info;
+    inf.grid = grid; inf.threads = WN_NT; inf.M = M; inf.Mt = Mt; inf.sm_count = sm_count;
+    inf.smem_bytes_layer = h->smem_layer; inf.smem_bytes_tail = h->smem_tail; inf.smem_bytes_sampler = h->smem_samp;
+    int64_t per_layer = 2LL * 2 * R * D + 2LL * D + 2LL * C * D + (int64_t)D * R + R + (int64_t)D * S + S;
+    int64_t causal = c.scalar_input ? (int64_t)ifw * R : 2LL * R;
+    inf.p_hot = per_layer * L + causal + (int64_t)S * S + S + (int64_t)S * O + O;
+    inf.weights_in_smem = ((int64_t)p.layer_smem_floats * L * M + (int64_t)p.tail_smem_floats * Mt + p.samp_smem_floats);
+    return WN_OK;
+}
+
+int wn_plan_config(const wn_config *cfg, int sm_count, wn_plan *plan, wn_info *info)
+{
+    wn_handle *h = nullptr;
+    int rc = wn_create(cfg, &h);
+    if (rc) return rc;
+    rc = plan_layout(h, sm_count > 0 ? sm_count : 148);
+    if (rc) g_create_error = h->err;
+    if (!rc && plan) *plan = h->plan;
+    if (!rc && info) *info = h->info;
+    wn_destroy(h);
+    return rc;
+}
+
+int wn_finalize(wn_handle *h)
+{
+    if (!h) return WN_ERR_ARG;
+    const wn_config &c = h->cfg;
+    const int N = c.batch, L = c.n_layers, R = c.residual_channels, D = c.dilation_channels, S = c.skip_channels;
+    const int G = c.gc_channels, C = c.lc_channels, O = h->out_dim, Q = c.quantization_channels, ifw = c.initial_filter_width;
+
+    int dev = 0;
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDevice(&dev));
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(h, WN_ERR_CUDA, "device %s is sm_%d%d; this library contains sm_100a code only", prop.name, prop.major, prop.minor);
+    if (!prop.cooperativeLaunch) return fail(h, WN_ERR_CUDA, "device does not support cooperative launch");
+    {
+        int rc = plan_layout(h, prop.multiProcessorCount);
+        if (rc) return rc;
+    }
+    WnParams &p = h->base;
+    const int M = p.M, Mt = p.Mt, Dm = p.Dm, Sm = p.Sm, St = p.St, grid = p.grid;
+
+    // ---- required weights, in TF layout --------------------------------------------------------
+    auto need = [&](const std::string &nm, size_t n, const std::vector<float> **out) -> int {
+        const std::vector<float> *v = find_w(h, nm);
+        if (!v) return fail(h, WN_ERR_STATE, "missing weight %s", nm.c_str());
+        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
+        *out = v;
+        return WN_OK;
+    };
+    std::vector<float> zeros((size_t)std::max(std::max(S, D), std::max(R, O)) + 8, 0.0f);
+    auto opt = [&](const std::string &nm, size_t n, const float **out) -> int {
+        const std::vector<float> *v = find_w(h, nm);
+        if (!v) { *out = zeros.data(); return WN_OK; }
+        if (v->size() != n) return fail(h, WN_ERR_ARG, "weight %s has %zu elements, expected %zu", nm.c_str(), v->size(), n);
+        *out = v->data();
+        return WN_OK;
+    };
+
+    // ---- layer images -------------------------------------------------------------------------------
     std::vector<float> limg((size_t)p.layer_img_floats * L * M, 0.0f);
     for (int l = 0; l < L; ++l) {
         std::string pre = "wavenet/dilated_stack/layer" + std::to_string(l) + "/dilation_layer/";
@@ -333,27 +413,7 @@ int wn_finalize(wn_handle *h)
         }
     }
 
-    // ---- tail images -------------------------------------------------------------------------------------
-    {
-        int off = 0;
-        p.off_b1 = off; off += align4(St);
-        int so = 0;
-        p.ts.as1 = so; so += p.post1.xlen;
-        p.ts.c1s = so; so += p.post2.xlen;
-        p.ts.total_floats = so;
-        const int cap = kMaxDynSmem / 4 - so;
-        p.post1.off = off; off += mat_floats(p.post1);
-        p.post2.off = off; off += mat_floats(p.post2);
-        int resident = off;
-        if (off > cap) {   // spill conv2 first, then conv1
-            p.post2.in_smem = 0; resident = p.post2.off;
-            h->info.weights_in_global += (int64_t)mat_floats(p.post2) * Mt;
-            if (resident > cap) { p.post1.in_smem = 0; resident = p.post1.off; h->info.weights_in_global += (int64_t)mat_floats(p.post1) * Mt; }
-        }
-        p.tail_img_floats = align32(off);
-        p.tail_smem_floats = align4(resident);
-        h->smem_tail = (p.tail_smem_floats + so) * 4;
-    }
+    // ---- tail images -----------------------------------------------------------------------------------
     std::vector<float> timg((size_t)p.tail_img_floats * Mt, 0.0f);
     const float *b2v;
     {
@@ -372,29 +432,9 @@ int wn_finalize(wn_handle *h)
         }
     }
 
-    // ---- sampler image ----------------------------------------------------------------------------------
-    std::vector<float> simg;
+    // ---- sampler image --------------------------------------------------------------------------------
+    std::vector<float> simg((size_t)p.samp_img_floats, 0.0f);
     {
-        int off = 0;
-        p.off_b2 = off; off += align4(O);
-        p.causal.off = off;
-        if (c.scalar_input) off += mat_floats(p.causal);
-        int so = 0;
-        p.ss.c2s = so; so += align4(std::max(O, WN_NT));
-        p.ss.cq = so; so += align4(N * std::max(ifw, 1));
-        p.ss.cqx = so; so += p.causal.xlen;
-        p.ss.ids = so; so += align4(2 * N);
-        p.ss.qs = so; so += WN_NT;
-        so = (so + 1) & ~1;
-        p.ss.cdf = so; so += 2 * WN_NT;
-        p.ss.red = so; so += 2 * 16;
-        p.ss.misc = so; so += 32;
-        p.ss.total_floats = so;
-        if ((off + so) * 4 > kMaxDynSmem) return fail(h, WN_ERR_ARG, "sampler image does not fit shared memory");
-        p.samp_img_floats = align32(off);
-        p.samp_smem_floats = align4(off);
-        h->smem_samp = (p.samp_smem_floats + so) * 4;
-        simg.assign((size_t)p.samp_img_floats, 0.0f);
         for (int o = 0; o < O; ++o) simg[p.off_b2 + o] = b2v[o];
         const std::vector<float> *wc;
         int rc;
@@ -463,20 +503,11 @@ int wn_finalize(wn_handle *h)
     p.ring_off = (const long long *)h->ring_off.p;
     p.status = (int32_t *)h->status.p;
 
-    h->smem_launch = std::max(h->smem_layer, std::max(h->smem_tail, h->smem_samp));
     CUDA_TRY(h, cudaFuncSetAttribute(wn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
     int occ = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel, WN_NT, h->smem_launch));
     if ((long)occ * h->sm_count < grid) return fail(h, WN_ERR_CUDA, "cannot co-schedule %d CTAs (occupancy %d x %d SMs)", grid, occ, h->sm_count);
-
-    // ---- info ----------------------------------------------------------------------------------------------
-    wn_info &inf = h->info;
-    inf.grid = grid; inf.threads = WN_NT; inf.M = M; inf.Mt = Mt; inf.sm_count = h->sm_count;
-    inf.smem_bytes_layer = h->smem_layer; inf.smem_bytes_tail = h->smem_tail; inf.smem_bytes_sampler = h->smem_samp;
-    int64_t per_layer = 2LL * 2 * R * D + 2LL * D + 2LL * C * D + (int64_t)D * R + R + (int64_t)D * S + S;
-    int64_t causal = c.scalar_input ? (int64_t)ifw * R : 2LL * R;
-    inf.p_hot = per_layer * L + causal + (int64_t)S * S + S + (int64_t)S * O + O;
-    inf.weights_in_smem = ((int64_t)p.layer_smem_floats * L * M + (int64_t)p.tail_smem_floats * Mt + p.samp_smem_floats);
+    (void)St; (void)Sm;
     h->finalized = true;
     return WN_OK;
 }

@@ -12,6 +12,50 @@ import torch
 from .. import _lib
 
 
+def _make_cfg(batch_size, dilations, filter_width, residual_channels, dilation_channels, skip_channels,
+              quantization_channels=2 ** 8, out_channels=30, use_biases=False, scalar_input=False,
+              initial_filter_width=32, global_condition_channels=None, global_condition_cardinality=None,
+              local_condition_channels=80, upsample_factor=None, train_mode=True, force_M=0, force_Mt=0, **_ignored):
+    dilations = list(dilations)
+    uf = list(upsample_factor) if upsample_factor else []
+    if len(uf) > _lib.WN_MAX_UPSAMPLE or len(dilations) > _lib.WN_MAX_LAYERS:
+        raise ValueError("too many upsample stages / layers")
+    cfg = _lib.WnConfig()
+    cfg.batch = batch_size
+    cfg.n_layers = len(dilations)
+    cfg.filter_width = filter_width
+    cfg.residual_channels = residual_channels
+    cfg.dilation_channels = dilation_channels
+    cfg.skip_channels = skip_channels
+    cfg.quantization_channels = quantization_channels
+    cfg.out_channels = out_channels
+    cfg.use_biases = int(bool(use_biases))
+    cfg.scalar_input = int(bool(scalar_input))
+    cfg.initial_filter_width = initial_filter_width
+    cfg.gc_channels = global_condition_channels or 0
+    cfg.gc_cardinality = global_condition_cardinality or 0
+    cfg.lc_channels = local_condition_channels or 0
+    cfg.n_upsample = len(uf)
+    for i, f in enumerate(uf):
+        cfg.upsample_factor[i] = f
+    for i, d in enumerate(dilations):
+        cfg.dilations[i] = d
+    cfg.force_M = force_M
+    cfg.force_Mt = force_Mt
+    return cfg
+
+
+def plan_config(sm_count=148, **model_kwargs):
+    """(plan, info) the library picks for a WaveNetModel(**model_kwargs) on a device with `sm_count`
+    SMs -- host-only (wn_plan_config), usable without a GPU."""
+    cfg = _make_cfg(**model_kwargs)
+    plan, info = _lib.WnPlan(), _lib.WnInfo()
+    rc = _lib.lib().wn_plan_config(C.byref(cfg), sm_count, C.byref(plan), C.byref(info))
+    if rc != 0:
+        raise ValueError(_lib.lib().wn_last_error(None).decode())
+    return plan.as_dict(), info.as_dict()
+
+
 class WaveNetModel(object):
     def __init__(self, batch_size, dilations, filter_width, residual_channels, dilation_channels, skip_channels,
                  quantization_channels=2 ** 8, out_channels=30, use_biases=False, scalar_input=False,
@@ -40,31 +84,10 @@ class WaveNetModel(object):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
             if torch.cuda.is_available() else None
 
-        cfg = _lib.WnConfig()
-        cfg.batch = batch_size
-        cfg.n_layers = len(self.dilations)
-        cfg.filter_width = filter_width
-        cfg.residual_channels = residual_channels
-        cfg.dilation_channels = dilation_channels
-        cfg.skip_channels = skip_channels
-        cfg.quantization_channels = quantization_channels
-        cfg.out_channels = out_channels
-        cfg.use_biases = int(bool(use_biases))
-        cfg.scalar_input = int(bool(scalar_input))
-        cfg.initial_filter_width = initial_filter_width
-        cfg.gc_channels = global_condition_channels or 0
-        cfg.gc_cardinality = global_condition_cardinality or 0
-        cfg.lc_channels = local_condition_channels or 0
-        uf = self.upsample_factor or []
-        cfg.n_upsample = len(uf)
-        if len(uf) > _lib.WN_MAX_UPSAMPLE or len(self.dilations) > _lib.WN_MAX_LAYERS:
-            raise ValueError("too many upsample stages / layers")
-        for i, f in enumerate(uf):
-            cfg.upsample_factor[i] = f
-        for i, d in enumerate(self.dilations):
-            cfg.dilations[i] = d
-        cfg.force_M = force_M
-        cfg.force_Mt = force_Mt
+        cfg = _make_cfg(batch_size, dilations, filter_width, residual_channels, dilation_channels, skip_channels,
+                        quantization_channels, out_channels, use_biases, scalar_input, initial_filter_width,
+                        global_condition_channels, global_condition_cardinality, local_condition_channels,
+                        upsample_factor, train_mode, force_M, force_Mt)
         self._cfg = cfg
         self._h = C.c_void_p()
         rc = _lib.lib().wn_create(C.byref(cfg), C.byref(self._h))

@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path (through the C ABI / WaveNetModel) against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes --
+through size-independent properties.  Tolerances: every output is compared BIT-EXACT (the oracle is run
+with the evaluation plan the kernel reports); the 1e-4 bound of north_star is additionally checked against
+the oracle's natural evaluation order."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.helpers import make_inputs, oracle_model, plan_from_dict
+from tacotron_wavenet_vocoder_korean_b200 import _lib, synth
+from tacotron_wavenet_vocoder_korean_b200.wavenet import WaveNetModel, mu_law_encode, mu_law_decode
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def build(kw, **extra):
+    w = synth.make_weights(**kw)
+    net = WaveNetModel(train_mode=False, **kw, **extra)
+    net.load_state_dict(w)
+    return net, w
+
+
+def run_both(kw, T, teacher=False, temperature=1.0, lc_shift=0, forced=None, **extra):
+    net, w = build(kw, **extra)
+    om = oracle_model(kw, w)
+    inp = make_inputs(kw, T)
+    lc_o = lc_t = None
+    if 'mel' in inp:
+        lc_t = net.create_upsample(inp['mel'])
+        lc_o = om.upsample(inp['mel'])
+        assert np.array_equal(lc_o, lc_t.cpu().numpy()), 'create_upsample differs'
+    if forced is None:
+        forced = inp['forced_full'] if teacher else inp['x0']
+    s, lg = net.generate(T, forced, inp['uniforms'], lc_up=lc_t, lc_shift=lc_shift, gc_ids=inp['gc_ids'],
+                         temperature=temperature, want_logits=True)
+    plan = plan_from_dict(net.plan())
+    so, lo = om.generate(T, forced, inp['uniforms'], lc_up=lc_o, lc_shift=lc_shift, gc_ids=inp['gc_ids'],
+                         temperature=temperature, plan=plan, want_logits=True)
+    return net, om, inp, (s.cpu().numpy(), lg.cpu().numpy()), (so, lo), (lc_t, lc_o)
+
+
+def assert_exact(got, exp):
+    (s, lg), (so, lo) = got, exp
+    if not np.array_equal(lo, lg):
+        bad = np.argwhere(lo != lg)[0]
+        raise AssertionError('logits differ first at (row, step, channel) %s: oracle %r kernel %r (max abs diff %g)'
+                             % (bad, lo[tuple(bad)], lg[tuple(bad)], np.abs(lo - lg).max()))
+    if not np.array_equal(so, s):
+        bad = np.argwhere(so != s)[0]
+        raise AssertionError('samples differ first at (row, step) %s: oracle %r kernel %r' % (bad, so[tuple(bad)], s[tuple(bad)]))
+
+
+@pytest.mark.parametrize('fac,T', [(synth.tiny_mol, 150), (synth.tiny_mulaw, 300)])
+@pytest.mark.parametrize('teacher', [False, True])
+def test_tiny_bit_exact(fac, T, teacher):
+    _, _, _, got, exp, _ = run_both(fac(), T, teacher=teacher)
+    assert_exact(got, exp)
+
+
+@pytest.mark.parametrize('fac', [synth.tiny_mol, synth.tiny_mulaw])
+@pytest.mark.parametrize('M,Mt', [(1, 1), (2, 2), (4, 4), (2, 8), (4, 1)])
+def test_every_split_bit_exact(fac, M, Mt):
+    # every layer / tail split is a different evaluation plan and a different CTA topology
+    kw = fac()
+    if kw['skip_channels'] // Mt < 4:
+        pytest.skip('slice too small')
+    net, _, _, got, exp, _ = run_both(kw, 120, force_M=M, force_Mt=Mt)
+    assert net.plan()['M'] == M and net.plan()['Mt'] == Mt
+    assert_exact(got, exp)
+
+
+def test_cfg1_full_length_integer_samples_bit_exact():
+    # BASELINE configs[0]: 10-layer mu-law 256, 0.5 s @ 16 kHz = 8000 steps, unconditioned, free running
+    kw = synth.cfg1()
+    net, om, inp, got, exp, _ = run_both(kw, 8000)
+    assert_exact(got, exp)
+    s = got[0]
+    assert s.min() >= 0 and s.max() <= 255 and np.all(s == np.round(s))
+    assert len(np.unique(s)) > 100                       # a real draw, not a stuck value
+    # north_star tolerance vs the natural evaluation order (teacher forcing with the kernel's own samples)
+    forced = np.concatenate([inp['x0'], s[:, :-1]], axis=1)
+    _, lnat = om.generate(8000, forced, inp['uniforms'], want_logits=True)
+    assert np.max(np.abs(lnat - got[1])) < 1e-4
+
+
+def test_cfg2_batch8_bit_exact_and_tolerance():
+    # BASELINE configs[1]: 30 layers, R=D=128, S=512, MoL-10, mel + speaker conditioned, batch 8
+    kw = synth.cfg2(8)
+    net, om, inp, got, exp, (lc_t, lc_o) = run_both(kw, 260)
+    info = net.info()
+    assert (info['grid'], info['M'], info['Mt']) == (137, 4, 16) and info['weights_in_global'] == 0
+    assert_exact(got, exp)
+    assert np.all(np.abs(got[0]) <= 1.0)
+    forced = np.concatenate([inp['x0'], got[0][:, :-1]], axis=1)
+    _, lnat = om.generate(260, forced, inp['uniforms'], lc_up=lc_o, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.max(np.abs(lnat - got[1])) < 1e-4          # float MoL logits within 1e-4 (north_star)
+
+
+def test_hparams_default_model_bit_exact():
+    # the reference's own defaults (hparams.py:59-79): 50 layers, R=D=32, scalar input, lc + gc
+    _, _, _, got, exp, _ = run_both(synth.cfg_hparams_default(2), 400)
+    assert_exact(got, exp)
+
+
+@pytest.mark.parametrize('name', ['tiny_mol', 'tiny_mulaw', 'cfg1', 'cfg2_n2'])
+def test_matches_committed_golden(name):
+    from tests.golden.make_golden import CASES
+    g = np.load(os.path.join(GOLD, name + '.npz'))
+    fac, fkw, T = CASES[name]
+    kw = fac(**fkw)
+    net, _ = build(kw)
+    inp = make_inputs(kw, T)
+    assert [net.plan()[k] for k, _ in oracle.OrcPlan._fields_] == [int(v) for v in g['plan']]
+    lc = net.create_upsample(inp['mel']) if 'mel' in inp else None
+    s, lg = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.array_equal(s.cpu().numpy(), g['samples_kernel'])
+    assert np.array_equal(lg[:, -4:].cpu().numpy(), g['logits_tail_kernel'])
+    _, lg = net.generate(48, inp['forced_full'][:, :48], inp['uniforms'][:, :48], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.array_equal(lg.cpu().numpy(), g['tf_logits_kernel'])
+    assert np.max(np.abs(lg.cpu().numpy() - g['tf_logits_natural'])) < 1e-4
+    if lc is not None:
+        assert np.array_equal(lc[:, :7].cpu().numpy(), g['lc_head'])
+
+
+def test_temperature_changes_draw_and_stays_exact():
+    _, _, _, got, exp, _ = run_both(synth.tiny_mulaw(), 200, temperature=0.7)
+    assert_exact(got, exp)
+    _, _, _, got1, _, _ = run_both(synth.tiny_mulaw(), 200, temperature=1.0)
+    assert not np.array_equal(got[0], got1[0])
+
+
+def test_priming_with_seed_path():
+    # generate.py:170-180: rf-1 priming steps with zero LC, then generation from seed[-1]
+    kw = synth.tiny_mol()
+    rf = WaveNetModel.calculate_receptive_field(2, kw['dilations'], True, kw['initial_filter_width'])
+    T = rf - 1 + 90
+    inp = make_inputs(kw, T)
+    seed = inp['forced_full'][:, :rf]
+    _, _, _, got, exp, _ = run_both(kw, T, forced=seed, lc_shift=rf - 1)
+    assert_exact(got, exp)
+
+
+def test_ragged_rows_and_partial_batch():
+    kw = synth.tiny_mol(batch_size=4)
+    net, w = build(kw)
+    om = oracle_model(kw, w)
+    T = 90
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    T_row = [90, 17, 0, 55]
+    s = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], T_row=T_row).cpu().numpy()
+    so = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc.cpu().numpy(), gc_ids=inp['gc_ids'], plan=plan_from_dict(net.plan()))
+    for b, tr in enumerate(T_row):
+        assert np.array_equal(s[b, :tr], so[b, :tr])
+    # fewer rows than batch_size: rows are independent, so row b equals the full-batch result
+    s2 = net.generate(T, inp['x0'][:2], inp['uniforms'][:2], lc_up=lc[:2], gc_ids=inp['gc_ids'][:2]).cpu().numpy()
+    assert np.array_equal(s2, so[:2])
+    # empty job
+    assert net.generate(0, inp['x0'], inp['uniforms'][:, :0], lc_up=lc, gc_ids=inp['gc_ids']).shape == (4, 0)
+
+
+def test_host_buffer_entry_point_equals_device_entry_point():
+    kw = synth.tiny_mol()
+    net, _ = build(kw)
+    T = 120
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    dev = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids']).cpu().numpy()
+    host = net.generate_host(T, inp['x0'], inp['uniforms'], mel=inp['mel'], gc_ids=inp['gc_ids'])
+    assert np.array_equal(dev, host)
+
+
+def test_predict_proba_incremental_emulation():
+    kw = synth.tiny_mulaw()
+    net, w = build(kw)
+    om = oracle_model(kw, w)
+    inp = make_inputs(kw, 5)
+    _, lo = om.generate(5, inp['forced_full'][:, :5], inp['uniforms'], plan=plan_from_dict(net.plan()), want_logits=True)
+    net.reset_incremental()
+    for t in range(5):
+        proba = net.predict_proba_incremental(inp['forced_full'][:, t:t + 1])
+        assert proba.shape == (2, 256)
+        ref = np.stack([oracle.softmax_probs(r) for r in lo[:, t]])
+        np.testing.assert_allclose(proba.cpu().numpy(), ref, rtol=2e-6, atol=1e-12)
+        np.testing.assert_allclose(proba.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)   # generate.py:227 invariant
+
+
+def test_mu_law_codec_on_device():
+    g = np.load(os.path.join(GOLD, 'codec.npz'))
+    enc = mu_law_encode(torch.from_numpy(g['grid']).cuda(), 256).cpu().numpy()
+    assert np.mean(enc != g['enc']) < 2e-3 and np.max(np.abs(enc - g['enc'])) <= 1     # libm vs libdevice log1p at cell edges
+    dec = mu_law_decode(torch.arange(256, dtype=torch.float32).cuda(), 256, True).cpu().numpy()
+    np.testing.assert_allclose(dec, g['dec_q'], atol=1e-4, rtol=1e-5)
+    assert np.array_equal(mu_law_encode(torch.from_numpy(dec).cuda(), 256).cpu().numpy(), np.arange(256))
+    dec_c = mu_law_decode(torch.linspace(-1, 1, 513).cuda(), 256, False).cpu().numpy()
+    np.testing.assert_allclose(dec_c, g['dec_c'], atol=1e-4, rtol=1e-5)
+
+
+def test_argument_errors_are_loud():
+    kw = synth.tiny_mol()
+    net, _ = build(kw)
+    inp = make_inputs(kw, 8)
+    lc = net.create_upsample(inp['mel'])
+    with pytest.raises(RuntimeError, match='gc_ids'):
+        net.generate(8, inp['x0'], inp['uniforms'], lc_up=lc)                        # generate.py:72-77
+    with pytest.raises(ValueError):
+        net.generate(8, inp['x0'], inp['uniforms'][:, :, :5], lc_up=lc, gc_ids=inp['gc_ids'])
+    with pytest.raises(RuntimeError):
+        net.generate(8, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=[0, 99])
+    fresh = WaveNetModel(train_mode=False, **kw)
+    with pytest.raises(RuntimeError):
+        fresh.generate(8, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])   # not loaded
+    with pytest.raises(RuntimeError, match='missing weight'):
+        fresh.load_state_dict({k: v for k, v in synth.make_weights(**kw).items() if 'skip/kernel' not in k})
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE configs[1] at full length (8 utterances x 2 s @ 24 kHz = 48000 steps), checked through
+    properties that do not need a 48000-step CPU run: determinism, causality (prefix property), batch-row
+    independence, and an oracle check on a bounded prefix."""
+    kw = synth.cfg2(8)
+    net, w = build(kw)
+    T = 48000
+    inp = make_inputs(kw, T, t_mel=160)
+    assert inp['mel'].shape == (8, 160, 80)
+    lc = net.create_upsample(inp['mel'])
+    assert lc.shape == (8, 48000, 80)
+    a = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])
+    b = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])
+    assert torch.equal(a, b)                                                   # deterministic
+    a = a.cpu().numpy()
+    assert np.all(np.isfinite(a)) and np.all(np.abs(a) <= 1.0) and a.std() > 1e-3
+    k = 3000
+    pre = net.generate(k, inp['x0'], inp['uniforms'][:, :k], lc_up=lc, gc_ids=inp['gc_ids']).cpu().numpy()
+    assert np.array_equal(pre, a[:, :k])                                        # causal: prefix of the long run
+    # rows never interact (model.py:112-167 is row-wise): row 5 alone == row 5 of the batch
+    one = net.generate(T, inp['x0'][5:6], inp['uniforms'][5:6], lc_up=lc[5:6], gc_ids=inp['gc_ids'][5:6]).cpu().numpy()
+    assert np.array_equal(one[0], a[5])
+    # oracle on a bounded prefix of two rows
+    om = oracle_model(synth.cfg2(2), w)
+    so = om.generate(200, inp['x0'][:2], inp['uniforms'][:2, :200], lc_up=lc[:2, :200].cpu().numpy(),
+                     gc_ids=inp['gc_ids'][:2], plan=plan_from_dict(net.plan()))
+    assert np.array_equal(so, a[:2, :200])
