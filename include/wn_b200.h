@@ -56,7 +56,10 @@ typedef struct wn_config {
     int32_t dilations[WN_MAX_LAYERS];
     int32_t force_M;
     int32_t force_Mt;
+    int32_t flags;                     /* WN_FLAG_* */
 } wn_config;
+
+#define WN_FLAG_GENERIC_KERNEL 1       /* never pick a compile-time specialised kernel instantiation */
 
 /* Floating-point evaluation order implemented by the kernel (DESIGN.md "Pinned arithmetic").
  * Field meaning is identical to oracle/wn_oracle.c's orc_plan. */
@@ -74,6 +77,8 @@ typedef struct wn_info {
     int64_t weights_in_smem;           /* floats resident in shared memory over the whole grid */
     int64_t weights_in_global;         /* floats that overflowed to L2/HBM */
     int64_t kernel_launches;           /* kernels launched by this handle so far */
+    int32_t static_shape;              /* 0: runtime-shaped kernel; 1: cfg2 shape, 2: cfg1 shape, 3: hparams.py default shape */
+    int32_t reserved;
 } wn_info;
 
 typedef struct wn_handle wn_handle;

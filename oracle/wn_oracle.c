@@ -392,12 +392,30 @@ static int mulaw_draw(const float *c2, int Q, float temperature, double u, float
         s[j] = orc_log32(p) / temperature;
     }
     float lse = tree_logaddexp32(s, Q);
-    double acc = 0.0;
-    for (int j = 0; j < Q; ++j) {
-        float q = orc_exp32(s[j] - lse);
-        acc += (double)q;                       /* np.cumsum: sequential */
-        e[j] = acc;
+    for (int j = 0; j < Q; ++j) e[j] = (double)orc_exp32(s[j] - lse);
+    /* np.cumsum(float64(q)) in a pinned, parallel-friendly order: a Kogge-Stone scan inside each block
+     * of 32 (v[j] += v[j-off], off = 1,2,..,16), then each block adds the left-to-right sum of the
+     * preceding block totals.  numpy accumulates strictly left to right; the two differ by at most an
+     * ulp of fp64, which moves a draw only when u lies within ~1e-16 of a bin edge. */
+    {
+        double tot[64];
+        int nb = (Q + 31) / 32;
+        for (int bk = 0; bk < nb; ++bk) {
+            int blk = bk * 32;
+            int n = (Q - blk < 32) ? (Q - blk) : 32;
+            for (int off = 1; off < n; off <<= 1)
+                for (int j = n - 1; j >= off; --j) e[blk + j] = e[blk + j] + e[blk + j - off];
+            tot[bk] = e[blk + n - 1];
+        }
+        double base = tot[0];
+        for (int bk = 1; bk < nb; ++bk) {
+            int blk = bk * 32;
+            int n = (Q - blk < 32) ? (Q - blk) : 32;
+            for (int j = 0; j < n; ++j) e[blk + j] = base + e[blk + j];
+            base = base + tot[bk];
+        }
     }
+    double acc = e[Q - 1];
     int cnt = 0;
     for (int j = 0; j < Q; ++j) if (e[j] / acc <= u) ++cnt;   /* searchsorted(side='right') */
     if (cnt > Q - 1) cnt = Q - 1;

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libwn_b200.so")
 WN_MAX_LAYERS = 256
 WN_MAX_UPSAMPLE = 8
 WN_MAX_BATCH = 32
+WN_FLAG_GENERIC_KERNEL = 1
 
 
 class WnConfig(C.Structure):
@@ -21,7 +22,7 @@ class WnConfig(C.Structure):
         ("gc_channels", C.c_int32), ("gc_cardinality", C.c_int32), ("lc_channels", C.c_int32),
         ("n_upsample", C.c_int32), ("upsample_factor", C.c_int32 * WN_MAX_UPSAMPLE),
         ("dilations", C.c_int32 * WN_MAX_LAYERS),
-        ("force_M", C.c_int32), ("force_Mt", C.c_int32),
+        ("force_M", C.c_int32), ("force_Mt", C.c_int32), ("flags", C.c_int32),
     ]
 
 
@@ -37,7 +38,8 @@ class WnInfo(C.Structure):
     _fields_ = [("grid", C.c_int32), ("threads", C.c_int32), ("M", C.c_int32), ("Mt", C.c_int32),
                 ("smem_bytes_layer", C.c_int32), ("smem_bytes_tail", C.c_int32), ("smem_bytes_sampler", C.c_int32),
                 ("sm_count", C.c_int32), ("p_hot", C.c_int64), ("weights_in_smem", C.c_int64),
-                ("weights_in_global", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("weights_in_global", C.c_int64), ("kernel_launches", C.c_int64),
+                ("static_shape", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

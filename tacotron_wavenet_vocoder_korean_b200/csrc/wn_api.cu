@@ -50,7 +50,10 @@ struct wn_handle {
     wn_info info{};
     WnParams base{};            // everything except the per-call fields
     int smem_layer = 0, smem_tail = 0, smem_samp = 0, smem_launch = 0;
+    const void *kernel = nullptr;
     DevBuf layer_img, tail_img, samp_img, gc_table, wc_onehot, upk, mbox, ring, ring_off, status;
+    DevBuf prof;
+    bool prof_on = false;
     DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
     DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
     size_t mbox_bytes = 0, ring_bytes = 0;
@@ -100,6 +103,8 @@ WnMat make_mat(int K, int ncols, int t)
     else m.xstride = (m.ch % 2 == 1) ? m.ch : m.ch + 1;
     m.xlen = align4(t * m.xstride);
     m.in_smem = 1;
+    m.u = (m.V == 4) ? wn_u_for_n4(m.ch / 4) : 1;      // mirrors dot_thread() in wn_kernel.cu
+    if (t * m.u > 64 && t > 1) return make_mat(K, ncols, t / 2);   // canonical chunk count is capped at 64 per column
     return m;
 }
 
@@ -179,7 +184,7 @@ void wn_destroy(wn_handle *h)
 {
     if (!h) return;
     DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
-                      &h->ring_off, &h->status, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
+                      &h->ring_off, &h->status, &h->prof, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
                       &h->h_out, &h->h_logits};
     for (DevBuf *b : bufs) b->release();
     delete h;
@@ -234,7 +239,8 @@ static int plan_layout(wn_handle *h, int sm_count)
     p.post2 = make_mat(St, O, choose_t(O, St, 32));
     p.causal = make_mat(c.scalar_input ? ifw : 4, R, c.scalar_input ? choose_t(R, ifw, 32) : 1);
     if (p.cur.npass != 1 || p.old.npass != 1) return fail(h, WN_ERR_ARG, "internal: filter/gate must be single pass");
-    h->plan = wn_plan{M, Mt, p.cur.t, p.old.t, p.lc.t, p.gc.t, p.dense.t, p.skip.t, p.post1.t, p.post2.t, p.causal.t};
+    h->plan = wn_plan{M, Mt, p.cur.t * p.cur.u, p.old.t * p.old.u, p.lc.t * p.lc.u, p.gc.t * p.gc.u, p.dense.t * p.dense.u,
+                      p.skip.t * p.skip.u, p.post1.t * p.post1.u, p.post2.t * p.post2.u, p.causal.t * p.causal.u};
 
     // ---- layer image = [bfg | bd | bs | cur | dense | skip | old | lc | gc]; the resident prefix is what fits
     {
@@ -324,6 +330,13 @@ static int plan_layout(wn_handle *h, int sm_count)
     int64_t causal = c.scalar_input ? (int64_t)ifw * R : 2LL * R;
     inf.p_hot = per_layer * L + causal + (int64_t)S * S + S + (int64_t)S * O + O;
     inf.weights_in_smem = ((int64_t)p.layer_smem_floats * L * M + (int64_t)p.tail_smem_floats * Mt + p.samp_smem_floats);
+    // compile-time specialised instantiation, when the planned shapes coincide with one
+    h->kernel = (const void *)wn_persistent_kernel;
+    if (!(c.flags & WN_FLAG_GENERIC_KERNEL) && inf.weights_in_global == 0) {
+        if (shape_matches<ShapeCfg2>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg2>; inf.static_shape = 1; }
+        else if (shape_matches<ShapeCfg1>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg1>; inf.static_shape = 2; }
+        else if (shape_matches<ShapeHparams>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeHparams>; inf.static_shape = 3; }
+    }
     return WN_OK;
 }
 
@@ -503,9 +516,12 @@ int wn_finalize(wn_handle *h)
     p.ring_off = (const long long *)h->ring_off.p;
     p.status = (int32_t *)h->status.p;
 
-    CUDA_TRY(h, cudaFuncSetAttribute(wn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
+    CUDA_TRY(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
     int occ = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel, WN_NT, h->smem_launch));
+    if (h->info.static_shape == 1) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeCfg2>, WN_NT, h->smem_launch));
+    else if (h->info.static_shape == 2) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeCfg1>, WN_NT, h->smem_launch));
+    else if (h->info.static_shape == 3) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeHparams>, WN_NT, h->smem_launch));
+    else CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel, WN_NT, h->smem_launch));
     if ((long)occ * h->sm_count < grid) return fail(h, WN_ERR_CUDA, "cannot co-schedule %d CTAs (occupancy %d x %d SMs)", grid, occ, h->sm_count);
     (void)St; (void)Sm;
     h->finalized = true;
@@ -603,10 +619,44 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
     CUDA_TRY(h, cudaMemsetAsync(h->mbox.p, 0, h->mbox_bytes, st));
     if (h->ring_bytes) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));
     CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 16, st));
+    p.prof = nullptr;
+    if (h->prof_on) {
+        CUDA_TRY(h, h->prof.ensure((size_t)p.grid * 16 * sizeof(long long)));
+        CUDA_TRY(h, cudaMemsetAsync(h->prof.p, 0, (size_t)p.grid * 16 * sizeof(long long), st));
+        p.prof = (long long *)h->prof.p;
+    }
     void *args[] = {&p};
-    CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)wn_persistent_kernel, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
+    CUDA_TRY(h, cudaLaunchCooperativeKernel(h->kernel, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
     h->launches++;
     return WN_OK;
+}
+
+/* Diagnostics (not part of the reference-facing surface): per-CTA phase cycle counters of the next launches. */
+int wn_debug_profile(wn_handle *h, int enable, long long *out, int n)
+{
+    if (!h) return WN_ERR_ARG;
+    h->prof_on = enable != 0;
+    if (out && h->prof.p) {
+        CUDA_TRY(h, cudaDeviceSynchronize());
+        size_t bytes = std::min((size_t)n * sizeof(long long), h->prof.bytes);
+        CUDA_TRY(h, cudaMemcpy(out, h->prof.p, bytes, cudaMemcpyDeviceToHost));
+    }
+    return WN_OK;
+}
+
+/* Diagnostics: average LL-mailbox round trip between two CTAs, in SM clock cycles. */
+long long wn_debug_pingpong(int iters)
+{
+    unsigned long long *box = nullptr;
+    long long *out = nullptr, host = -1;
+    if (cudaMalloc(&box, 256) != cudaSuccess || cudaMalloc(&out, 8) != cudaSuccess) return -1;
+    cudaMemset(box, 0, 256);
+    void *args[] = {&box, &iters, &out};
+    if (cudaLaunchCooperativeKernel((const void *)wn_pingpong_kernel, dim3(2), dim3(32), args, 0, 0) != cudaSuccess) return -2;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+    cudaMemcpy(&host, out, 8, cudaMemcpyDeviceToHost);
+    cudaFree(box); cudaFree(out);
+    return host;
 }
 
 int wn_sync_check(wn_handle *h, void *stream)

@@ -26,6 +26,8 @@
 #include "wn_params.h"
 #include "wn_math.cuh"
 
+extern __shared__ __align__(128) float g_smem[];
+
 namespace {
 
 using wn::fadd;
@@ -58,6 +60,17 @@ __device__ __forceinline__ int ld_volatile_i32(const int *p)
     asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+
+// optional phase profile: prof[cta*16 + phase] accumulates clock64() deltas of thread 0
+struct Prof {
+    long long *slot;
+    long long last;
+    __device__ __forceinline__ void start() { if (slot && threadIdx.x == 0) last = clock64(); }
+    __device__ __forceinline__ void mark(int phase)
+    {
+        if (slot && threadIdx.x == 0) { long long now = clock64(); slot[phase] += now - last; last = now; }
+    }
+};
 
 struct Abort {
     int32_t *status;
@@ -151,39 +164,109 @@ __device__ void load_image_tma(float *smem_dst, const float *gsrc, int n_floats,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Thread-major matvec.  All WN_NT threads must call it (warp shuffles inside).
+// Thread-major matvec (layout: wn_params.h).  Per-thread view of one packed matrix, built once
+// before the step loop so no index arithmetic (integer divisions!) sits on the sample chain.
+struct MatT {
+    const float *ws;     // shared-memory copy:  packed base + tid*V   (valid when smem)
+    const float *wg;     // global image copy:   packed base + tid*V
+    const float *xc;     // this thread's chunk of the padded input vector (shared memory)
+    int grp;             // tid / tpc : column within a pass
+    int n4, ch, u, tpc, npass, gpp, ncols, V;
+    bool lead;           // tid % tpc == 0 : holds the result after the butterfly
+    bool smem;
+};
+
 __device__ __forceinline__ int xpad(const WnMat &m, int k) { return (k / m.ch) * m.xstride + (k % m.ch); }
 
-template <class F>
-__device__ __forceinline__ void matvec(const WnMat &m, const float *__restrict__ w, const float *__restrict__ xs, F &&epi)
+__device__ __forceinline__ MatT make_matt(const WnMat &m, const float *gimg, const float *xs)
 {
     const int tid = threadIdx.x;
-    const int chunk = tid % m.t;
-    const int grp = tid / m.t;
-    const float *xc = xs + chunk * m.xstride;
-    for (int pass = 0; pass < m.npass; ++pass) {
-        float acc = 0.0f;
-        if (m.V == 4) {
-            const float4 *w4 = reinterpret_cast<const float4 *>(w) + (size_t)pass * (m.ch >> 2) * WN_NT + tid;
-            const float4 *x4 = reinterpret_cast<const float4 *>(xc);
-            const int n4 = m.ch >> 2;
-#pragma unroll 4
-            for (int i = 0; i < n4; ++i) {
-                float4 wv = w4[(size_t)i * WN_NT];
-                float4 xv = x4[i];
-                acc = ffma(wv.x, xv.x, acc);
-                acc = ffma(wv.y, xv.y, acc);
-                acc = ffma(wv.z, xv.z, acc);
-                acc = ffma(wv.w, xv.w, acc);
-            }
-        } else {
-            const float *w1 = w + (size_t)pass * m.ch * WN_NT + tid;
-#pragma unroll 4
-            for (int i = 0; i < m.ch; ++i) acc = ffma(w1[(size_t)i * WN_NT], xc[i], acc);
+    MatT t;
+    t.ws = g_smem + m.off + tid * m.V;
+    t.wg = gimg + m.off + tid * m.V;
+    t.xc = xs + (tid % m.t) * m.xstride;
+    t.grp = tid / m.t;
+    t.n4 = m.ch >> 2; t.ch = m.ch; t.u = m.u; t.tpc = m.t; t.npass = m.npass; t.gpp = m.gpp; t.ncols = m.ncols; t.V = m.V;
+    t.lead = (tid % m.t) == 0;
+    t.smem = m.in_smem != 0;
+    return t;
+}
+
+// N4 float4 loads per thread, U independent fma sub-chains of N4/U float4 each (canonical chunks
+// chunk*U .. chunk*U+U-1), combined by the first log2(U) levels of the ascending butterfly.
+template <int N4, int U>
+__device__ __forceinline__ float dot_regs(const float4 *__restrict__ w4, const float4 *__restrict__ x4)
+{
+    float4 wv[N4], xv[N4];
+#pragma unroll
+    for (int i = 0; i < N4; ++i) { wv[i] = w4[i * WN_NT]; xv[i] = x4[i]; }
+    constexpr int PER = N4 / U;
+    float acc[U];
+#pragma unroll
+    for (int s = 0; s < U; ++s) {
+        float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const float4 ww = wv[s * PER + i], xx = xv[s * PER + i];
+            a = ffma(ww.x, xx.x, a);
+            a = ffma(ww.y, xx.y, a);
+            a = ffma(ww.z, xx.z, a);
+            a = ffma(ww.w, xx.w, a);
         }
-        for (int off = 1; off < m.t; off <<= 1) acc = fadd(acc, __shfl_xor_sync(FULL, acc, off));
-        const int col = pass * m.gpp + grp;
-        if (chunk == 0 && col < m.ncols) epi(col, acc);
+        acc[s] = a;
+    }
+#pragma unroll
+    for (int off = 1; off < U; off <<= 1)
+#pragma unroll
+        for (int c = 0; c < U; c += 2 * off) acc[c] = fadd(acc[c], acc[c + off]);
+    return acc[0];
+}
+
+// sub-chain count the device code implements for a chunk of n4 float4 (host mirrors this: wn_api.cu make_mat)
+__host__ __device__ constexpr int wn_u_for_n4(int n4)
+{
+    return n4 == 2 ? 2 : n4 == 4 ? 4 : n4 == 8 ? 8 : n4 == 16 ? 8 : 1;
+}
+
+__device__ __forceinline__ float dot_thread(const MatT &m, const float *__restrict__ w)
+{
+    if (m.V == 4) {
+        const float4 *w4 = reinterpret_cast<const float4 *>(w);
+        const float4 *x4 = reinterpret_cast<const float4 *>(m.xc);
+        switch (m.n4) {
+        case 1: return dot_regs<1, 1>(w4, x4);
+        case 2: return dot_regs<2, 2>(w4, x4);
+        case 4: return dot_regs<4, 4>(w4, x4);
+        case 8: return dot_regs<8, 8>(w4, x4);
+        case 16: return dot_regs<16, 8>(w4, x4);
+        case 5: return dot_regs<5, 1>(w4, x4);
+        default: {
+            float acc = 0.0f;
+            for (int i = 0; i < m.n4; ++i) {
+                const float4 ww = w4[i * WN_NT], xx = x4[i];
+                acc = ffma(ww.x, xx.x, acc);
+                acc = ffma(ww.y, xx.y, acc);
+                acc = ffma(ww.z, xx.z, acc);
+                acc = ffma(ww.w, xx.w, acc);
+            }
+            return acc;
+        }
+        }
+    }
+    float acc = 0.0f;
+    for (int i = 0; i < m.ch; ++i) acc = ffma(w[i * WN_NT], m.xc[i], acc);
+    return acc;
+}
+
+// All WN_NT threads must call it (warp shuffles inside).  epi(col, dot) runs on the lead lane of each column.
+template <class F>
+__device__ __forceinline__ void matvec(const MatT &m, F &&epi)
+{
+    for (int pass = 0; pass < m.npass; ++pass) {
+        float acc = m.smem ? dot_thread(m, m.ws + (size_t)pass * m.ch * WN_NT) : dot_thread(m, m.wg + (size_t)pass * m.ch * WN_NT);
+        for (int off = 1; off < m.tpc; off <<= 1) acc = fadd(acc, __shfl_xor_sync(FULL, acc, off));
+        const int col = pass * m.gpp + m.grp;
+        if (m.lead && col < m.ncols) epi(col, acc);
     }
 }
 
@@ -203,8 +286,9 @@ __device__ __forceinline__ float relu32(float v) { return v > 0.0f ? v : 0.0f; }
 
 // =============================================================================================
 // Layer CTA
-__device__ void layer_role(const WnParams &p, float *smem, int l, int m)
+__device__ void layer_role(const WnParams &p, int l, int m)
 {
+    float *smem = g_smem;
     const int tid = threadIdx.x;
     const int N = p.N, L = p.L, R = p.R, M = p.M, Dm = p.Dm, Sm = p.Sm;
     const int cta = l * M + m;
@@ -212,9 +296,6 @@ __device__ void layer_role(const WnParams &p, float *smem, int l, int m)
     __shared__ uint64_t bar;
     load_image_tma(smem, gimg, p.layer_smem_floats, &bar);
 
-    auto wptr = [&](const WnMat &mt) -> const float * { return mt.in_smem ? (smem + mt.off) : (gimg + mt.off); };
-    const float *w_cur = wptr(p.cur), *w_old = wptr(p.old), *w_lc = wptr(p.lc), *w_gc = wptr(p.gc);
-    const float *w_dense = wptr(p.dense), *w_skip = wptr(p.skip);
     // small vectors are always inside the resident prefix
     const float *bfg = smem + p.off_bfg, *bd = smem + p.off_bd, *bs = smem + p.off_bs;
 
@@ -228,6 +309,32 @@ __device__ void layer_role(const WnParams &p, float *smem, int l, int m)
     const int ncol2 = 2 * Dm;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
+    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+
+    // ---- per-thread views and indices, computed once ------------------------------------------------
+    const MatT mt_cur = make_matt(p.cur, gimg, xs_cur), mt_old = make_matt(p.old, gimg, xs_old);
+    const MatT mt_lc = make_matt(p.lc, gimg, lcs), mt_gc = make_matt(p.gc, gimg, gvec);
+    const MatT mt_dense = make_matt(p.dense, gimg, zs_dense), mt_skip = make_matt(p.skip, gimg, zs_skip);
+    const int xp_cur = (tid < R) ? xpad(p.cur, tid) : 0;
+    const int xp_old = (tid < R) ? xpad(p.old, tid) : 0;
+    const int xp_lc = (p.C && tid < p.C) ? xpad(p.lc, tid) : 0;
+    const int xp_zskip_gather = (tid < p.D) ? xpad(p.skip, tid) : 0;
+    const int g_mm = (tid < p.D) ? tid / Dm : 0, g_j = (tid < p.D) ? tid % Dm : 0;   // z gather source
+    // fg epilogue lane: column grp = 2*j + gate
+    const int fg_grp = mt_cur.grp;
+    const bool fg_valid = fg_grp < ncol2;
+    const bool fg_gate = (fg_grp & 1) != 0;
+    const bool fg_store = fg_valid && mt_cur.lead && !fg_gate;
+    const int fg_j = fg_grp >> 1;
+    const int xp_zd = fg_store ? xpad(p.dense, fg_j) : 0;
+    const int xp_zs = fg_store ? xpad(p.skip, m * Dm + fg_j) : 0;
+    const size_t rowx = (size_t)L * M * R, rowz = (size_t)L * M * Dm, rowa = (size_t)L * M * Sm;
+    const u64 *mbx_in = p.mb_x + ((size_t)l * M) * R + tid;
+    u64 *mbx_out = p.mb_x + ((size_t)(l + 1) * M + m) * R;
+    u64 *mbz_out = p.mb_z + ((size_t)l * M + m) * Dm + fg_j;
+    const u64 *mbz_in = p.mb_z + ((size_t)l * M + g_mm) * Dm + g_j;
+    const u64 *mba_in = p.mb_acc + ((size_t)(l > 0 ? l - 1 : 0) * M + m) * Sm;
+    u64 *mba_out = p.mb_acc + ((size_t)l * M + m) * Sm;
 
     // zero the padded vectors once (pad lanes are never read, but keep them defined)
     for (int i = tid; i < p.cur.xlen; i += WN_NT) xs_cur[i] = 0.0f;
@@ -244,19 +351,21 @@ __device__ void layer_role(const WnParams &p, float *smem, int l, int m)
             float v;
             if (d == 1) v = (tn == 0) ? 0.0f : xraw[tid];
             else v = __ldcg(ring_cta + ((size_t)b * d + (tn % d)) * R + tid);
-            xs_old[xpad(p.old, tid)] = v;
+            xs_old[xp_old] = v;
         }
         if (p.C && tid < p.C) {
             long idx = (long)tn - 1 - p.lc_shift;
             float v = 0.0f;
             if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) v = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * p.C + tid);
-            lcs[xpad(p.lc, tid)] = v;
+            lcs[xp_lc] = v;
         }
         __syncthreads();
-        matvec(p.old, w_old, xs_old, [&](int col, float dot) { pre[b * ncol2 + col] = fadd(bfgN[b * ncol2 + col], dot); });
+        float *pre_b = pre + b * ncol2;
+        const float *bias_b = bfgN + b * ncol2;
+        matvec(mt_old, [&](int col, float dot) { pre_b[col] = fadd(bias_b[col], dot); });
         if (p.C) {
             __syncthreads();
-            matvec(p.lc, w_lc, lcs, [&](int col, float dot) { pre[b * ncol2 + col] = fadd(pre[b * ncol2 + col], dot); });
+            matvec(mt_lc, [&](int col, float dot) { pre_b[col] = fadd(pre_b[col], dot); });
         }
         __syncthreads();
     };
@@ -266,7 +375,7 @@ __device__ void layer_role(const WnParams &p, float *smem, int l, int m)
         if (p.G) {
             if (tid < p.G) gvec[xpad(p.gc, tid)] = __ldg(p.gc_table + (size_t)p.gc_id[b] * p.G + tid);
             __syncthreads();
-            matvec(p.gc, w_gc, gvec, [&](int col, float dot) { bfgN[b * ncol2 + col] = fadd(bfg[col], dot); });
+            matvec(mt_gc, [&](int col, float dot) { bfgN[b * ncol2 + col] = fadd(bfg[col], dot); });
         } else {
             if (tid < ncol2) bfgN[b * ncol2 + tid] = bfg[tid];
         }
@@ -275,166 +384,231 @@ __device__ void layer_role(const WnParams &p, float *smem, int l, int m)
     }
 
     // ---- main loop
-    const int grp = tid / p.cur.t, chunk = tid % p.cur.t;
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
             if (t >= p.T_row[b]) continue;
+            pf.start();
             // 1. wait for the layer input: sum of the partial residual outputs of layer l-1
             if (tid < R) {
                 float q[4];
-                ll_wait_n(p.mb_x + (((size_t)b * L + l) * M) * R + tid, (size_t)R, nin, seq, ab, q);
+                ll_wait_n(mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
                 float v = q[0];
                 for (int i = 1; i < nin; ++i) v = fadd(v, q[i]);
-                xs_cur[xpad(p.cur, tid)] = v;
+                xs_cur[xp_cur] = v;
                 xraw[tid] = v;
             }
             if (__syncthreads_or(ab.flag)) return;
+            pf.mark(0);
 
             // 2. filter/gate for the current tap + gated activation (model.py:68-69,86)
             {
-                float acc = 0.0f;
-                const float *xc = xs_cur + chunk * p.cur.xstride;
-                if (p.cur.V == 4) {
-                    const float4 *w4 = reinterpret_cast<const float4 *>(w_cur) + tid;
-                    const float4 *x4 = reinterpret_cast<const float4 *>(xc);
-                    const int n4 = p.cur.ch >> 2;
-#pragma unroll 8
-                    for (int i = 0; i < n4; ++i) {
-                        float4 wv = w4[(size_t)i * WN_NT];
-                        float4 xv = x4[i];
-                        acc = ffma(wv.x, xv.x, acc);
-                        acc = ffma(wv.y, xv.y, acc);
-                        acc = ffma(wv.z, xv.z, acc);
-                        acc = ffma(wv.w, xv.w, acc);
-                    }
-                } else {
-                    const float *w1 = w_cur + tid;
-                    for (int i = 0; i < p.cur.ch; ++i) acc = ffma(w1[(size_t)i * WN_NT], xc[i], acc);
-                }
-                for (int off = 1; off < p.cur.t; off <<= 1) acc = fadd(acc, __shfl_xor_sync(FULL, acc, off));
-                const bool valid = grp < ncol2;
-                float pv = valid ? pre[b * ncol2 + grp] : 0.0f;
+                float acc = mt_cur.smem ? dot_thread(mt_cur, mt_cur.ws) : dot_thread(mt_cur, mt_cur.wg);
+                for (int off = 1; off < mt_cur.tpc; off <<= 1) acc = fadd(acc, __shfl_xor_sync(FULL, acc, off));
+                float pv = fg_valid ? pre[b * ncol2 + fg_grp] : 0.0f;
                 float fg = fadd(pv, acc);
-                const bool is_gate = (grp & 1) != 0;
-                float a = act_fg(fg, is_gate);
-                float other = __shfl_xor_sync(FULL, a, p.cur.t);   // partner column (filter <-> gate)
-                if (valid && chunk == 0 && !is_gate) {
+                float a = act_fg(fg, fg_gate);
+                float other = __shfl_xor_sync(FULL, a, mt_cur.tpc);   // partner column (filter <-> gate)
+                if (fg_store) {
                     float z = fmul(a, other);
-                    int j = grp >> 1;
-                    zs_dense[xpad(p.dense, j)] = z;
-                    zs_skip[xpad(p.skip, m * Dm + j)] = z;
-                    if (M > 1) ll_post(p.mb_z + (((size_t)b * L + l) * M + m) * Dm + j, z, seq);
+                    zs_dense[xp_zd] = z;
+                    zs_skip[xp_zs] = z;
+                    if (M > 1) ll_post(mbz_out + b * rowz, z, seq);
                 }
             }
             __syncthreads();
+            pf.mark(1);
 
             // 3. partial dense 1x1 + residual (model.py:89,98-101) -> mailbox of layer l+1
             if (l + 1 < L) {
-                u64 *dst = p.mb_x + (((size_t)b * L + (l + 1)) * M + m) * R;
-                matvec(p.dense, w_dense, zs_dense, [&](int r, float dot) {
+                u64 *dst = mbx_out + b * rowx;
+                matvec(mt_dense, [&](int r, float dot) {
                     float v = (m == 0) ? fadd(fadd(xraw[r], bd[r]), dot) : dot;
                     ll_post(dst + r, v, seq);
                 });
             }
+            pf.mark(2);
             // ---- everything below is off the sample-to-sample critical chain ----
             // 4. push x_l(t) into the private dilation-queue ring (model.py:145)
             if (d >= 2 && tid < R) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + tid, xraw[tid]);
             // 5. gather the sibling CTAs' gated activations
-            if (M > 1 && tid < p.D) {
-                int mm = tid / Dm;
-                if (mm != m) {
-                    float z = ll_wait(p.mb_z + (((size_t)b * L + l) * M + mm) * Dm + (tid % Dm), seq, ab);
-                    zs_skip[xpad(p.skip, tid)] = z;
-                }
-            }
+            if (M > 1 && tid < p.D && g_mm != m) zs_skip[xp_zskip_gather] = ll_wait(mbz_in + b * rowz, seq, ab);
             if (__syncthreads_or(ab.flag)) return;
+            pf.mark(3);
             // 6. skip 1x1 (model.py:94-96) + running sum over layers (model.py:157)
             {
-                const u64 *src = (l > 0) ? p.mb_acc + (((size_t)b * L + (l - 1)) * M + m) * Sm : nullptr;
-                u64 *dst = p.mb_acc + (((size_t)b * L + l) * M + m) * Sm;
-                matvec(p.skip, w_skip, zs_skip, [&](int c, float dot) {
+                const u64 *src = mba_in + b * rowa;
+                u64 *dst = mba_out + b * rowa;
+                matvec(mt_skip, [&](int c, float dot) {
                     float v = fadd(bs[c], dot);
                     if (l > 0) v = fadd(ll_wait(src + c, seq, ab), v);
                     ll_post(dst + c, v, seq);
                 });
             }
+            pf.mark(4);
             // 7. pre-activations of the next step
             if (t + 1 < p.T_row[b]) compute_pre(b, t + 1);
             else __syncthreads();
             if (__syncthreads_or(ab.flag)) return;
+            pf.mark(5);
         }
     }
 }
 
 // =============================================================================================
 // Tail CTA: relu -> conv1 (S->S) -> relu -> partial conv2 (model.py:158-165)
-__device__ void tail_role(const WnParams &p, float *smem, int mt)
+__device__ void tail_role(const WnParams &p, int mt)
 {
+    float *smem = g_smem;
     const int tid = threadIdx.x;
     const int N = p.N, L = p.L, M = p.M, Sm = p.Sm, S = p.S;
     const float *gimg = p.tail_img + (size_t)mt * p.tail_img_floats;
     __shared__ uint64_t bar;
     load_image_tma(smem, gimg, p.tail_smem_floats, &bar);
-    const float *w1 = p.post1.in_smem ? smem + p.post1.off : gimg + p.post1.off;
-    const float *w2 = p.post2.in_smem ? smem + p.post2.off : gimg + p.post2.off;
     const float *b1 = smem + p.off_b1;
     float *sc = smem + p.tail_smem_floats;
     float *as1 = sc + p.ts.as1, *c1s = sc + p.ts.c1s;
     for (int i = tid; i < p.post1.xlen; i += WN_NT) as1[i] = 0.0f;
     for (int i = tid; i < p.post2.xlen; i += WN_NT) c1s[i] = 0.0f;
     __syncthreads();
+    const MatT mt_p1 = make_matt(p.post1, gimg, as1), mt_p2 = make_matt(p.post2, gimg, c1s);
+    // this thread polls acc words c = tid, tid + NT, ... (at most 4 supported per thread, else loop)
+    const size_t rowa = (size_t)L * M * Sm;
+    const u64 *src0 = p.mb_acc + ((size_t)(L - 1) * M) * Sm;   // [M][Sm] == S contiguous words
+    u64 *dst0 = p.mb_c2 + (size_t)mt * p.O;
+    const int xp1_lead = mt_p1.lead ? xpad(p.post2, mt_p1.grp < p.St ? mt_p1.grp : 0) : 0;   // single pass: col == grp
     Abort ab{p.status, 0};
+    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
             if (t >= p.T_row[b]) continue;
-            const u64 *src = p.mb_acc + (((size_t)b * L + (L - 1)) * M) * Sm;   // [M][Sm] == S contiguous words
+            pf.start();
+            const u64 *src = src0 + b * rowa;
             for (int c = tid; c < S; c += WN_NT) as1[xpad(p.post1, c)] = relu32(ll_wait(src + c, seq, ab));
             if (__syncthreads_or(ab.flag)) return;
-            matvec(p.post1, w1, as1, [&](int c, float dot) { c1s[xpad(p.post2, c)] = relu32(fadd(b1[c], dot)); });
+            pf.mark(0);
+            if (mt_p1.npass == 1)
+                matvec(mt_p1, [&](int c, float dot) { c1s[xp1_lead] = relu32(fadd(b1[c], dot)); });
+            else
+                matvec(mt_p1, [&](int c, float dot) { c1s[xpad(p.post2, c)] = relu32(fadd(b1[c], dot)); });
             __syncthreads();
-            u64 *dst = p.mb_c2 + ((size_t)b * p.Mt + mt) * p.O;
-            matvec(p.post2, w2, c1s, [&](int o, float dot) { ll_post(dst + o, dot, seq); });
+            pf.mark(1);
+            u64 *dst = dst0 + (size_t)b * p.Mt * p.O;
+            matvec(mt_p2, [&](int o, float dot) { ll_post(dst + o, dot, seq); });
             __syncthreads();
+            pf.mark(2);
         }
     }
 }
 
+// float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231).
+// Called by every thread of the sampler CTA; returns the drawn id (as float) to all of them.
+__device__ float mulaw_draw_cta(const float *c2s, int Q, float temperature, double u64v, float *misc, double *red, double *cdf)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231)
+    const int nw = Q >> 5;
+    const bool act = tid < Q;
+    float c = act ? c2s[tid] : __int_as_float(0xff800000);
+    float mx = c;
+    for (int off = 1; off < 32; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, off));
+    if (lane == 0) misc[8 + warp] = mx;
+    __syncthreads();
+    mx = misc[8];
+    for (int w = 1; w < nw; ++w) mx = fmaxf(mx, misc[8 + w]);
+    double e = act ? wn::exp64((double)c - (double)mx) : 0.0;
+    double sum = e;
+    for (int off = 1; off < 32; off <<= 1) sum = __dadd_rn(sum, __shfl_xor_sync(FULL, sum, off));
+    if (lane == 0 && act) red[warp] = sum;
+    __syncthreads();
+    if (warp == 0) {      // levels 32, 64, 128 of the butterfly: lanes 0..nw-1 hold the warp sums
+        double v = (lane < nw) ? red[lane] : 0.0;
+        for (int off = 1; off < nw; off <<= 1) v = __dadd_rn(v, __shfl_xor_sync(FULL, v, off));
+        if (lane == 0) red[8] = v;
+    }
+    __syncthreads();
+    const double den = red[8];
+    float pr = act ? (float)__ddiv_rn(e, den) : 0.0f;
+    float s = fdiv(wn::log32(pr), temperature);
+    float a = s;
+    for (int off = 1; off < 32; off <<= 1) {
+        float o = __shfl_xor_sync(FULL, a, off);
+        a = (lane & off) ? wn::logaddexp32(o, a) : wn::logaddexp32(a, o);
+    }
+    if (lane == 0 && act) misc[16 + warp] = a;
+    __syncthreads();
+    if (warp == 0) {
+        float v = (lane < nw) ? misc[16 + lane] : 0.0f;
+        for (int off = 1; off < nw; off <<= 1) {
+            float o = __shfl_xor_sync(FULL, v, off);
+            v = (lane & off) ? wn::logaddexp32(o, v) : wn::logaddexp32(v, o);
+        }
+        if (lane == 0) misc[1] = v;
+    }
+    __syncthreads();
+    const float lse = misc[1];
+    // cumulative sum of float64(q), pinned order: Kogge-Stone scan inside each block of 32
+    // (v_j += v_{j-off}, off = 1..16), block totals added left to right as the block's base.
+    double v = act ? (double)wn::exp32(fsub(s, lse)) : 0.0;
+    for (int off = 1; off < 32; off <<= 1) {
+        double o = __shfl_up_sync(FULL, v, off);
+        if (lane >= off) v = __dadd_rn(v, o);
+    }
+    if (lane == 31 && act) red[warp] = v;
+    __syncthreads();
+    if (warp > 0) {
+        double base = red[0];
+        for (int w = 1; w < warp; ++w) base = __dadd_rn(base, red[w]);
+        v = __dadd_rn(base, v);
+    }
+    if (tid == Q - 1) cdf[0] = v;
+    __syncthreads();
+    const double total = cdf[0];
+    int pred = act && (__ddiv_rn(v, total) <= u64v);      // searchsorted(side='right')
+    int cnt = __syncthreads_count(pred);
+    if (cnt > Q - 1) cnt = Q - 1;
+    return (float)cnt;
+}
+
 // =============================================================================================
 // Sampler CTA
-__device__ void sampler_role(const WnParams &p, float *smem)
+__device__ void sampler_role(const WnParams &p)
 {
+    float *smem = g_smem;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, R = p.R, O = p.O, Q = p.Q, nr = p.nr_mix, ifw = p.ifw;
     const float *gimg = p.samp_img;
     __shared__ uint64_t bar;
     load_image_tma(smem, gimg, p.samp_smem_floats, &bar);
-    const float *w_c = p.causal.in_smem ? smem + p.causal.off : gimg + p.causal.off;
     const float *b2 = smem + p.off_b2;
     float *sc = smem + p.samp_smem_floats;
     float *c2s = sc + p.ss.c2s, *cq = sc + p.ss.cq, *cqx = sc + p.ss.cqx, *qs = sc + p.ss.qs;
     int *ids = reinterpret_cast<int *>(sc + p.ss.ids);
     double *cdf = reinterpret_cast<double *>(sc + p.ss.cdf);
     double *red = reinterpret_cast<double *>(sc + p.ss.red);     // 16 doubles
-    float *misc = sc + p.ss.misc;                                 // [0] sample
+    float *misc = sc + p.ss.misc;                                 // 32 floats
     Abort ab{p.status, 0};
+    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
 
     for (int i = tid; i < N * ifw; i += WN_NT) cq[i] = 0.0f;
     for (int i = tid; i < p.causal.xlen; i += WN_NT) cqx[i] = 0.0f;
     for (int i = tid; i < 2 * N; i += WN_NT) ids[i] = -1;
     __syncthreads();
+    const MatT mt_c = make_matt(p.causal, gimg, cqx);
+    const int xp_cq = (p.scalar_input && tid < ifw) ? xpad(p.causal, tid) : 0;
+    const size_t rowx = (size_t)p.L * p.M * R;
 
     // push x_in into row b's causal queue, run the causal conv, post to layer 0 with tag seq
     auto feed = [&](int b, float x_in, unsigned seq) {
-        u64 *dst = p.mb_x + (((size_t)b * p.L + 0) * p.M + 0) * R;
+        u64 *dst = p.mb_x + b * rowx;
         if (p.scalar_input) {
             float v = 0.0f;
             if (tid < ifw) v = (tid < ifw - 1) ? cq[b * ifw + tid + 1] : x_in;
             __syncthreads();
-            if (tid < ifw) { cq[b * ifw + tid] = v; cqx[xpad(p.causal, tid)] = v; }
+            if (tid < ifw) { cq[b * ifw + tid] = v; cqx[xp_cq] = v; }
             __syncthreads();
-            matvec(p.causal, w_c, cqx, [&](int r, float dot) { ll_post(dst + r, dot, seq); });
+            matvec(mt_c, [&](int r, float dot) { ll_post(dst + r, dot, seq); });
         } else {
             int prev = ids[2 * b + 1];
             int cur = (int)x_in;
@@ -456,6 +630,7 @@ __device__ void sampler_role(const WnParams &p, float *smem)
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
             if (t >= p.T_row[b]) continue;
+            pf.start();
             // prefetch this step's uniforms and the next forced input while the network runs
             float gum = 0.0f, logistic = 0.0f, next_forced = 0.0f;
             double u64v = 0.0;
@@ -483,6 +658,7 @@ __device__ void sampler_role(const WnParams &p, float *smem)
                 if (p.out_logits) p.out_logits[((size_t)b * p.T + t) * O + tid] = v;
             }
             if (__syncthreads_or(ab.flag)) return;
+            pf.mark(0);
 
             float sample;
             if (p.scalar_input) {
@@ -509,88 +685,64 @@ __device__ void sampler_role(const WnParams &p, float *smem)
                 __syncthreads();
                 sample = misc[0];
             } else {
-                // float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231)
-                const int nw = Q >> 5;
-                const bool act = tid < Q;
-                float c = act ? c2s[tid] : __int_as_float(0xff800000);
-                float mx = c;
-                for (int off = 1; off < 32; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, off));
-                if (lane == 0) misc[8 + warp] = mx;
-                __syncthreads();
-                mx = misc[8];
-                for (int w = 1; w < nw; ++w) mx = fmaxf(mx, misc[8 + w]);
-                double e = act ? wn::exp64((double)c - (double)mx) : 0.0;
-                double sum = e;
-                for (int off = 1; off < 32; off <<= 1) sum = __dadd_rn(sum, __shfl_xor_sync(FULL, sum, off));
-                if (lane == 0 && act) red[warp] = sum;
-                __syncthreads();
-                double arr[8];
-#pragma unroll
-                for (int w = 0; w < 8; ++w) arr[w] = (w < nw) ? red[w] : 0.0;
-                for (int off = 1; off < nw; off <<= 1) {
-                    double nx[8];
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) nx[w] = (w < nw) ? __dadd_rn(arr[w], arr[(w ^ off) & 7]) : 0.0;
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) arr[w] = nx[w];
-                }
-                const double den = arr[0];
-                float pr = act ? (float)__ddiv_rn(e, den) : 0.0f;
-                float s = fdiv(wn::log32(pr), p.temperature);
-                float a = s;
-                for (int off = 1; off < 32; off <<= 1) {
-                    float o = __shfl_xor_sync(FULL, a, off);
-                    a = (lane & off) ? wn::logaddexp32(o, a) : wn::logaddexp32(a, o);
-                }
-                __syncthreads();                     // red/misc reuse
-                if (lane == 0 && act) misc[16 + warp] = a;
-                __syncthreads();
-                float fa[8];
-#pragma unroll
-                for (int w = 0; w < 8; ++w) fa[w] = (w < nw) ? misc[16 + w] : 0.0f;
-                for (int off = 1; off < nw; off <<= 1) {
-                    float nx[8];
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        int o = (w ^ off) & 7;
-                        nx[w] = (w < nw) ? ((w < o) ? wn::logaddexp32(fa[w], fa[o]) : wn::logaddexp32(fa[o], fa[w])) : 0.0f;
-                    }
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) fa[w] = nx[w];
-                }
-                const float lse = fa[0];
-                if (act) qs[tid] = wn::exp32(fsub(s, lse));
-                __syncthreads();
-                if (tid == 0) {
-                    double accd = 0.0;
-                    for (int j = 0; j < Q; ++j) { accd = __dadd_rn(accd, (double)qs[j]); cdf[j] = accd; }   // np.cumsum
-                    red[8] = accd;
-                }
-                __syncthreads();
-                const double total = red[8];
-                int pred = act && (__ddiv_rn(cdf[tid < Q ? tid : 0], total) <= u64v);
-                int cnt = __syncthreads_count(pred);
-                if (cnt > Q - 1) cnt = Q - 1;
-                sample = (float)cnt;
+                sample = mulaw_draw_cta(c2s, Q, p.temperature, u64v, misc, red, cdf);
             }
+            pf.mark(1);
             if (tid == 0) p.out_samples[(size_t)b * p.T + t] = sample;
             if (has_next) feed(b, (t + 1 < p.n_forced) ? next_forced : sample, seq + 1u);
             else __syncthreads();
+            pf.mark(2);
         }
     }
 }
 
+#include "wn_kernel_static.cuh"
+
+// LL-mailbox ping-pong between CTA 0 and CTA 1: average round trip in clock cycles (diagnostic).
+__device__ void pingpong_role(u64 *box, int iters, long long *out)
+{
+    const int me = blockIdx.x;
+    if (threadIdx.x != 0 || me > 1) return;
+    u64 *mine = box + me * 16, *theirs = box + (1 - me) * 16;
+    long long t0 = clock64();
+    for (int i = 1; i <= iters; ++i) {
+        if (me == 0) {
+            ll_post(theirs, 1.0f, (unsigned)i);
+            while ((unsigned)(ld_relaxed_u64(mine) >> 32) != (unsigned)i) {}
+        } else {
+            while ((unsigned)(ld_relaxed_u64(mine) >> 32) != (unsigned)i) {}
+            ll_post(theirs, 1.0f, (unsigned)i);
+        }
+    }
+    if (me == 0) out[0] = (clock64() - t0) / iters;
+}
+
 }  // namespace
+
+extern "C" __global__ void wn_pingpong_kernel(unsigned long long *box, int iters, long long *out)
+{
+    pingpong_role(box, iters, out);
+}
 
 // =============================================================================================
 extern "C" __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel(const __grid_constant__ WnParams p)
 {
-    extern __shared__ __align__(128) float smem[];
     const int cta = blockIdx.x;
     const int n_layer = p.L * p.M;
-    if (cta < n_layer) layer_role(p, smem, cta / p.M, cta % p.M);
-    else if (cta < n_layer + p.Mt) tail_role(p, smem, cta - n_layer);
-    else sampler_role(p, smem);
+    if (cta < n_layer) layer_role(p, cta / p.M, cta % p.M);
+    else if (cta < n_layer + p.Mt) tail_role(p, cta - n_layer);
+    else sampler_role(p);
+}
+
+template <class SH>
+__global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel_s(const __grid_constant__ WnParams p)
+{
+    const int cta = blockIdx.x;
+    constexpr int n_layer_per = SH::M;
+    const int n_layer = p.L * n_layer_per;
+    if (cta < n_layer) layer_role_s<SH>(p, cta / n_layer_per, cta % n_layer_per);
+    else if (cta < n_layer + SH::Mt) tail_role_s<SH>(p, cta - n_layer);
+    else sampler_role_s<SH>(p);
 }
 
 // create_upsample stage (wavenet/model.py:102-111): one conv2d_transpose(kernel (F,2), strides (F,1), 'same')

@@ -6,7 +6,8 @@
 #define WN_NT 256                 // threads per CTA (8 warps), every role
 
 // A matrix packed "thread-major" for one CTA: ncols dot products of length K.
-// Thread tid handles column (pass*gpp + tid/t) and the contiguous k-chunk (tid % t) of length ch = K/t.
+// Thread tid handles column (pass*gpp + tid/t) and the contiguous k-chunk (tid % t) of length ch = K/t,
+// which it evaluates as u consecutive sub-chains (canonical chunks (tid%t)*u .. (tid%t)*u + u-1 of length ch/u).
 // Packed layout (V = 4):  w[((pass*(ch/4) + i4)*WN_NT + tid)*4 + j] = W[chunk*ch + 4*i4 + j][col]
 //               (V = 1):  w[(pass*ch + i)*WN_NT + tid]              = W[chunk*ch + i][col]
 // so that every warp-wide load is one fully coalesced, bank-conflict-free 512 B / 128 B access.
@@ -21,7 +22,7 @@ struct WnMat {
     int32_t xstride;
     int32_t xlen;       // t * xstride: floats of the padded input vector
     int32_t in_smem;    // 1: resident in shared memory, 0: read from the global image (overflow)
-    int32_t pad_;
+    int32_t u;          // independent fma sub-chains per thread; the canonical plan uses t*u chunks per column
 };
 
 // Shared-memory float offsets of the per-role scratch vectors (after the resident image prefix).
@@ -78,4 +79,5 @@ struct WnParams {
     float *out_samples;
     float *out_logits;
     int32_t *status;               // [0] abort flag, [1] cta that raised it, [2] code
+    long long *prof;               // optional [grid][16] phase cycle counters (diagnostics), or null
 };

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_layout():
-    assert C.sizeof(_lib.WnConfig) == 4 * (15 + _lib.WN_MAX_UPSAMPLE + _lib.WN_MAX_LAYERS + 2)
+    assert C.sizeof(_lib.WnConfig) == 4 * (15 + _lib.WN_MAX_UPSAMPLE + _lib.WN_MAX_LAYERS + 3)
     assert C.sizeof(_lib.WnPlan) == 44
 
 
@@ -60,11 +60,15 @@ def test_host_side_planning():
     assert (info['grid'], info['M'], info['Mt'], info['threads']) == (137, 4, 16, 256)
     assert info['p_hot'] == 5347102 and info['weights_in_global'] == 0
     assert info['smem_bytes_layer'] <= 227 * 1024
-    assert plan['M'] == 4 and plan['Mt'] == 16
+    assert plan['M'] == 4 and plan['Mt'] == 16 and info['static_shape'] == 1
     plan, info = plan_config(**synth.cfg1())
-    assert info['p_hot'] == 615168 and info['grid'] == 27
+    assert info['p_hot'] == 615168 and info['grid'] == 27 and info['static_shape'] == 2
     plan, info = plan_config(**synth.cfg_hparams_default())
-    assert info['p_hot'] == 1640670 and info['M'] == 1 and info['grid'] == 67
+    assert info['p_hot'] == 1640670 and info['M'] == 1 and info['grid'] == 67 and info['static_shape'] == 3
+    _, info = plan_config(generic_kernel=True, **synth.cfg2())
+    assert info['static_shape'] == 0
+    _, info = plan_config(**synth.tiny_mol())
+    assert info['static_shape'] == 0                    # unknown shapes run the runtime-shaped kernel
     # fewer SMs: the split shrinks instead of failing; too few SMs is an error
     _, small = plan_config(sm_count=80, **synth.cfg2())
     assert small['grid'] <= 80
@@ -84,7 +88,7 @@ def test_packing_is_a_permutation():
         plan, _ = plan_config(**kw)
         D, R, S = kw['dilation_channels'], kw['residual_channels'], kw['skip_channels']
         assert D % plan['M'] == 0 and S % plan['Mt'] == 0
-        assert R % plan['t_cur'] == 0 and plan['t_cur'] == plan['t_old'] and plan['t_cur'] <= 16
+        assert R % plan['t_cur'] == 0 and plan['t_cur'] == plan['t_old'] and plan['t_cur'] <= 64
         assert (D // plan['M']) % plan['t_dense'] == 0 and D % plan['t_skip'] == 0
         assert S % plan['t_post1'] == 0 and (S // plan['Mt']) % plan['t_post2'] == 0
 

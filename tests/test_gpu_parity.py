@@ -94,12 +94,31 @@ def test_cfg2_batch8_bit_exact_and_tolerance():
     kw = synth.cfg2(8)
     net, om, inp, got, exp, (lc_t, lc_o) = run_both(kw, 260)
     info = net.info()
-    assert (info['grid'], info['M'], info['Mt']) == (137, 4, 16) and info['weights_in_global'] == 0
+    assert (info['grid'], info['M'], info['Mt']) == (137, 4, 16) and info['weights_in_global'] == 0 and info['static_shape'] == 1
     assert_exact(got, exp)
     assert np.all(np.abs(got[0]) <= 1.0)
     forced = np.concatenate([inp['x0'], got[0][:, :-1]], axis=1)
     _, lnat = om.generate(260, forced, inp['uniforms'], lc_up=lc_o, gc_ids=inp['gc_ids'], want_logits=True)
     assert np.max(np.abs(lnat - got[1])) < 1e-4          # float MoL logits within 1e-4 (north_star)
+
+
+@pytest.mark.parametrize('fac,T,shape', [(lambda: synth.cfg2(3), 150, 1), (synth.cfg1, 600, 2), (lambda: synth.cfg_hparams_default(2), 200, 3)])
+def test_runtime_shaped_kernel_equals_specialised_kernel(fac, T, shape):
+    # the compile-time specialised instantiations and the generic kernel implement the same plan
+    kw = fac()
+    net_s, w = build(kw)
+    net_g, _ = build(kw, generic_kernel=True)
+    assert net_s.info()['static_shape'] == shape and net_g.info()['static_shape'] == 0
+    assert net_s.plan() == net_g.plan()
+    inp = make_inputs(kw, T)
+    lc = net_s.create_upsample(inp['mel']) if 'mel' in inp else None
+    a = net_s.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    b = net_g.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    om = oracle_model(kw, w)
+    so = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc.cpu().numpy() if lc is not None else None,
+                     gc_ids=inp['gc_ids'], plan=plan_from_dict(net_g.plan()))
+    assert np.array_equal(so, b[0].cpu().numpy())
 
 
 def test_hparams_default_model_bit_exact():
