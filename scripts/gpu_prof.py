@@ -20,6 +20,9 @@ def prof(name, kw, T):
     lc = net.create_upsample(inp['mel']) if 'mel' in inp else None
     info = net.info(); grid = info['grid']; N = kw['batch_size']
     net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], sync=False); e1.record(); torch.cuda.synchronize()
+    print('%s N=%d unprofiled: %.2f us/step (%.0f samples/s)' % (name, N, 1e3 * e0.elapsed_time(e1) / T, N * T / e0.elapsed_time(e1) * 1e3))
     lib.wn_debug_profile(net._h, 1, None, 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], sync=False); e1.record(); torch.cuda.synchronize()
@@ -41,6 +44,7 @@ def prof(name, kw, T):
     print('  layer busy cycles per row-step %.0f; chain part (fg+dense) %.0f' % (busy, lay[:, :, 1:3].sum(axis=2).mean()))
 
 
-prof('cfg2', synth.cfg2(1), 3000)
+import time
+prof("cfg2", synth.cfg2(1), 3000)
 prof('cfg2', synth.cfg2(8), 3000)
 prof('cfg1', synth.cfg1(1), 4000)

@@ -659,6 +659,23 @@ long long wn_debug_pingpong(int iters)
     return host;
 }
 
+/* Diagnostics: round trips of CTA 0 with each of grid-1 partners; out has 2*grid entries. */
+int wn_debug_pingpong_all(int grid, int iters, int mode, long long *out_host)
+{
+    unsigned long long *box = nullptr;
+    long long *out = nullptr;
+    size_t bb = (size_t)grid * 2 * 32 * 8 + 512;
+    if (cudaMalloc(&box, bb) != cudaSuccess || cudaMalloc(&out, (size_t)grid * 2 * 8) != cudaSuccess) return -1;
+    cudaMemset(box, 0, bb);
+    cudaMemset(out, 0, (size_t)grid * 2 * 8);
+    void *args[] = {&box, &iters, &out, &mode};
+    if (cudaLaunchCooperativeKernel((const void *)wn_pingpong_all_kernel, dim3(grid), dim3(32), args, 0, 0) != cudaSuccess) return -2;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+    cudaMemcpy(out_host, out, (size_t)grid * 2 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(box); cudaFree(out);
+    return 0;
+}
+
 int wn_sync_check(wn_handle *h, void *stream)
 {
     if (!h) return WN_ERR_ARG;

@@ -61,16 +61,42 @@ __device__ __forceinline__ int ld_volatile_i32(const int *p)
     return v;
 }
 
-// optional phase profile: prof[cta*16 + phase] accumulates clock64() deltas of thread 0
+// optional phase profile: per-phase clock64() deltas of thread 0, accumulated in REGISTERS (a global
+// read-modify-write per mark would stall the warp for an L2 round trip and distort what it measures)
+// and written to prof[cta*16 + phase] once, when the role returns normally.
 struct Prof {
     long long *slot;
     long long last;
-    __device__ __forceinline__ void start() { if (slot && threadIdx.x == 0) last = clock64(); }
+    long long acc[12];
+    __device__ __forceinline__ Prof(long long *s) : slot(s), last(0) { for (int i = 0; i < 12; ++i) acc[i] = 0; }
+    __device__ __forceinline__ void start() { if (slot) last = clock64(); }
     __device__ __forceinline__ void mark(int phase)
     {
-        if (slot && threadIdx.x == 0) { long long now = clock64(); slot[phase] += now - last; last = now; }
+        if (slot) { long long now = clock64(); acc[phase] += now - last; last = now; }
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (slot && threadIdx.x == 0)
+            for (int i = 0; i < 12; ++i) slot[i] = acc[i];
     }
 };
+
+// prefetch helpers: volatile asm keeps these loads (and, through pin(), what is computed from them)
+// ahead of the volatile polling loads, so their latency overlaps the wait instead of following it
+__device__ __forceinline__ float ld_nc_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_nc_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void pin(float &v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
 
 struct Abort {
     int32_t *status;
@@ -309,7 +335,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
     const int ncol2 = 2 * Dm;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     // ---- per-thread views and indices, computed once ------------------------------------------------
     const MatT mt_cur = make_matt(p.cur, gimg, xs_cur), mt_old = make_matt(p.old, gimg, xs_old);
@@ -453,6 +479,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
             pf.mark(5);
         }
     }
+    pf.flush();
 }
 
 // =============================================================================================
@@ -478,7 +505,7 @@ __device__ void tail_role(const WnParams &p, int mt)
     u64 *dst0 = p.mb_c2 + (size_t)mt * p.O;
     const int xp1_lead = mt_p1.lead ? xpad(p.post2, mt_p1.grp < p.St ? mt_p1.grp : 0) : 0;   // single pass: col == grp
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
@@ -500,6 +527,7 @@ __device__ void tail_role(const WnParams &p, int mt)
             pf.mark(2);
         }
     }
+    pf.flush();
 }
 
 // float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231).
@@ -589,7 +617,7 @@ __device__ void sampler_role(const WnParams &p)
     double *red = reinterpret_cast<double *>(sc + p.ss.red);     // 16 doubles
     float *misc = sc + p.ss.misc;                                 // 32 floats
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     for (int i = tid; i < N * ifw; i += WN_NT) cq[i] = 0.0f;
     for (int i = tid; i < p.causal.xlen; i += WN_NT) cqx[i] = 0.0f;
@@ -636,13 +664,14 @@ __device__ void sampler_role(const WnParams &p)
             double u64v = 0.0;
             if (p.scalar_input) {
                 const float *u = (const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1);
-                if (warp == 0 && lane < nr) gum = wn::log32(-wn::log32(__ldg(u + lane)));
-                if (tid == 0) { float u2 = __ldg(u + nr); logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
+                if (warp == 0 && lane < nr) gum = wn::log32(-wn::log32(ld_nc_f32(u + lane)));
+                if (tid == 0) { float u2 = ld_nc_f32(u + nr); logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
             } else {
-                u64v = __ldg((const double *)p.uniforms + (size_t)b * p.T + t);
+                u64v = ld_nc_f64((const double *)p.uniforms + (size_t)b * p.T + t);
             }
             const bool has_next = (t + 1 < p.T_row[b]);
-            if (has_next && t + 1 < p.n_forced) next_forced = __ldg(p.forced + (size_t)b * p.n_forced + t + 1);
+            if (has_next && t + 1 < p.n_forced) next_forced = ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1);
+            pin(gum); pin(logistic); pin(next_forced); pin(u64v);
 
             // conv2 output: bias + the Mt partial sums in order
             if (tid < O) {
@@ -694,6 +723,7 @@ __device__ void sampler_role(const WnParams &p)
             pf.mark(2);
         }
     }
+    pf.flush();
 }
 
 #include "wn_kernel_static.cuh"
@@ -722,6 +752,60 @@ __device__ void pingpong_role(u64 *box, int iters, long long *out)
 extern "C" __global__ void wn_pingpong_kernel(unsigned long long *box, int iters, long long *out)
 {
     pingpong_role(box, iters, out);
+}
+
+// Diagnostic: CTA 0 ping-pongs with every other CTA in turn; out[k] = round trip cycles with CTA k,
+// out[grid + k] = SM id of CTA k.  mode 0: ld.relaxed.gpu / st.relaxed.gpu, 1: ld.volatile / st.volatile,
+// 2: ld.global.cg / st.global.cg, 3: relaxed with 4 staggered poller lanes.
+extern "C" __global__ void wn_pingpong_all_kernel(unsigned long long *box, int iters, long long *out, int mode)
+{
+    const int me = blockIdx.x, G = gridDim.x;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0) out[G + me] = smid;
+    auto ld = [&](const u64 *p) -> u64 {
+        u64 v;
+        if (mode == 1) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        else if (mode == 2) asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+    };
+    auto st = [&](u64 *p, u64 v) {
+        if (mode == 1) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+        else if (mode == 2) asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+        else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    };
+    // mailbox pair for partner k: box[(2k)*32] (to CTA k) and box[(2k+1)*32] (to CTA 0), 256 B apart
+    const int lane = threadIdx.x;
+    if (me == 0) {
+        for (int k = 1; k < G; ++k) {
+            u64 *to = box + (size_t)(2 * k) * 32, *from = box + (size_t)(2 * k + 1) * 32;
+            long long t0 = clock64();
+            for (int i = 1; i <= iters; ++i) {
+                if (lane == 0) st(to, (u64)i);
+                if (mode == 3) {
+                    // lanes 0..3 poll the same word, started a quarter period apart
+                    bool seen = false;
+                    if (lane < 4) { for (int w = 0; w < lane * 8; ++w) __nanosleep(0); }
+                    while (true) {
+                        if (lane < 4 && !seen) seen = (ld(from) == (u64)i);
+                        if (__any_sync(0xffffffffu, seen)) break;
+                    }
+                } else if (lane == 0) {
+                    while (ld(from) != (u64)i) {}
+                }
+                __syncwarp();
+            }
+            if (lane == 0) out[k] = (clock64() - t0) / iters;
+        }
+    } else {
+        u64 *mine = box + (size_t)(2 * me) * 32, *back = box + (size_t)(2 * me + 1) * 32;
+        if (lane == 0)
+            for (int i = 1; i <= iters; ++i) {
+                while (ld(mine) != (u64)i) {}
+                st(back, (u64)i);
+            }
+    }
 }
 
 // =============================================================================================

@@ -166,7 +166,7 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
     const int nin = (l == 0) ? 1 : M;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     // ---- chain weights -> registers (resident for the whole launch) ---------------------------------
     float4 wcur[Cur::N4], wdense[Dense::N4];
@@ -311,6 +311,7 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
             pf.mark(5);
         }
     }
+    pf.flush();
 }
 
 // =============================================================================================
@@ -352,7 +353,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
     const u64 *src0 = p.mb_acc + ((size_t)(L - 1) * M) * Sm + tid;
     u64 *dst0 = p.mb_c2 + (size_t)mt * O + o2;
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
@@ -380,6 +381,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
             pf.mark(2);
         }
     }
+    pf.flush();
 }
 
 // =============================================================================================
@@ -403,7 +405,7 @@ __device__ void sampler_role_s(const WnParams &p)
     double *red = reinterpret_cast<double *>(sc + p.ss.red);
     float *misc = sc + p.ss.misc;
     Abort ab{p.status, 0};
-    Prof pf{p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr, 0};
+    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     for (int i = tid; i < p.ss.total_floats; i += WN_NT) sc[i] = 0.0f;
     __syncthreads();
@@ -454,13 +456,14 @@ __device__ void sampler_role_s(const WnParams &p)
             double u64v = 0.0;
             if (SH::SCALAR) {
                 const float *u = (const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1);
-                if (warp == 0 && lane < nr) gum = wn::log32(-wn::log32(__ldg(u + lane)));
-                if (tid == 0) { float u2 = __ldg(u + nr); logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
+                if (warp == 0 && lane < nr) gum = wn::log32(-wn::log32(ld_nc_f32(u + lane)));
+                if (tid == 0) { float u2 = ld_nc_f32(u + nr); logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
             } else {
-                u64v = __ldg((const double *)p.uniforms + (size_t)b * p.T + t);
+                u64v = ld_nc_f64((const double *)p.uniforms + (size_t)b * p.T + t);
             }
             const bool has_next = (t + 1 < p.T_row[b]);
-            if (has_next && t + 1 < p.n_forced) next_forced = __ldg(p.forced + (size_t)b * p.n_forced + t + 1);
+            if (has_next && t + 1 < p.n_forced) next_forced = ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1);
+            pin(gum); pin(logistic); pin(next_forced); pin(u64v);
 
             if (tid < O) {
                 float v = b2v;
@@ -513,4 +516,5 @@ __device__ void sampler_role_s(const WnParams &p)
             pf.mark(2);
         }
     }
+    pf.flush();
 }
