@@ -60,6 +60,7 @@ typedef struct wn_config {
 } wn_config;
 
 #define WN_FLAG_GENERIC_KERNEL 1       /* never pick a compile-time specialised kernel instantiation */
+#define WN_FLAG_NO_DIE_AWARE 2         /* single-homed mailboxes (no die calibration); also env WN_NO_DIE_AWARE */
 
 /* Floating-point evaluation order implemented by the kernel (DESIGN.md "Pinned arithmetic").
  * Field meaning is identical to oracle/wn_oracle.c's orc_plan. */
@@ -78,7 +79,7 @@ typedef struct wn_info {
     int64_t weights_in_global;         /* floats that overflowed to L2/HBM */
     int64_t kernel_launches;           /* kernels launched by this handle so far */
     int32_t static_shape;              /* 0: runtime-shaped kernel; 1: cfg2 shape, 2: cfg1 shape, 3: hparams.py default shape */
-    int32_t reserved;
+    int32_t die_aware;                 /* 1: mailboxes are dual-homed (one L2 copy per die), set by wn_finalize */
 } wn_info;
 
 typedef struct wn_handle wn_handle;

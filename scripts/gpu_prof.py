@@ -41,10 +41,10 @@ def prof(name, kw, T):
     print('  tail: ', {n: int(tl[:, i].mean()) for i, n in enumerate(['wait_acc', 'post1', 'post2'])})
     print('  sampler:', {n: int(p[-1, i]) for i, n in enumerate(['wait_c2', 'draw', 'feed'])})
     busy = lay[:, :, 1:6].sum(axis=2).mean()
+    print('  extra marks: [6]=wait until own words arrive, phase0=barrier after poll; [7]=dense dot, phase2=epilogue+post:', int(lay[1:, :, 6].mean()), int(lay[1:, :, 0].mean()), int(lay[:-1, :, 7].mean()), int(lay[:-1, :, 2].mean()))
     print('  layer busy cycles per row-step %.0f; chain part (fg+dense) %.0f' % (busy, lay[:, :, 1:3].sum(axis=2).mean()))
 
 
 import time
 prof("cfg2", synth.cfg2(1), 3000)
-prof('cfg2', synth.cfg2(8), 3000)
-prof('cfg1', synth.cfg1(1), 4000)
+net = WaveNetModel(train_mode=False, **synth.cfg2(8)); net.load_state_dict(synth.make_weights(**synth.cfg2(8))); print('info', net.info())

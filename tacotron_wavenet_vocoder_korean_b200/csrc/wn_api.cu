@@ -39,6 +39,124 @@ struct DevBuf {
 
 }  // namespace
 
+namespace {
+// One-time, per-process die calibration: which die each SM id belongs to.
+struct Calib {
+    bool tried = false, ok = false;
+    int n_sm = 0, ref_smid = -1;
+    std::vector<unsigned char> sm_die;
+    std::vector<unsigned> raw;
+    void *d_sm_die = nullptr;
+    std::string note;
+};
+Calib g_calib;
+constexpr int kCalibSmem = 150 * 1024;     // forces one calibration CTA per SM
+
+// two separated modes?  returns the midpoint between the 5th and 95th percentile
+bool bimodal_threshold(std::vector<unsigned> v, unsigned *thr)
+{
+    if (v.size() < 4) return false;
+    std::sort(v.begin(), v.end());
+    unsigned lo = v[v.size() / 20], hi = v[v.size() - 1 - v.size() / 20];
+    if (lo == 0 || hi < lo + lo / 4) return false;
+    *thr = (lo + hi) / 2;
+    return true;
+}
+
+// runs a job list on a one-CTA-per-SM grid; out must hold the offsets used by the jobs
+cudaError_t run_calib_jobs(unsigned long long *grains, const std::vector<WnCalibJob> &jobs, int iters, std::vector<unsigned> &out,
+                           int n_sm, bool *aborted)
+{
+    WnCalibJob *dj = nullptr; unsigned *dout = nullptr; int *dab = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&dj, jobs.size() * sizeof(WnCalibJob))) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&dout, out.size() * 4)) != cudaSuccess) { cudaFree(dj); return e; }
+    if ((e = cudaMalloc(&dab, 4)) != cudaSuccess) { cudaFree(dj); cudaFree(dout); return e; }
+    cudaMemcpy(dj, jobs.data(), jobs.size() * sizeof(WnCalibJob), cudaMemcpyHostToDevice);
+    cudaMemset(dout, 0, out.size() * 4);
+    cudaMemset(dab, 0, 4);
+    int n_jobs = (int)jobs.size();
+    e = cudaFuncSetAttribute(wn_calib_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCalibSmem);
+    if (e == cudaSuccess) {
+        void *args[] = {(void *)&grains, (void *)&dj, (void *)&n_jobs, (void *)&iters, (void *)&dout, (void *)&dab};
+        e = cudaLaunchCooperativeKernel((const void *)wn_calib_kernel, dim3(n_sm), dim3(32), args, (size_t)kCalibSmem, 0);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    int ab = 0;
+    if (e == cudaSuccess) {
+        cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&ab, dab, 4, cudaMemcpyDeviceToHost);
+    }
+    *aborted = ab != 0;
+    cudaFree(dj); cudaFree(dout); cudaFree(dab);
+    return e;
+}
+
+// SM -> die map: SM `ref` ping-pongs with every other SM over G probe grains.  A partner on ref's die shows
+// two modes over the grains (fast = grain homed on that die); a partner on the other die is uniformly slow.
+void calibrate_once(int n_sm)
+{
+    Calib &c = g_calib;
+    if (c.tried) return;
+    c.tried = true;
+    c.n_sm = n_sm;
+    if (getenv("WN_NO_DIE_AWARE")) { c.note = "disabled by WN_NO_DIE_AWARE"; return; }
+    const int G = 16, ref = 0;
+    unsigned long long *probe = nullptr;
+    if (cudaMalloc(&probe, (size_t)G * 2048) != cudaSuccess) { c.note = "calibration alloc failed"; return; }
+    cudaMemset(probe, 0, (size_t)G * 2048);
+    std::vector<WnCalibJob> jobs;
+    for (int s = 0; s < n_sm; ++s)
+        if (s != ref) jobs.push_back(WnCalibJob{ref, s, 0, G, s * G});
+    std::vector<unsigned> out((size_t)n_sm * G, 0);
+    bool aborted = false;
+    cudaError_t e = run_calib_jobs(probe, jobs, 12, out, n_sm, &aborted);
+    cudaFree(probe);
+    if (e != cudaSuccess || aborted) { c.note = std::string("calibration run failed: ") + (aborted ? "timeout" : cudaGetErrorString(e)); cudaGetLastError(); return; }
+    c.raw = out;
+    c.sm_die.assign(n_sm, 1);
+    c.sm_die[ref] = 0;
+    int n0 = 1, n1 = 0;
+    for (int s = 0; s < n_sm; ++s) {
+        if (s == ref) continue;
+        std::vector<unsigned> row(out.begin() + (size_t)s * G, out.begin() + (size_t)(s + 1) * G);
+        unsigned mn = *std::min_element(row.begin(), row.end()), mx = *std::max_element(row.begin(), row.end());
+        if (mn == 0) { c.note = "no data for SM " + std::to_string(s); return; }
+        if (mx > mn + mn / 2) { c.sm_die[s] = 0; ++n0; }     // two modes: same die as ref
+        else ++n1;
+    }
+    if (n0 < 8 || n1 < 8) { c.note = "implausible die split " + std::to_string(n0) + "/" + std::to_string(n1); return; }
+    if (cudaMalloc(&c.d_sm_die, n_sm) != cudaSuccess ||
+        cudaMemcpy(c.d_sm_die, c.sm_die.data(), n_sm, cudaMemcpyHostToDevice) != cudaSuccess) { c.note = "upload failed"; return; }
+    c.ref_smid = ref;
+    c.ok = true;
+    c.note = "dies " + std::to_string(n0) + "/" + std::to_string(n1) + " SMs";
+}
+
+// grain -> die map for a mailbox arena: pairs of SMs on ref's die bounce a word through every grain
+bool classify_grains(unsigned long long *arena, size_t n_raw, std::vector<unsigned char> &is_far)
+{
+    const Calib &c = g_calib;
+    std::vector<int> d0;
+    for (int s = 0; s < c.n_sm; ++s) if (c.sm_die[s] == 0) d0.push_back(s);
+    const int n_pairs = std::min<int>(24, (int)d0.size() / 2);
+    std::vector<WnCalibJob> jobs;
+    const int per = (int)((n_raw + n_pairs - 1) / n_pairs);
+    for (int i = 0; i < n_pairs; ++i) {
+        int g0 = i * per, ng = std::min<int>(per, (int)n_raw - g0);
+        if (ng > 0) jobs.push_back(WnCalibJob{d0[2 * i], d0[2 * i + 1], g0, ng, g0});
+    }
+    std::vector<unsigned> out(n_raw, 0);
+    bool aborted = false;
+    if (run_calib_jobs(arena, jobs, 8, out, c.n_sm, &aborted) != cudaSuccess || aborted) { cudaGetLastError(); return false; }
+    unsigned thr;
+    if (!bimodal_threshold(out, &thr)) return false;
+    is_far.resize(n_raw);
+    for (size_t g = 0; g < n_raw; ++g) is_far[g] = out[g] > thr;
+    return true;
+}
+}  // namespace
+
 struct wn_handle {
     wn_config cfg;
     std::map<std::string, std::vector<float>> w;
@@ -52,8 +170,9 @@ struct wn_handle {
     int smem_layer = 0, smem_tail = 0, smem_samp = 0, smem_launch = 0;
     const void *kernel = nullptr;
     DevBuf layer_img, tail_img, samp_img, gc_table, wc_onehot, upk, mbox, ring, ring_off, status;
-    DevBuf prof;
+    DevBuf prof, mb_tab;
     bool prof_on = false;
+    int mb_dual = 0;
     DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
     DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
     size_t mbox_bytes = 0, ring_bytes = 0;
@@ -184,7 +303,7 @@ void wn_destroy(wn_handle *h)
 {
     if (!h) return;
     DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
-                      &h->ring_off, &h->status, &h->prof, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
+                      &h->ring_off, &h->status, &h->prof, &h->mb_tab, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
                       &h->h_out, &h->h_logits};
     for (DevBuf *b : bufs) b->release();
     delete h;
@@ -491,9 +610,36 @@ int wn_finalize(wn_handle *h)
     CUDA_TRY(h, h->samp_img.ensure(simg.size() * 4));
     CUDA_TRY(h, cudaMemcpy(h->samp_img.p, simg.data(), simg.size() * 4, cudaMemcpyHostToDevice));
 
+    // ---- mailboxes: logical word space -> dual-homed 2 KB grains ----------------------------------------
     const size_t n_x = (size_t)N * L * M * R, n_z = (size_t)N * L * M * Dm, n_acc = (size_t)N * L * M * Sm, n_c2 = (size_t)N * Mt * O;
-    h->mbox_bytes = (n_x + n_z + n_acc + n_c2) * 8;
+    const size_t n_lg = (n_x + n_z + n_acc + n_c2 + 255) / 256 + 1;            // logical grains
+    calibrate_once(prop.multiProcessorCount);
+    const bool want_dual = g_calib.ok && !(c.flags & WN_FLAG_NO_DIE_AWARE);
+    const size_t n_raw = want_dual ? (n_lg * 5) / 2 + 64 : n_lg;
+    h->mbox_bytes = n_raw * 2048;
     CUDA_TRY(h, h->mbox.ensure(h->mbox_bytes));
+    CUDA_TRY(h, cudaMemset(h->mbox.p, 0, h->mbox_bytes));
+    std::vector<unsigned long long> tabs(2 * n_lg);
+    unsigned long long base = (unsigned long long)(uintptr_t)h->mbox.p;
+    h->mb_dual = 0;
+    for (size_t g = 0; g < n_lg; ++g) tabs[g] = tabs[n_lg + g] = base + g * 2048;
+    h->info.die_aware = 0;
+    if (want_dual) {
+        std::vector<unsigned char> is_far;
+        if (classify_grains((unsigned long long *)h->mbox.p, n_raw, is_far)) {
+            std::vector<size_t> near_g, far_g;
+            for (size_t g = 0; g < n_raw; ++g) (is_far[g] ? far_g : near_g).push_back(g);
+            if (near_g.size() >= n_lg && far_g.size() >= n_lg) {
+                // the classifying SM pairs are on die 0: near grains are homed on die 0
+                for (size_t g = 0; g < n_lg; ++g) { tabs[g] = base + near_g[g] * 2048; tabs[n_lg + g] = base + far_g[g] * 2048; }
+                h->mb_dual = 1;
+                h->info.die_aware = 1;
+            }
+        }
+        CUDA_TRY(h, cudaMemset(h->mbox.p, 0, h->mbox_bytes));
+    }
+    CUDA_TRY(h, h->mb_tab.ensure(tabs.size() * 8));
+    CUDA_TRY(h, cudaMemcpy(h->mb_tab.p, tabs.data(), tabs.size() * 8, cudaMemcpyHostToDevice));
     std::vector<long long> roff(L);
     size_t rtot = 0;
     for (int l = 0; l < L; ++l) { roff[l] = (long long)rtot; rtot += (size_t)M * N * c.dilations[l] * R; }
@@ -508,10 +654,14 @@ int wn_finalize(wn_handle *h)
     p.samp_img = (const float *)h->samp_img.p;
     p.gc_table = (const float *)h->gc_table.p;
     p.wc_onehot = (const float *)h->wc_onehot.p;
-    p.mb_x = (unsigned long long *)h->mbox.p;
-    p.mb_z = p.mb_x + n_x;
-    p.mb_acc = p.mb_z + n_z;
-    p.mb_c2 = p.mb_acc + n_acc;
+    p.mb_x = reinterpret_cast<unsigned long long *>((uintptr_t)0);                    // logical addresses
+    p.mb_z = reinterpret_cast<unsigned long long *>((uintptr_t)(n_x * 8));
+    p.mb_acc = reinterpret_cast<unsigned long long *>((uintptr_t)((n_x + n_z) * 8));
+    p.mb_c2 = reinterpret_cast<unsigned long long *>((uintptr_t)((n_x + n_z + n_acc) * 8));
+    p.mb_tab[0] = (unsigned long long *const *)h->mb_tab.p;
+    p.mb_tab[1] = (unsigned long long *const *)h->mb_tab.p + n_lg;
+    p.sm_die = h->mb_dual ? (const unsigned char *)g_calib.d_sm_die : nullptr;
+    p.mb_dual = h->mb_dual;
     p.ring = (float *)h->ring.p;
     p.ring_off = (const long long *)h->ring_off.p;
     p.status = (int32_t *)h->status.p;
@@ -674,6 +824,52 @@ int wn_debug_pingpong_all(int grid, int iters, int mode, long long *out_host)
     cudaMemcpy(out_host, out, (size_t)grid * 2 * 8, cudaMemcpyDeviceToHost);
     cudaFree(box); cudaFree(out);
     return 0;
+}
+
+/* Diagnostics: ping-pong RTT matrix over (partner, grain of partner inbox, grain of CTA0 inbox). */
+int wn_debug_pingpong_grid(int grid, const int *part_host, int np, int ng, int iters, long long *out_host, unsigned *smids_host)
+{
+    unsigned long long *box = nullptr; int *part = nullptr; long long *out = nullptr; unsigned *smids = nullptr;
+    size_t bb = (size_t)ng * 2048;
+    if (cudaMalloc(&box, bb) != cudaSuccess || cudaMalloc(&part, np * 4) != cudaSuccess ||
+        cudaMalloc(&out, (size_t)np * ng * ng * 8) != cudaSuccess || cudaMalloc(&smids, grid * 4) != cudaSuccess) return -1;
+    cudaMemset(box, 0, bb);
+    cudaMemcpy(part, part_host, np * 4, cudaMemcpyHostToDevice);
+    void *args[] = {&box, &part, &np, &ng, &iters, &out, &smids};
+    if (cudaLaunchCooperativeKernel((const void *)wn_pingpong_grid_kernel, dim3(grid), dim3(32), args, 0, 0) != cudaSuccess) return -2;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+    cudaMemcpy(out_host, out, (size_t)np * ng * ng * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(smids_host, smids, grid * 4, cudaMemcpyDeviceToHost);
+    cudaFree(box); cudaFree(part); cudaFree(out); cudaFree(smids);
+    return 0;
+}
+
+/* Diagnostics: average cycles of one polling round (see wn_pollbench_kernel). */
+long long wn_debug_pollbench(int ctas, int iters, int warps, int lanes, int K)
+{
+    unsigned long long *box = nullptr; long long *out = nullptr;
+    size_t bb = (size_t)ctas * 4096 * 8 + 65536;
+    if (cudaMalloc(&box, bb) != cudaSuccess || cudaMalloc(&out, ctas * 8) != cudaSuccess) return -1;
+    cudaMemset(box, 0, bb);
+    wn_pollbench_kernel<<<ctas, 256>>>(box, iters, warps, lanes, K, out);
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    std::vector<long long> h(ctas);
+    cudaMemcpy(h.data(), out, ctas * 8, cudaMemcpyDeviceToHost);
+    cudaFree(box); cudaFree(out);
+    long long s = 0;
+    for (long long v : h) s += v;
+    return s / ctas;
+}
+
+/* Diagnostics: outcome of the per-process die calibration. */
+const char *wn_debug_calib_note(void) { return g_calib.note.c_str(); }
+
+/* Diagnostics: raw SM-map calibration round trips, out[n_sm*16]; returns n_sm (0 if not calibrated). */
+int wn_debug_calib_raw(unsigned *out, int max_sm)
+{
+    if (g_calib.raw.empty() || g_calib.n_sm > max_sm) return 0;
+    memcpy(out, g_calib.raw.data(), g_calib.raw.size() * 4);
+    return g_calib.n_sm;
 }
 
 int wn_sync_check(wn_handle *h, void *stream)

@@ -49,10 +49,56 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p)
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void ll_post(u64 *p, float val, unsigned seq)
+__device__ __forceinline__ void ll_store(u64 *p, float val, unsigned seq)
 {
     u64 v = ((u64)seq << 32) | (u64)__float_as_uint(val);
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Mailbox context: logical word address -> the grain copy on one die (wn_params.h)
+struct MBox {
+    u64 *const *tab0;
+    u64 *const *tab1;
+    u64 *const *mine;     // table of the reader's own die
+    bool dual;
+    __device__ __forceinline__ static u64 *at(u64 *const *tab, const u64 *logical)
+    {
+        const size_t w = reinterpret_cast<size_t>(logical) >> 3;
+        return reinterpret_cast<u64 *>(__ldg(reinterpret_cast<const unsigned long long *>(tab) + (w >> 8))) + (w & 255);
+    }
+    __device__ __forceinline__ u64 *rd(const u64 *logical) const { return at(mine, logical); }
+};
+// resolved destination(s) of one posted word; resolve early (before the data exists), store late
+struct MDst {
+    u64 *p0, *p1;
+};
+__device__ __forceinline__ MDst mb_dst(const MBox &mb, const u64 *logical)
+{
+    MDst d;
+    d.p0 = MBox::at(mb.tab0, logical);
+    d.p1 = mb.dual ? MBox::at(mb.tab1, logical) : nullptr;
+    return d;
+}
+__device__ __forceinline__ void ll_post(const MDst &d, float val, unsigned seq)
+{
+    ll_store(d.p0, val, seq);
+    if (d.p1) ll_store(d.p1, val, seq);
+}
+__device__ __forceinline__ void ll_post(const MBox &mb, const u64 *logical, float val, unsigned seq)
+{
+    ll_post(mb_dst(mb, logical), val, seq);
+}
+__device__ __forceinline__ MBox make_mbox(const WnParams &p)
+{
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    MBox mb;
+    mb.tab0 = p.mb_tab[0];
+    mb.tab1 = p.mb_tab[1];
+    const int side = (p.sm_die != nullptr) ? (int)p.sm_die[smid] : 0;
+    mb.mine = side ? p.mb_tab[1] : p.mb_tab[0];
+    mb.dual = p.mb_dual != 0;
+    return mb;
 }
 __device__ __forceinline__ int ld_volatile_i32(const int *p)
 {
@@ -115,8 +161,9 @@ __device__ __noinline__ bool watchdog_check(Abort &ab, long long &t0)
     return false;
 }
 
-__device__ __forceinline__ float ll_wait(const u64 *p, unsigned seq, Abort &ab)
+__device__ __forceinline__ float ll_wait(const MBox &mb, const u64 *logical, unsigned seq, Abort &ab)
 {
+    const u64 *p = mb.rd(logical);
     u64 v = ld_relaxed_u64(p);
     unsigned spins = 0;
     long long t0 = 0;
@@ -127,12 +174,18 @@ __device__ __forceinline__ float ll_wait(const u64 *p, unsigned seq, Abort &ab)
     return __uint_as_float((unsigned)v);
 }
 
-// wait for n (<=4) words p[i*stride]; loads are issued together so the latencies overlap
-__device__ __forceinline__ void ll_wait_n(const u64 *p, size_t stride, int n, unsigned seq, Abort &ab, float *out)
+// wait for n (<=4) words p[i*stride]; the loads are issued together so their latencies overlap.
+// One poll = one L2 round trip (~350 cycles, profiles/r01_hop_latency.md).  Measured alternatives that were
+// WORSE on the real kernel: two staggered polls per word in flight (+8 % step time), a delay between polling
+// rounds (+6..18 %), a lazy single-thread "heads-up" watch on the previous stage (+10 %).
+__device__ __forceinline__ void ll_wait_n(const MBox &mb, const u64 *logical, size_t stride, int n, unsigned seq, Abort &ab, float *out)
 {
+    const u64 *pp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pp[i] = (i < n) ? mb.rd(logical + i * stride) : nullptr;
     u64 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (i < n) ? ld_relaxed_u64(p + i * stride) : ((u64)seq << 32);
+    for (int i = 0; i < 4; ++i) v[i] = (i < n) ? ld_relaxed_u64(pp[i]) : ((u64)seq << 32);
     unsigned spins = 0;
     long long t0 = 0;
     while (true) {
@@ -143,7 +196,7 @@ __device__ __forceinline__ void ll_wait_n(const u64 *p, size_t stride, int n, un
         if (((++spins) & 0x3ffu) == 0 && watchdog_check(ab, t0)) break;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i < n && (unsigned)(v[i] >> 32) != seq) v[i] = ld_relaxed_u64(p + i * stride);
+            if (i < n && (unsigned)(v[i] >> 32) != seq) v[i] = ld_relaxed_u64(pp[i]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = __uint_as_float((unsigned)v[i]);
@@ -335,6 +388,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
     const int ncol2 = 2 * Dm;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     // ---- per-thread views and indices, computed once ------------------------------------------------
@@ -418,7 +472,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
             // 1. wait for the layer input: sum of the partial residual outputs of layer l-1
             if (tid < R) {
                 float q[4];
-                ll_wait_n(mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
+                ll_wait_n(mb, mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
                 float v = q[0];
                 for (int i = 1; i < nin; ++i) v = fadd(v, q[i]);
                 xs_cur[xp_cur] = v;
@@ -439,7 +493,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
                     float z = fmul(a, other);
                     zs_dense[xp_zd] = z;
                     zs_skip[xp_zs] = z;
-                    if (M > 1) ll_post(mbz_out + b * rowz, z, seq);
+                    if (M > 1) ll_post(mb, mbz_out + b * rowz, z, seq);
                 }
             }
             __syncthreads();
@@ -450,7 +504,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
                 u64 *dst = mbx_out + b * rowx;
                 matvec(mt_dense, [&](int r, float dot) {
                     float v = (m == 0) ? fadd(fadd(xraw[r], bd[r]), dot) : dot;
-                    ll_post(dst + r, v, seq);
+                    ll_post(mb, dst + r, v, seq);
                 });
             }
             pf.mark(2);
@@ -458,7 +512,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
             // 4. push x_l(t) into the private dilation-queue ring (model.py:145)
             if (d >= 2 && tid < R) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + tid, xraw[tid]);
             // 5. gather the sibling CTAs' gated activations
-            if (M > 1 && tid < p.D && g_mm != m) zs_skip[xp_zskip_gather] = ll_wait(mbz_in + b * rowz, seq, ab);
+            if (M > 1 && tid < p.D && g_mm != m) zs_skip[xp_zskip_gather] = ll_wait(mb, mbz_in + b * rowz, seq, ab);
             if (__syncthreads_or(ab.flag)) return;
             pf.mark(3);
             // 6. skip 1x1 (model.py:94-96) + running sum over layers (model.py:157)
@@ -467,8 +521,8 @@ __device__ void layer_role(const WnParams &p, int l, int m)
                 u64 *dst = mba_out + b * rowa;
                 matvec(mt_skip, [&](int c, float dot) {
                     float v = fadd(bs[c], dot);
-                    if (l > 0) v = fadd(ll_wait(src + c, seq, ab), v);
-                    ll_post(dst + c, v, seq);
+                    if (l > 0) v = fadd(ll_wait(mb, src + c, seq, ab), v);
+                    ll_post(mb, dst + c, v, seq);
                 });
             }
             pf.mark(4);
@@ -505,6 +559,7 @@ __device__ void tail_role(const WnParams &p, int mt)
     u64 *dst0 = p.mb_c2 + (size_t)mt * p.O;
     const int xp1_lead = mt_p1.lead ? xpad(p.post2, mt_p1.grp < p.St ? mt_p1.grp : 0) : 0;   // single pass: col == grp
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
@@ -512,7 +567,7 @@ __device__ void tail_role(const WnParams &p, int mt)
             if (t >= p.T_row[b]) continue;
             pf.start();
             const u64 *src = src0 + b * rowa;
-            for (int c = tid; c < S; c += WN_NT) as1[xpad(p.post1, c)] = relu32(ll_wait(src + c, seq, ab));
+            for (int c = tid; c < S; c += WN_NT) as1[xpad(p.post1, c)] = relu32(ll_wait(mb, src + c, seq, ab));
             if (__syncthreads_or(ab.flag)) return;
             pf.mark(0);
             if (mt_p1.npass == 1)
@@ -522,7 +577,7 @@ __device__ void tail_role(const WnParams &p, int mt)
             __syncthreads();
             pf.mark(1);
             u64 *dst = dst0 + (size_t)b * p.Mt * p.O;
-            matvec(mt_p2, [&](int o, float dot) { ll_post(dst + o, dot, seq); });
+            matvec(mt_p2, [&](int o, float dot) { ll_post(mb, dst + o, dot, seq); });
             __syncthreads();
             pf.mark(2);
         }
@@ -617,6 +672,7 @@ __device__ void sampler_role(const WnParams &p)
     double *red = reinterpret_cast<double *>(sc + p.ss.red);     // 16 doubles
     float *misc = sc + p.ss.misc;                                 // 32 floats
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     for (int i = tid; i < N * ifw; i += WN_NT) cq[i] = 0.0f;
@@ -636,7 +692,7 @@ __device__ void sampler_role(const WnParams &p)
             __syncthreads();
             if (tid < ifw) { cq[b * ifw + tid] = v; cqx[xp_cq] = v; }
             __syncthreads();
-            matvec(mt_c, [&](int r, float dot) { ll_post(dst + r, dot, seq); });
+            matvec(mt_c, [&](int r, float dot) { ll_post(mb, dst + r, dot, seq); });
         } else {
             int prev = ids[2 * b + 1];
             int cur = (int)x_in;
@@ -645,7 +701,7 @@ __device__ void sampler_role(const WnParams &p)
             if (tid < R) {
                 float a = (prev >= 0) ? __ldg(p.wc_onehot + ((size_t)0 * Q + prev) * R + tid) : 0.0f;
                 float bb = (cur >= 0 && cur < Q) ? __ldg(p.wc_onehot + ((size_t)1 * Q + cur) * R + tid) : 0.0f;
-                ll_post(dst + tid, fadd(a, bb), seq);
+                ll_post(mb, dst + tid, fadd(a, bb), seq);
             }
         }
         __syncthreads();
@@ -680,7 +736,7 @@ __device__ void sampler_role(const WnParams &p)
                 for (int m0 = 0; m0 < p.Mt; m0 += 4) {
                     float q[4];
                     int n = (p.Mt - m0 < 4) ? (p.Mt - m0) : 4;
-                    ll_wait_n(src + (size_t)m0 * O, (size_t)O, n, seq, ab, q);
+                    ll_wait_n(mb, src + (size_t)m0 * O, (size_t)O, n, seq, ab, q);
                     for (int i = 0; i < n; ++i) v = fadd(v, q[i]);
                 }
                 c2s[tid] = v;
@@ -737,11 +793,11 @@ __device__ void pingpong_role(u64 *box, int iters, long long *out)
     long long t0 = clock64();
     for (int i = 1; i <= iters; ++i) {
         if (me == 0) {
-            ll_post(theirs, 1.0f, (unsigned)i);
+            ll_store(theirs, 1.0f, (unsigned)i);
             while ((unsigned)(ld_relaxed_u64(mine) >> 32) != (unsigned)i) {}
         } else {
             while ((unsigned)(ld_relaxed_u64(mine) >> 32) != (unsigned)i) {}
-            ll_post(theirs, 1.0f, (unsigned)i);
+            ll_store(theirs, 1.0f, (unsigned)i);
         }
     }
     if (me == 0) out[0] = (clock64() - t0) / iters;
@@ -827,6 +883,100 @@ __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel_s(const __grid_
     if (cta < n_layer) layer_role_s<SH>(p, cta / n_layer_per, cta % n_layer_per);
     else if (cta < n_layer + SH::Mt) tail_role_s<SH>(p, cta - n_layer);
     else sampler_role_s<SH>(p);
+}
+
+// Diagnostic: cycles per polling round.  `warps` warps x `lanes` lanes each keep K strong loads in flight
+// (distinct 8-byte words, the kernel's own mailbox pattern) and wait for all of them, `iters` times.
+extern "C" __global__ void wn_pollbench_kernel(const unsigned long long *box, int iters, int warps, int lanes, int K, long long *out)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp >= warps || lane >= lanes) return;
+    const u64 *p = box + (size_t)blockIdx.x * 4096 + tid;
+    u64 acc = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        u64 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (k < K) ? ld_relaxed_u64(p + k * 128 + (acc & 1)) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += v[k];
+    }
+    long long t1 = clock64();
+    if (tid == 0) out[blockIdx.x] = (t1 - t0) / iters + (acc == 0x1234567 ? 1 : 0);
+}
+
+// Diagnostic: CTA 0 ping-pongs with partner CTAs part[0..np-1]; for each partner all (X, Y) combinations of
+// ng grains: partner's inbox in grain X, CTA 0's inbox in grain Y.  out[(pi*ng + X)*ng + Y] = round trip cycles.
+extern "C" __global__ void wn_pingpong_grid_kernel(unsigned long long *box, const int *part, int np, int ng, int iters,
+                                                   long long *out, unsigned *smids)
+{
+    const int me = blockIdx.x;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x != 0) return;
+    smids[me] = smid;
+    unsigned tag = 0;
+    for (int pi = 0; pi < np; ++pi) {
+        const int k = part[pi];
+        if (me != 0 && me != k) continue;
+        for (int X = 0; X < ng; ++X)
+            for (int Y = 0; Y < ng; ++Y) {
+                u64 *to_k = box + (size_t)X * 256 + 8 * (pi + 1);       // word inside grain X
+                u64 *to_0 = box + (size_t)Y * 256 + 8 * (pi + 1) + 4;   // word inside grain Y
+                long long t0 = clock64();
+                for (int i = 1; i <= iters; ++i) {
+                    tag = (unsigned)(((pi * ng + X) * ng + Y) * iters + i);     // identical on both sides
+                    if (me == 0) {
+                        ll_store(to_k, 1.0f, tag);
+                        while ((unsigned)(ld_relaxed_u64(to_0) >> 32) != tag) {}
+                    } else {
+                        while ((unsigned)(ld_relaxed_u64(to_k) >> 32) != tag) {}
+                        ll_store(to_0, 1.0f, tag);
+                    }
+                }
+                if (me == 0) out[((size_t)pi * ng + X) * ng + Y] = (clock64() - t0) / iters;
+            }
+    }
+}
+
+// Die calibration by ping-pong.  One CTA per SM.  A job = {smid_a, smid_b, first grain, grain
+// count, out offset}: the CTAs running on SMs a and b bounce an LL word through each grain (both inboxes in the
+// same 2 KB grain) and SM a records the round trip in out[offset + g].  A round trip is ~900 cycles only when both
+// SMs sit on the die whose L2 homes the grain, ~1300-2100 otherwise.  Every wait is bounded (abort flag).
+struct WnCalibJob {
+    int a, b, g0, ng, out0;
+};
+extern "C" __global__ void wn_calib_kernel(unsigned long long *grains, const WnCalibJob *jobs, int n_jobs, int iters,
+                                           unsigned *out, int *abort_flag)
+{
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x != 0) return;
+    for (int j = 0; j < n_jobs; ++j) {
+        const WnCalibJob jb = jobs[j];
+        const bool is_a = (int)smid == jb.a, is_b = (int)smid == jb.b;
+        if (!is_a && !is_b) continue;
+        for (int g = 0; g < jb.ng; ++g) {
+            u64 *base = grains + (size_t)(jb.g0 + g) * 256 + 2 * (j & 63);
+            u64 *to_b = base, *to_a = base + 1;
+            long long t0 = clock64();
+            for (int i = 1; i <= iters + 2; ++i) {
+                if (i == 3) t0 = clock64();                       // two warm-up exchanges
+                const unsigned tag = ((unsigned)(j + 1) << 12) + (unsigned)(g * 64 + i);
+                unsigned spins = 0;
+                if (is_a) {
+                    ll_store(to_b, 0.0f, tag);
+                    while ((unsigned)(ld_relaxed_u64(to_a) >> 32) != tag)
+                        if ((++spins & 0xfff) == 0 && (ld_volatile_i32(abort_flag) || spins > (1u << 22))) { *abort_flag = 1; return; }
+                } else {
+                    while ((unsigned)(ld_relaxed_u64(to_b) >> 32) != tag)
+                        if ((++spins & 0xfff) == 0 && (ld_volatile_i32(abort_flag) || spins > (1u << 22))) { *abort_flag = 1; return; }
+                    ll_store(to_a, 0.0f, tag);
+                }
+            }
+            if (is_a) out[jb.out0 + g] = (unsigned)((clock64() - t0) / iters);
+        }
+    }
 }
 
 // create_upsample stage (wavenet/model.py:102-111): one conv2d_transpose(kernel (F,2), strides (F,1), 'same')

@@ -166,6 +166,7 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
     const int nin = (l == 0) ? 1 : M;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     // ---- chain weights -> registers (resident for the whole launch) ---------------------------------
@@ -253,10 +254,13 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
         for (int b = 0; b < N; ++b) {
             if (t >= p.T_row[b]) continue;
             pf.start();
+            // destinations of this step's posts, resolved before the data exists
+            const MDst dx = mb_dst(mb, mbx_out + b * rowx);
+            const MDst dz = mb_dst(mb, mbz_out + b * rowz);
             // 1. layer input = sum of the partial residual outputs of layer l-1
             if (tid < R) {
                 float q[4];
-                ll_wait_n(mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
+                ll_wait_n(mb, mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
                 float v = q[0];
 #pragma unroll
                 for (int i = 1; i < 4; ++i)
@@ -276,7 +280,7 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
                     float z = fmul(a, other);
                     zs_dense[xp_zd] = z;
                     zs_skip[xp_zs] = z;
-                    if (M > 1) ll_post(mbz_out + b * rowz, z, seq);
+                    if (M > 1) ll_post(dz, z, seq);
                 }
             }
             __syncthreads();
@@ -286,13 +290,13 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
                 float dot = butterfly<Dense::TPC>(dot_wreg<Dense::N4, Dense::U>(wdense, reinterpret_cast<const float4 *>(xc_dense)));
                 if (dn_lead) {
                     float v = (m == 0) ? fadd(fadd(xraw[dn_r], dn_bd), dot) : dot;
-                    ll_post(mbx_out + b * rowx, v, seq);
+                    ll_post(dx, v, seq);
                 }
             }
             pf.mark(2);
             // ---- off the critical chain ----
             if (d >= 2 && tid < R) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + tid, xraw[tid]);
-            if (M > 1 && tid < D && g_mm != m) zs_skip[xp_zgather] = ll_wait(mbz_in + b * rowz, seq, ab);
+            if (M > 1 && tid < D && g_mm != m) zs_skip[xp_zgather] = ll_wait(mb, mbz_in + b * rowz, seq, ab);
             if (__syncthreads_or(ab.flag)) return;
             pf.mark(3);
             {
@@ -300,8 +304,8 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
                 u64 *dst = mba_out + b * rowa;
                 matvec_s<Skip>(w_skip, xc_skip, sk_grp, sk_lead, Sm, [&](int c, float dot) {
                     float v = fadd(bs[c], dot);
-                    if (l > 0) v = fadd(ll_wait(src + c, seq, ab), v);
-                    ll_post(dst + c, v, seq);
+                    if (l > 0) v = fadd(ll_wait(mb, src + c, seq, ab), v);
+                    ll_post(mb, dst + c, v, seq);
                 });
             }
             pf.mark(4);
@@ -353,6 +357,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
     const u64 *src0 = p.mb_acc + ((size_t)(L - 1) * M) * Sm + tid;
     u64 *dst0 = p.mb_c2 + (size_t)mt * O + o2;
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
@@ -361,7 +366,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
             pf.start();
             {
                 float q[4];
-                ll_wait_n(src0 + b * rowa, (size_t)WN_NT, PER, seq, ab, q);
+                ll_wait_n(mb, src0 + b * rowa, (size_t)WN_NT, PER, seq, ab, q);
 #pragma unroll
                 for (int i = 0; i < PER; ++i) as1[xp_a[i]] = relu32(q[i]);
             }
@@ -375,7 +380,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
             pf.mark(1);
             {
                 float dot = butterfly<Post2::TPC>(dot_wreg<Post2::N4, Post2::U>(w2r, reinterpret_cast<const float4 *>(xc2)));
-                if (lead2) ll_post(dst0 + (size_t)b * Mt * O, dot, seq);
+                if (lead2) ll_post(mb, dst0 + (size_t)b * Mt * O, dot, seq);
             }
             __syncthreads();
             pf.mark(2);
@@ -405,6 +410,7 @@ __device__ void sampler_role_s(const WnParams &p)
     double *red = reinterpret_cast<double *>(sc + p.ss.red);
     float *misc = sc + p.ss.misc;
     Abort ab{p.status, 0};
+    const MBox mb = make_mbox(p);
     Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
 
     for (int i = tid; i < p.ss.total_floats; i += WN_NT) sc[i] = 0.0f;
@@ -429,7 +435,7 @@ __device__ void sampler_role_s(const WnParams &p)
             if (tid < ifw) { cq[b * ifw + tid] = v; cqx[xp_cq] = v; }
             __syncthreads();
             float dot = butterfly<Causal::TPC>(dot_wreg<Causal::N4, Causal::U>(wcr, reinterpret_cast<const float4 *>(xc_c)));
-            if (c_lead) ll_post(dst + c_r, dot, seq);
+            if (c_lead) ll_post(mb, dst + c_r, dot, seq);
         } else {
             int prev = ids[2 * b + 1];
             int cur = (int)x_in;
@@ -438,7 +444,7 @@ __device__ void sampler_role_s(const WnParams &p)
             if (tid < R) {
                 float a = (prev >= 0) ? __ldg(p.wc_onehot + ((size_t)0 * Q + prev) * R + tid) : 0.0f;
                 float bb = (cur >= 0 && cur < Q) ? __ldg(p.wc_onehot + ((size_t)1 * Q + cur) * R + tid) : 0.0f;
-                ll_post(dst + tid, fadd(a, bb), seq);
+                ll_post(mb, dst + tid, fadd(a, bb), seq);
             }
         }
         __syncthreads();
@@ -471,7 +477,7 @@ __device__ void sampler_role_s(const WnParams &p)
 #pragma unroll
                 for (int m0 = 0; m0 < Mt; m0 += 4) {
                     float q[4];
-                    ll_wait_n(src + (size_t)m0 * O, (size_t)O, (Mt - m0 < 4) ? (Mt - m0) : 4, seq, ab, q);
+                    ll_wait_n(mb, src + (size_t)m0 * O, (size_t)O, (Mt - m0 < 4) ? (Mt - m0) : 4, seq, ab, q);
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (m0 + i < Mt) v = fadd(v, q[i]);

@@ -67,10 +67,18 @@ struct WnParams {
     const float *layer_img, *tail_img, *samp_img;
     const float *gc_table;         // (card, G)
     const float *wc_onehot;        // (2, Q, R) causal kernel for one-hot input, read by row
+    // Mailboxes live in a LOGICAL word space: these four are logical addresses (word index * 8, base 0),
+    // never dereferenced.  A logical word w is stored at mb_tab[side][w >> 8] + (w & 255): 2 KB grains,
+    // one copy homed in each die's L2 ("dual-homed").  Writers post to both copies, readers poll the copy
+    // homed on their own die (sm_die[smid]).  Without calibration both tables point at the same grains.
     unsigned long long *mb_x;      // [N][L][M][R]    partial inputs of layer l
     unsigned long long *mb_z;      // [N][L][M][Dm]   gated activations, exchanged between the M siblings
     unsigned long long *mb_acc;    // [N][L][M][Sm]   running skip sum after layer l
     unsigned long long *mb_c2;     // [N][Mt][O]      partial conv2 outputs
+    unsigned long long *const *mb_tab[2];
+    const unsigned char *sm_die;   // [n_sm] die (0/1) of each SM id, or null
+    int32_t mb_dual;               // 1: the two tables differ (post twice)
+    int32_t pad2_;
     float *ring;                   // private dilation-queue rings
     const long long *ring_off;     // [L] float offset of layer l's ring block; block = [M][N][d][R]
     const float *forced;

@@ -1,0 +1,54 @@
+"""The WaveNet / audio hyper-parameters generate.py reads (reference hparams.py:18-34,57-79), as a
+plain attribute bag.  The reference uses one global tf.contrib.training.HParams mutated in place by
+load_hparams (utils/__init__.py:156-172); the same semantics are kept: `hparams` is a module-level
+singleton and `load_hparams` overrides known keys from <checkpoint_dir>/params.json."""
+import json
+import os
+import re
+
+
+class HParams(object):
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def values(self):
+        return dict(self.__dict__)
+
+
+hparams = HParams(
+    name="Tacotron-Wavenet-Vocoder",
+    # audio (hparams.py:18-34)
+    sample_rate=24000, hop_size=300, fft_size=2048, win_size=1200, num_mels=80,
+    preemphasize=True, preemphasis=0.97, min_level_db=-100, ref_level_db=20,
+    signal_normalization=True, allow_clipping_in_normalization=True, symmetric_mels=True, max_abs_value=4.,
+    rescaling=True, rescaling_max=0.999,
+    # wavenet (hparams.py:57-79)
+    filter_width=2, gc_channels=32, input_type="raw", scalar_input=True,
+    dilations=[1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 5,
+    residual_channels=32, dilation_channels=32, quantization_channels=256, out_channels=30,
+    skip_channels=512, use_biases=True, initial_filter_width=32, upsample_factor=[5, 5, 12],
+)
+
+PARAMS_NAME = "params.json"
+
+
+def load_json(path, encoding='euc-kr'):
+    # utils/__init__.py:173-185: tolerates trailing commas, euc-kr encoded
+    with open(path, encoding=encoding) as f:
+        content = f.read()
+    content = re.sub(r",\s*}", "}", content)
+    content = re.sub(r",\s*]", "]", content)
+    return json.loads(content)
+
+
+def load_hparams(hp, load_path, skip_list=()):
+    """utils/__init__.py:156-172: update the singleton from <load_path>/params.json."""
+    new = load_json(os.path.join(load_path, PARAMS_NAME))
+    for key, value in new.items():
+        if key in skip_list or key not in vars(hp):
+            print("Skip {} because it not exists".format(key))
+            continue
+        if getattr(hp, key) != value:
+            print("UPDATE {}: {} -> {}".format(key, getattr(hp, key), value))
+            setattr(hp, key, value)
+    return hp

@@ -121,6 +121,19 @@ def test_runtime_shaped_kernel_equals_specialised_kernel(fac, T, shape):
     assert np.array_equal(so, b[0].cpu().numpy())
 
 
+def test_dual_homed_mailboxes_do_not_change_results():
+    # die-aware (dual-homed) mailboxes are a placement optimisation only
+    kw = synth.cfg2(2)
+    net_a, _ = build(kw)
+    net_b, _ = build(kw, die_aware=False)
+    assert net_b.info()['die_aware'] == 0
+    inp = make_inputs(kw, 200)
+    lc = net_a.create_upsample(inp['mel'])
+    a = net_a.generate(200, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])
+    b = net_b.generate(200, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])
+    assert torch.equal(a, b)
+
+
 def test_hparams_default_model_bit_exact():
     # the reference's own defaults (hparams.py:59-79): 50 layers, R=D=32, scalar input, lc + gc
     _, _, _, got, exp, _ = run_both(synth.cfg_hparams_default(2), 400)
