@@ -117,7 +117,9 @@ def run_reference(args, rank, world):
     t0 = time.perf_counter()
     vals = [cpu_port_throughput(sample_steps, threads) for _ in range(args.steps)]
     dt = time.perf_counter() - t0
-    v = ROWS * sample_steps * args.steps / dt
+    # each step's throughput is timed around the generation loop only (as generate.py:199 does); the
+    # wall time per step additionally contains building the oracle model and the upsampling
+    v = ROWS * sample_steps * args.steps / sum(ROWS * sample_steps / x for x in vals)
     line = {"impl": "reference", "metric": "wavenet_generation_samples_per_sec", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -249,6 +251,25 @@ def main():
     torch.cuda.synchronize()
     batch1 = 12000 / (b0.elapsed_time(b1) / 1e3)
 
+    # ---- more rows in flight (the e2e scenario of BASELINE configs[4] has 32 sentences per GPU) ---------------
+    more = {}
+    for nb in (16, 32):
+        kwb = dict(kw, batch_size=nb)
+        netb = WaveNetModel(train_mode=False, device=dev, **kwb)
+        netb.load_state_dict(w)
+        reps = nb // ROWS
+        melb = mel_d.repeat(reps, 1, 1)
+        unib = uni_d[:, :6000].repeat(reps, 1, 1)
+        lcb = netb.create_upsample(melb)
+        gcb = gc * reps
+        netb.generate(6000, x0_d.repeat(reps, 1), unib, lc_up=lcb, gc_ids=gcb)
+        b0.record()
+        netb.generate(6000, x0_d.repeat(reps, 1), unib, lc_up=lcb, gc_ids=gcb, sync=False)
+        b1.record()
+        torch.cuda.synchronize()
+        more["batch%d_samples_per_sec" % nb] = nb * 6000 / (b0.elapsed_time(b1) / 1e3)
+        del netb, lcb, melb, unib
+
     # ---- roofline -------------------------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -266,7 +287,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "wn_persistent_kernel",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "wn_persistent_kernel_s<ShapeCfg2>" if info.get("static_shape") == 1 else "wn_persistent_kernel",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step": b_step, "steps_per_launch": T_STEPS,
                 "note": "weights (21.4 MB) are resident in shared memory across the grid, so DRAM traffic is far below the "
                         "algorithmic bytes; the binding limit is the 34-stage dependent chain per sample (DESIGN.md latency model)",
@@ -290,7 +311,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "realtime_factor_per_utterance": value / world / ROWS / SAMPLE_RATE,
-            "batch1_samples_per_sec": batch1}
+            "batch1_samples_per_sec": batch1, "die_aware_mailboxes": info.get("die_aware"), **more}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,7 @@
 
 namespace {
 
+constexpr int kManyRows = 10;
 constexpr int kMaxDynSmem = 232448 - 2048;   // 227 KB opt-in limit minus static/reserved slack
 
 std::string g_create_error;
@@ -169,6 +170,7 @@ struct wn_handle {
     WnParams base{};            // everything except the per-call fields
     int smem_layer = 0, smem_tail = 0, smem_samp = 0, smem_launch = 0;
     const void *kernel = nullptr;
+    const void *kernel_many = nullptr;     // variant used when >= kManyRows rows are in flight (or null)
     DevBuf layer_img, tail_img, samp_img, gc_table, wc_onehot, upk, mbox, ring, ring_off, status;
     DevBuf prof, mb_tab;
     bool prof_on = false;
@@ -380,6 +382,7 @@ static int plan_layout(wn_handle *h, int sm_count)
         p.ls.bfgN = so; so += align4(N * 2 * Dm);
         p.ls.pre = so; so += align4(N * 2 * Dm);
         p.ls.total_floats = so;
+        so += align4(N * (R + Dm));            // rowbuf of the warp-specialised layer role (follows total_floats)
         const int cap = kMaxDynSmem / 4 - so;
         int resident = off;
         bool spill = false;
@@ -451,8 +454,13 @@ static int plan_layout(wn_handle *h, int sm_count)
     inf.weights_in_smem = ((int64_t)p.layer_smem_floats * L * M + (int64_t)p.tail_smem_floats * Mt + p.samp_smem_floats);
     // compile-time specialised instantiation, when the planned shapes coincide with one
     h->kernel = (const void *)wn_persistent_kernel;
+    h->kernel_many = nullptr;
     if (!(c.flags & WN_FLAG_GENERIC_KERNEL) && inf.weights_in_global == 0) {
-        if (shape_matches<ShapeCfg2>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg2>; inf.static_shape = 1; }
+        if (shape_matches<ShapeCfg2>(p)) {
+            h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg2>;
+            h->kernel_many = (const void *)wn_persistent_kernel_s<ShapeCfg2WS>;
+            inf.static_shape = 1;
+        }
         else if (shape_matches<ShapeCfg1>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg1>; inf.static_shape = 2; }
         else if (shape_matches<ShapeHparams>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeHparams>; inf.static_shape = 3; }
     }
@@ -667,6 +675,7 @@ int wn_finalize(wn_handle *h)
     p.status = (int32_t *)h->status.p;
 
     CUDA_TRY(h, cudaFuncSetAttribute(h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
+    if (h->kernel_many) CUDA_TRY(h, cudaFuncSetAttribute(h->kernel_many, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_launch));
     int occ = 0;
     if (h->info.static_shape == 1) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeCfg2>, WN_NT, h->smem_launch));
     else if (h->info.static_shape == 2) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeCfg1>, WN_NT, h->smem_launch));
@@ -776,7 +785,8 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
         p.prof = (long long *)h->prof.p;
     }
     void *args[] = {&p};
-    CUDA_TRY(h, cudaLaunchCooperativeKernel(h->kernel, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
+    const void *fn = (h->kernel_many && a->rows >= kManyRows) ? h->kernel_many : h->kernel;
+    CUDA_TRY(h, cudaLaunchCooperativeKernel(fn, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
     h->launches++;
     return WN_OK;
 }

@@ -120,9 +120,9 @@ struct Prof {
     {
         if (slot) { long long now = clock64(); acc[phase] += now - last; last = now; }
     }
-    __device__ __forceinline__ void flush()
+    __device__ __forceinline__ void flush(bool writer = (threadIdx.x == 0))
     {
-        if (slot && threadIdx.x == 0)
+        if (slot && writer)
             for (int i = 0; i < 12; ++i) slot[i] = acc[i];
     }
 };
@@ -783,6 +783,7 @@ __device__ void sampler_role(const WnParams &p)
 }
 
 #include "wn_kernel_static.cuh"
+#include "wn_kernel_ws.cuh"
 
 // LL-mailbox ping-pong between CTA 0 and CTA 1: average round trip in clock cycles (diagnostic).
 __device__ void pingpong_role(u64 *box, int iters, long long *out)
@@ -880,7 +881,10 @@ __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel_s(const __grid_
     const int cta = blockIdx.x;
     constexpr int n_layer_per = SH::M;
     const int n_layer = p.L * n_layer_per;
-    if (cta < n_layer) layer_role_s<SH>(p, cta / n_layer_per, cta % n_layer_per);
+    if (cta < n_layer) {
+        if constexpr (SH::WS) layer_role_ws<SH>(p, cta / n_layer_per, cta % n_layer_per);
+        else layer_role_s<SH>(p, cta / n_layer_per, cta % n_layer_per);
+    }
     else if (cta < n_layer + SH::Mt) tail_role_s<SH>(p, cta - n_layer);
     else sampler_role_s<SH>(p);
 }

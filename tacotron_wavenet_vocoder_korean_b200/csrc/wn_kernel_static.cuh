@@ -26,7 +26,7 @@ struct MS {
 
 // BASELINE configs[1]: R = D = 128, S = 512, M = 4, Mt = 16, MoL-10, lc 80, gc 32
 struct ShapeCfg2 {
-    static constexpr bool SCALAR = true, HAS_LC = true, HAS_GC = true;
+    static constexpr bool SCALAR = true, HAS_LC = true, HAS_GC = true, WS = false;
     static constexpr int R = 128, D = 128, M = 4, Dm = 32, S = 512, Sm = 128, Mt = 16, St = 32, O = 30, C = 80, G = 32, IFW = 32, Q = 256;
     using Cur = MS<4, 8, 8, 1>;
     using Lc = MS<4, 5, 1, 1>;
@@ -37,9 +37,14 @@ struct ShapeCfg2 {
     using Post2 = MS<8, 1, 1, 1>;
     using Causal = MS<2, 4, 4, 1>;
 };
+// same shape with the warp-specialised layer CTA (wn_kernel_ws.cuh): ~4 % more latency per step but the
+// off-chain work leaves the in-order loop, so it wins once >= 10 rows are in flight (profiles/r01_rows_sweep.md)
+struct ShapeCfg2WS : ShapeCfg2 {
+    static constexpr bool WS = true;
+};
 // BASELINE configs[0]: R = D = 32, S = 512, M = 1, Mt = 16, mu-law 256, unconditioned
 struct ShapeCfg1 {
-    static constexpr bool SCALAR = false, HAS_LC = false, HAS_GC = false;
+    static constexpr bool SCALAR = false, HAS_LC = false, HAS_GC = false, WS = false;
     static constexpr int R = 32, D = 32, M = 1, Dm = 32, S = 512, Sm = 512, Mt = 16, St = 32, O = 256, C = 0, G = 0, IFW = 32, Q = 256;
     using Cur = MS<4, 2, 2, 1>;
     using Lc = MS<1, 1, 1, 1>;
@@ -52,7 +57,7 @@ struct ShapeCfg1 {
 };
 // the reference's hparams.py defaults: R = D = 32, S = 512, M = 1, Mt = 16, MoL-10, lc 80, gc 32
 struct ShapeHparams {
-    static constexpr bool SCALAR = true, HAS_LC = true, HAS_GC = true;
+    static constexpr bool SCALAR = true, HAS_LC = true, HAS_GC = true, WS = false;
     static constexpr int R = 32, D = 32, M = 1, Dm = 32, S = 512, Sm = 512, Mt = 16, St = 32, O = 30, C = 80, G = 32, IFW = 32, Q = 256;
     using Cur = MS<4, 2, 2, 1>;
     using Lc = MS<4, 5, 1, 1>;

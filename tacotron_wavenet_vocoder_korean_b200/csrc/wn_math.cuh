@@ -20,11 +20,14 @@ __device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf
 // e^x: x < -87 -> 0; x > 88 -> 88; n = RN(x*log2e) by magic add; Cody-Waite r; degree-5 polynomial.
 __device__ __forceinline__ float exp32(float x)
 {
-    if (x < -87.0f) return 0.0f;
-    x = (x > 88.0f) ? 88.0f : x;
+    // branch-free: evaluate on the clamped argument, select +0 for x < -87 at the end (same bits as the
+    // early-return form of the specification; no divergence, so two independent calls interleave)
+    const bool tiny = x < -87.0f;
+    float xc = tiny ? -87.0f : x;
+    xc = (xc > 88.0f) ? 88.0f : xc;
     const float magic = 12582912.0f;                    // 1.5 * 2^23
-    float n = fsub(ffma(x, 1.44269504088896341f, magic), magic);
-    float r = ffma(n, -0.693359375f, x);
+    float n = fsub(ffma(xc, 1.44269504088896341f, magic), magic);
+    float r = ffma(n, -0.693359375f, xc);
     r = ffma(n, 2.12194440e-4f, r);
     float p = 1.9875691500e-4f;
     p = ffma(p, r, 1.3981999507e-3f);
@@ -34,7 +37,8 @@ __device__ __forceinline__ float exp32(float x)
     p = ffma(p, r, 5.0000001201e-1f);
     float e = fadd(ffma(p, fmul(r, r), r), 1.0f);
     int ni = __float2int_rz(n);
-    return __uint_as_float(__float_as_uint(e) + ((unsigned)ni << 23));
+    float res = __uint_as_float(__float_as_uint(e) + ((unsigned)ni << 23));
+    return tiny ? 0.0f : res;
 }
 
 __device__ __forceinline__ float sigmoid32(float x)

