@@ -655,7 +655,7 @@ int wn_finalize(wn_handle *h)
     CUDA_TRY(h, h->ring.ensure(std::max<size_t>(h->ring_bytes, 16)));
     CUDA_TRY(h, h->ring_off.ensure(L * sizeof(long long)));
     CUDA_TRY(h, cudaMemcpy(h->ring_off.p, roff.data(), L * sizeof(long long), cudaMemcpyHostToDevice));
-    CUDA_TRY(h, h->status.ensure(16));
+    CUDA_TRY(h, h->status.ensure(32));
 
     p.layer_img = (const float *)h->layer_img.p;
     p.tail_img = (const float *)h->tail_img.p;
@@ -777,7 +777,7 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
 
     CUDA_TRY(h, cudaMemsetAsync(h->mbox.p, 0, h->mbox_bytes, st));
     if (h->ring_bytes) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));
-    CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 16, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 32, st));
     p.prof = nullptr;
     if (h->prof_on) {
         CUDA_TRY(h, h->prof.ensure((size_t)p.grid * 16 * sizeof(long long)));

@@ -389,7 +389,7 @@ __device__ void layer_role(const WnParams &p, int l, int m)
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)cta * 16 : nullptr);
 
     // ---- per-thread views and indices, computed once ------------------------------------------------
     const MatT mt_cur = make_matt(p.cur, gimg, xs_cur), mt_old = make_matt(p.old, gimg, xs_old);
@@ -560,7 +560,7 @@ __device__ void tail_role(const WnParams &p, int mt)
     const int xp1_lead = mt_p1.lead ? xpad(p.post2, mt_p1.grp < p.St ? mt_p1.grp : 0) : 0;   // single pass: col == grp
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)(p.L * p.M + mt) * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
@@ -673,7 +673,7 @@ __device__ void sampler_role(const WnParams &p)
     float *misc = sc + p.ss.misc;                                 // 32 floats
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)(p.L * p.M + p.Mt) * 16 : nullptr);
 
     for (int i = tid; i < N * ifw; i += WN_NT) cq[i] = 0.0f;
     for (int i = tid; i < p.causal.xlen; i += WN_NT) cqx[i] = 0.0f;
@@ -866,9 +866,30 @@ extern "C" __global__ void wn_pingpong_all_kernel(unsigned long long *box, int i
 }
 
 // =============================================================================================
+// Role of this CTA.  Roles are numbered along the sample chain (layers, tail, sampler).  With a die map,
+// CTAs running on die 0 claim roles from the front of the list and CTAs on die 1 from the back, so the chain
+// crosses the die boundary twice per sample instead of on about every second hop (writers on the reader's
+// die save ~160 cycles per hop, profiles/r01_hop_latency.md).  Mailboxes are addressed by role, so no CTA
+// needs to know who claimed what.  status[4], status[5]: claim counters, zeroed before every launch.
+__device__ __forceinline__ int claim_role(const WnParams &p)
+{
+    __shared__ int s_role;
+    if (threadIdx.x == 0) {
+        int role = (int)blockIdx.x;
+        if (p.sm_die != nullptr) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            role = (p.sm_die[smid] == 0) ? atomicAdd(p.status + 4, 1) : p.grid - 1 - atomicAdd(p.status + 5, 1);
+        }
+        s_role = role;
+    }
+    __syncthreads();
+    return s_role;
+}
+
 extern "C" __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel(const __grid_constant__ WnParams p)
 {
-    const int cta = blockIdx.x;
+    const int cta = claim_role(p);
     const int n_layer = p.L * p.M;
     if (cta < n_layer) layer_role(p, cta / p.M, cta % p.M);
     else if (cta < n_layer + p.Mt) tail_role(p, cta - n_layer);
@@ -878,7 +899,7 @@ extern "C" __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel(cons
 template <class SH>
 __global__ void __launch_bounds__(WN_NT, 1) wn_persistent_kernel_s(const __grid_constant__ WnParams p)
 {
-    const int cta = blockIdx.x;
+    const int cta = claim_role(p);
     constexpr int n_layer_per = SH::M;
     const int n_layer = p.L * n_layer_per;
     if (cta < n_layer) {

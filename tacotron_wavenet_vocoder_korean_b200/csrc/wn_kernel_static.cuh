@@ -172,7 +172,7 @@ __device__ void layer_role_s(const WnParams &p, int l, int m)
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)cta * 16 : nullptr);
 
     // ---- chain weights -> registers (resident for the whole launch) ---------------------------------
     float4 wcur[Cur::N4], wdense[Dense::N4];
@@ -363,7 +363,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
     u64 *dst0 = p.mb_c2 + (size_t)mt * O + o2;
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)(p.L * SH::M + mt) * 16 : nullptr);
     for (int t = 0; t < p.T; ++t) {
         const unsigned seq = (unsigned)t + 1u;
         for (int b = 0; b < N; ++b) {
@@ -416,7 +416,7 @@ __device__ void sampler_role_s(const WnParams &p)
     float *misc = sc + p.ss.misc;
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)(p.L * SH::M + SH::Mt) * 16 : nullptr);
 
     for (int i = tid; i < p.ss.total_floats; i += WN_NT) sc[i] = 0.0f;
     __syncthreads();

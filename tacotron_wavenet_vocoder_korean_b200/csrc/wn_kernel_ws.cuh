@@ -96,7 +96,7 @@ __device__ void layer_role_ws(const WnParams &p, int l, int m)
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     Abort ab{p.status, 0};
     const MBox mb = make_mbox(p);
-    Prof pf(p.prof ? p.prof + (size_t)blockIdx.x * 16 : nullptr);
+    Prof pf(p.prof ? p.prof + (size_t)cta * 16 : nullptr);
     const size_t rowx = (size_t)L * M * R, rowz = (size_t)L * M * Dm, rowa = (size_t)L * M * Sm;
 
     for (int i = tid; i < p.ls.bfgN; i += WN_NT) sc[i] = 0.0f;
