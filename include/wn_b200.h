@@ -149,6 +149,18 @@ int wn_mu_law_encode(const float *audio_dev, int64_t n, int quantization_channel
 int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, int quantization,
                      float *out_dev, void *stream);
 
+/* utils/audio.py:69-75 melspectrogram(wav, hparams) ("next-2"): pre-emphasis -> librosa.stft
+ * (center, reflect pad, periodic Hann zero-padded to fft_size) -> |D| -> Slaney mel basis -> 20*log10(max(1e-5, .))
+ * - ref_level_db -> symmetric normalisation + clip.  Fields are the reference's hparams.py:18-34.
+ * wav_dev (rows, n) fp32 -> out_dev (rows, 1 + n / hop_size, num_mels) fp32 (the reference returns the
+ * transpose, (num_mels, frames), for one row).  On error wn_last_error(NULL) has the message. */
+typedef struct wn_mel_config {
+    int32_t sample_rate, fft_size, hop_size, win_size, num_mels;
+    int32_t preemphasize;
+    float preemphasis, min_level_db, ref_level_db, max_abs_value;
+} wn_mel_config;
+int wn_melspectrogram(const float *wav_dev, int rows, int64_t n, const wn_mel_config *mc, float *out_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,9 +54,15 @@ class WnGenerateArgs(C.Structure):
                 ("out_samples_dev", C.c_void_p), ("out_logits_dev", C.c_void_p)]
 
 
+class WnMelConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("fft_size", C.c_int32), ("hop_size", C.c_int32), ("win_size", C.c_int32),
+                ("num_mels", C.c_int32), ("preemphasize", C.c_int32), ("preemphasis", C.c_float),
+                ("min_level_db", C.c_float), ("ref_level_db", C.c_float), ("max_abs_value", C.c_float)]
+
+
 EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_plan_config", "wn_get_plan",
            "wn_get_info", "wn_receptive_field", "wn_upsample", "wn_generate", "wn_sync_check",
-           "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode"]
+           "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode", "wn_melspectrogram"]
 
 _lib = None
 
@@ -97,5 +103,6 @@ def lib():
         L.wn_generate_host.argtypes = [H, C.POINTER(WnGenerateArgs), C.c_void_p, C.c_int]
         L.wn_mu_law_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.wn_mu_law_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.wn_melspectrogram.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(WnMelConfig), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib

@@ -16,6 +16,9 @@
 
 // single translation unit: the device code is compiled together with its launch sites
 #include "wn_kernel.cu"
+#include "wn_mel.cuh"
+#include <cmath>
+#include <mutex>
 
 namespace {
 
@@ -962,6 +965,113 @@ int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, 
     int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     wn_mu_law_decode_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_dev, n, (float)(quantization_channels - 1), quantization, out_dev);
     return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+
+}  // extern "C"
+
+/* ---- STFT -> mel (utils/audio.py:69-75) ---------------------------------------------------------------- */
+namespace {
+struct MelTables {
+    int sr, n_fft, win, n_mels;
+    double *window = nullptr; double2 *twiddle = nullptr; int *start = nullptr, *len = nullptr, *off = nullptr; float *w = nullptr;
+};
+std::vector<MelTables> g_mel_tables;
+std::mutex g_mel_mutex;
+
+double hz_to_mel_slaney(double f)
+{
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz_slaney(double m)
+{
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// tables of librosa.stft's window / FFT twiddles and librosa.filters.mel (Slaney scale, area normalised)
+const MelTables *mel_tables(int sr, int n_fft, int win, int n_mels)
+{
+    std::lock_guard<std::mutex> lock(g_mel_mutex);
+    for (const MelTables &t : g_mel_tables)
+        if (t.sr == sr && t.n_fft == n_fft && t.win == win && t.n_mels == n_mels) return &t;
+    MelTables t; t.sr = sr; t.n_fft = n_fft; t.win = win; t.n_mels = n_mels;
+    const double PI = 3.14159265358979323846;
+    std::vector<double> window(win);
+    for (int i = 0; i < win; ++i) window[i] = 0.5 - 0.5 * std::cos(2.0 * PI * i / win);      // periodic Hann
+    std::vector<double2> tw(n_fft / 2);
+    for (int k = 0; k < n_fft / 2; ++k) tw[k] = make_double2(std::cos(2.0 * PI * k / n_fft), -std::sin(2.0 * PI * k / n_fft));
+    const int n_bins = n_fft / 2 + 1;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel_slaney(0.0), m_hi = hz_to_mel_slaney(sr / 2.0);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz_slaney(m_lo + (m_hi - m_lo) * i / (n_mels + 1));
+    std::vector<int> start(n_mels), len(n_mels), off(n_mels);
+    std::vector<float> w;
+    for (int i = 0; i < n_mels; ++i) {
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        int first = -1, last = -2;
+        std::vector<float> row(n_bins);
+        for (int k = 0; k < n_bins; ++k) {
+            const double fk = (sr / 2.0) * k / (n_bins - 1);
+            const double lower = (fk - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+            const double upper = (mel_f[i + 2] - fk) / (mel_f[i + 2] - mel_f[i + 1]);
+            const double v = std::max(0.0, std::min(lower, upper)) * enorm;
+            row[k] = (float)v;
+            if (row[k] != 0.0f) { if (first < 0) first = k; last = k; }
+        }
+        if (first < 0) { first = 0; last = -1; }
+        start[i] = first; len[i] = last - first + 1; off[i] = (int)w.size();
+        for (int k = first; k <= last; ++k) w.push_back(row[k]);
+    }
+    if (w.empty()) w.push_back(0.0f);
+    bool ok = cudaMalloc(&t.window, win * 8) == cudaSuccess && cudaMalloc(&t.twiddle, (n_fft / 2) * 16) == cudaSuccess &&
+              cudaMalloc(&t.start, n_mels * 4) == cudaSuccess && cudaMalloc(&t.len, n_mels * 4) == cudaSuccess &&
+              cudaMalloc(&t.off, n_mels * 4) == cudaSuccess && cudaMalloc(&t.w, w.size() * 4) == cudaSuccess;
+    ok = ok && cudaMemcpy(t.window, window.data(), win * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t.twiddle, tw.data(), (n_fft / 2) * 16, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t.start, start.data(), n_mels * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t.len, len.data(), n_mels * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t.off, off.data(), n_mels * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t.w, w.data(), w.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) return nullptr;
+    g_mel_tables.push_back(t);
+    return &g_mel_tables.back();
+}
+}  // namespace
+
+extern "C" {
+
+int wn_melspectrogram(const float *wav_dev, int rows, int64_t n, const wn_mel_config *mc, float *out_dev, void *stream)
+{
+    if (!wav_dev || !out_dev || !mc || rows < 1 || n < 2) return fail(nullptr, WN_ERR_ARG, "wn_melspectrogram: bad argument");
+    if (mc->fft_size < 64 || mc->fft_size > 8192 || (mc->fft_size & (mc->fft_size - 1)))
+        return fail(nullptr, WN_ERR_ARG, "fft_size must be a power of two in 64..8192");
+    if (mc->win_size < 1 || mc->win_size > mc->fft_size || mc->hop_size < 1 || mc->num_mels < 1 || mc->num_mels > 256)
+        return fail(nullptr, WN_ERR_ARG, "bad win_size / hop_size / num_mels");
+    if (n <= mc->fft_size / 2) return fail(nullptr, WN_ERR_ARG, "signal shorter than fft_size/2 cannot be reflect-padded");
+    const MelTables *t = mel_tables(mc->sample_rate, mc->fft_size, mc->win_size, mc->num_mels);
+    if (!t) { cudaGetLastError(); return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: table upload failed (no CUDA device?)"); }
+    WnMelParams p;
+    p.wav = wav_dev; p.n = n; p.rows = rows; p.frames = (int)(1 + n / mc->hop_size);
+    p.n_fft = mc->fft_size; p.log2n = 0;
+    while ((1 << p.log2n) < p.n_fft) ++p.log2n;
+    p.hop = mc->hop_size; p.win = mc->win_size; p.win_off = (mc->fft_size - mc->win_size) / 2;
+    p.n_mels = mc->num_mels; p.n_bins = mc->fft_size / 2 + 1;
+    p.window = t->window; p.twiddle = t->twiddle; p.mel_start = t->start; p.mel_len = t->len; p.mel_off = t->off; p.mel_w = t->w;
+    p.preemph = mc->preemphasize ? (double)mc->preemphasis : 0.0;
+    p.min_level = (float)std::exp(mc->min_level_db / 20.0 * std::log(10.0));
+    p.ref_level_db = mc->ref_level_db; p.min_level_db = mc->min_level_db; p.max_abs = mc->max_abs_value;
+    p.out = out_dev;
+    const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 4 + 16;
+    if (cudaFuncSetAttribute(wn_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");
+    }
+    const long long items = (long long)rows * p.frames;
+    const int grid = (int)std::min<long long>(items, 148LL * 16);
+    wn_mel_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: launch failed");
+    return WN_OK;
 }
 
 }  // extern "C"

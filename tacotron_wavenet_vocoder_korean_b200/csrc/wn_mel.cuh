@@ -1,0 +1,89 @@
+// wn_mel.cuh -- STFT -> mel -> dB -> normalise (the reference's utils/audio.py:69-75 melspectrogram chain:
+// preemphasis :22-25, librosa.stft(n_fft, hop, win) :139-143, mel basis dot :181-199, _amp_to_db :201-203,
+// _normalize :208-212) as one sm_100a kernel: one CTA per frame.
+//
+// librosa evaluates the FFT in float64 (the pre-emphasised signal is float64) and stores complex64; a float32
+// FFT would miss the 1e-4 tolerance in bands far below the frame's peak (absolute error ~1e-7 * peak), so the
+// FFT runs in fp64 in shared memory (B200 has full-rate fp64 units; 2048 points x 11 radix-2 stages is ~0.25
+// MFLOP per frame), components are rounded to fp32 like complex64, and everything after is fp32 like numpy.
+// Included by wn_api.cu (single translation unit).
+#pragma once
+
+struct WnMelParams {
+    const float *wav;          // [rows][n]
+    long long n;               // samples per row
+    int rows, frames;          // frames = 1 + n / hop
+    int n_fft, log2n, hop, win, win_off;   // win_off = (n_fft - win) / 2
+    int n_mels, n_bins;        // n_bins = n_fft/2 + 1
+    const double *window;      // [win]  periodic Hann
+    const double2 *twiddle;    // [n_fft/2]  exp(-2 pi i k / n_fft)
+    const int *mel_start;      // [n_mels] first non-zero bin
+    const int *mel_len;        // [n_mels]
+    const int *mel_off;        // [n_mels] offset into mel_w
+    const float *mel_w;        // packed non-zero filter weights
+    double preemph;            // 0 disables
+    float min_level, ref_level_db, min_level_db, max_abs;
+    float *out;                // [rows][frames][n_mels]
+};
+
+extern "C" __global__ void __launch_bounds__(256) wn_mel_kernel(const WnMelParams p)
+{
+    extern __shared__ __align__(16) unsigned char mel_smem[];
+    double2 *buf = reinterpret_cast<double2 *>(mel_smem);                  // [n_fft]
+    float *mag = reinterpret_cast<float *>(buf + p.n_fft);                 // [n_bins]
+    const int tid = threadIdx.x;
+    const int nth = blockDim.x;
+    for (long long item = blockIdx.x; item < (long long)p.rows * p.frames; item += gridDim.x) {
+        const int row = (int)(item / p.frames), f = (int)(item % p.frames);
+        const float *x = p.wav + (size_t)row * p.n;
+        // 1. windowed, pre-emphasised, reflect-padded frame, stored in bit-reversed order
+        for (int i = tid; i < p.n_fft; i += nth) {
+            double v = 0.0;
+            const int wi = i - p.win_off;
+            if (wi >= 0 && wi < p.win) {
+                long long q = (long long)f * p.hop + i - p.n_fft / 2;
+                if (q < 0) q = -q;
+                if (q >= p.n) q = 2 * (p.n - 1) - q;
+                double y = (double)x[q];
+                if (p.preemph != 0.0 && q > 0) y = __dadd_rn(y, __dmul_rn(-p.preemph, (double)x[q - 1]));
+                v = __dmul_rn(p.window[wi], y);
+            }
+            const unsigned r = __brev((unsigned)i) >> (32 - p.log2n);
+            buf[r] = make_double2(v, 0.0);
+        }
+        __syncthreads();
+        // 2. radix-2 decimation-in-time FFT, fp64
+        for (int s = 1; s <= p.log2n; ++s) {
+            const int half = 1 << (s - 1);
+            const int tw_stride = (p.n_fft >> 1) >> (s - 1);
+            for (int j = tid; j < (p.n_fft >> 1); j += nth) {
+                const int pos = j & (half - 1);
+                const int i0 = ((j >> (s - 1)) << s) + pos, i1 = i0 + half;
+                const double2 w = p.twiddle[pos * tw_stride];
+                const double2 a = buf[i0], b = buf[i1];
+                const double tr = w.x * b.x - w.y * b.y, ti = w.x * b.y + w.y * b.x;
+                buf[i0] = make_double2(a.x + tr, a.y + ti);
+                buf[i1] = make_double2(a.x - tr, a.y - ti);
+            }
+            __syncthreads();
+        }
+        // 3. |D| with the components rounded to fp32 first (complex64), np.abs -> hypot
+        for (int k = tid; k < p.n_bins; k += nth) {
+            const double re = (double)(float)buf[k].x, im = (double)(float)buf[k].y;
+            mag[k] = (float)sqrt(re * re + im * im);
+        }
+        __syncthreads();
+        // 4. mel filterbank (sparse triangles), dB, reference level, symmetric normalisation + clip; all fp32
+        if (tid < p.n_mels) {
+            const float *w = p.mel_w + p.mel_off[tid];
+            const float *m = mag + p.mel_start[tid];
+            float acc = 0.0f;
+            for (int j = 0; j < p.mel_len[tid]; ++j) acc = __fmaf_rn(w[j], m[j], acc);
+            float S = __fsub_rn(__fmul_rn(20.0f, log10f(fmaxf(p.min_level, acc))), p.ref_level_db);
+            float v = __fsub_rn(__fmul_rn(2.0f * p.max_abs, __fdiv_rn(__fsub_rn(S, p.min_level_db), -p.min_level_db)), p.max_abs);
+            v = fminf(fmaxf(v, -p.max_abs), p.max_abs);
+            p.out[((size_t)row * p.frames + f) * p.n_mels + tid] = v;
+        }
+        __syncthreads();
+    }
+}
