@@ -27,6 +27,15 @@ hparams = HParams(
     dilations=[1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 5,
     residual_channels=32, dilation_channels=32, quantization_channels=256, out_channels=30,
     skip_channels=512, use_biases=True, initial_filter_width=32, upsample_factor=[5, 5, 12],
+    # tacotron (hparams.py:124-166)
+    cleaners='korean_cleaners', model_type='deepvoice', speaker_embedding_size=16, embedding_size=256, dropout_prob=0.5,
+    enc_prenet_sizes=[256, 128], enc_bank_size=16, enc_bank_channel_size=128, enc_maxpool_width=2, enc_highway_depth=4,
+    enc_rnn_size=128, enc_proj_sizes=[128, 128], enc_proj_width=3,
+    attention_type='bah_mon_norm', attention_size=256, attention_state_size=256,
+    dec_layer_num=2, dec_rnn_size=256, dec_prenet_sizes=[256, 128],
+    post_bank_size=8, post_bank_channel_size=128, post_maxpool_width=2, post_highway_depth=4, post_rnn_size=128,
+    post_proj_sizes=[256, 80], post_proj_width=3, reduction_factor=5, min_tokens=30, min_iters=30, max_iters=200,
+    num_freq=1025, num_symbols=80,
 )
 
 PARAMS_NAME = "params.json"

@@ -120,3 +120,166 @@ def tiny_mulaw(batch_size=2):
                 dilation_channels=16, skip_channels=64, quantization_channels=256, use_biases=True,
                 scalar_input=False, initial_filter_width=32, global_condition_channels=None,
                 global_condition_cardinality=None, local_condition_channels=None, upsample_factor=None)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Tacotron.  Variable names follow the reference's TF scopes where they are
+# fixed by its own code (tacotron.py:46, modules.py:15-96: model/inference/{embedding, speaker_embedding,
+# dense*, prenet, encoder_cbhg, post_cbhg}); the decoder-cell names come from tf.contrib wrappers and are
+# not pinned by the reference, so short names under model/inference/decoder/ are used.
+TACO_HP = dict(
+    num_symbols=80, embedding_size=256, speaker_embedding_size=16, model_type='deepvoice',
+    enc_prenet_sizes=[256, 128], enc_bank_size=16, enc_bank_channel_size=128, enc_maxpool_width=2,
+    enc_highway_depth=4, enc_rnn_size=128, enc_proj_sizes=[128, 128], enc_proj_width=3,
+    attention_type='bah_mon_norm', attention_size=256, attention_state_size=256,
+    dec_layer_num=2, dec_rnn_size=256, dec_prenet_sizes=[256, 128],
+    post_bank_size=8, post_bank_channel_size=128, post_maxpool_width=2, post_highway_depth=4,
+    post_rnn_size=128, post_proj_sizes=[256, 80], post_proj_width=3,
+    reduction_factor=5, max_iters=200, num_mels=80, num_freq=1025,
+)
+
+
+def taco_tiny(**over):
+    """Small Tacotron for fast parity tests (every code path of the full model, small widths)."""
+    hp = dict(TACO_HP)
+    hp.update(embedding_size=32, speaker_embedding_size=8, enc_prenet_sizes=[32, 16], enc_bank_size=4,
+              enc_bank_channel_size=16, enc_rnn_size=16, enc_proj_sizes=[16, 16], attention_size=32,
+              attention_state_size=32, dec_rnn_size=32, dec_prenet_sizes=[32, 16], post_bank_size=3,
+              post_bank_channel_size=16, post_rnn_size=16, post_proj_sizes=[32, 20], reduction_factor=2,
+              max_iters=12, num_mels=20, num_freq=65)
+    hp.update(over)
+    return hp
+
+
+def _gru_shapes(shapes, scope, n_in, units):
+    shapes[scope + '/gates/kernel'] = (n_in + units, 2 * units)
+    shapes[scope + '/gates/bias'] = (2 * units,)
+    shapes[scope + '/candidate/kernel'] = (n_in + units, units)
+    shapes[scope + '/candidate/bias'] = (units,)
+
+
+def _cbhg_shapes(shapes, scope, n_in, K, bank_ch, proj_sizes, proj_width, depth, rnn_size):
+    def conv(s, k, ci, co):
+        shapes[s + '/conv1d/kernel'] = (k, ci, co)
+        shapes[s + '/conv1d/bias'] = (co,)
+        for n in ('gamma', 'beta', 'moving_mean', 'moving_variance'):
+            shapes[s + '/batch_normalization/' + n] = (co,)
+    for k in range(1, K + 1):
+        conv('%s/conv_bank/conv1d_%d' % (scope, k), k, n_in, bank_ch)
+    ci = K * bank_ch
+    for i, co in enumerate(proj_sizes):
+        conv('%s/proj_%d' % (scope, i + 1), proj_width, ci, co)
+        ci = co
+    if ci != rnn_size:
+        shapes[scope + '/dense/kernel'] = (ci, rnn_size)
+        shapes[scope + '/dense/bias'] = (rnn_size,)
+    for i in range(depth):
+        for g in ('H', 'T'):
+            shapes['%s/highway_%d/%s/kernel' % (scope, i + 1, g)] = (rnn_size, rnn_size)
+            shapes['%s/highway_%d/%s/bias' % (scope, i + 1, g)] = (rnn_size,)
+    for d in ('fw', 'bw'):
+        _gru_shapes(shapes, '%s/bidirectional_rnn/%s/gru_cell' % (scope, d), rnn_size, rnn_size)
+
+
+def taco_weight_shapes(hp, num_speakers):
+    """Ordered {tf_variable_name: shape} of the inference graph (tacotron.py:36-219)."""
+    P = 'model/inference/'
+    s = {}
+    E = hp['embedding_size']
+    s['embedding'] = (hp['num_symbols'], E)
+    nd = 0
+    if num_speakers > 1:
+        se = hp['speaker_embedding_size']
+        s['speaker_embedding'] = (num_speakers, se)
+        for width in [hp['enc_prenet_sizes'][-1], 2 * hp['enc_rnn_size'], hp['attention_state_size']] + \
+                [hp['dec_rnn_size']] * hp['dec_layer_num']:
+            n = 'dense' if nd == 0 else 'dense_%d' % nd
+            s[n + '/kernel'] = (se, width)
+            s[n + '/bias'] = (width,)
+            nd += 1
+    ci = E
+    for i, co in enumerate(hp['enc_prenet_sizes']):
+        s['prenet/dense_%d/kernel' % (i + 1)] = (ci, co)
+        s['prenet/dense_%d/bias' % (i + 1)] = (co,)
+        ci = co
+    assert hp['enc_proj_sizes'][-1] == ci, "encoder CBHG residual needs proj_sizes[-1] == prenet width"
+    _cbhg_shapes(s, 'encoder_cbhg', ci, hp['enc_bank_size'], hp['enc_bank_channel_size'], hp['enc_proj_sizes'],
+                 hp['enc_proj_width'], hp['enc_highway_depth'], hp['enc_rnn_size'])
+    mem = 2 * hp['enc_rnn_size']
+    A = hp['attention_size']
+    s['memory_layer/kernel'] = (mem, A)
+    D = 'decoder/'
+    nm = hp['num_mels']
+    ci = nm
+    for i, co in enumerate(hp['dec_prenet_sizes']):
+        s[D + 'decoder_prenet/dense_%d/kernel' % (i + 1)] = (ci, co)
+        s[D + 'decoder_prenet/dense_%d/bias' % (i + 1)] = (co,)
+        ci = co
+    H = hp['attention_state_size']
+    _gru_shapes(s, D + 'attention_cell/gru_cell', ci + mem, H)
+    s[D + 'attention/query_layer/kernel'] = (H, A)
+    at = hp['attention_type']
+    if at in ('bah_mon_norm', 'bah_mon'):
+        s[D + 'attention/attention_v'] = (A,)
+        if at == 'bah_mon_norm':
+            s[D + 'attention/attention_g'] = ()
+            s[D + 'attention/attention_b'] = (A,)
+        s[D + 'attention/attention_score_bias'] = ()
+    elif at == 'loc_sen':
+        s[D + 'attention/attention_variable'] = (A,)
+        s[D + 'attention/attention_bias'] = (A,)
+        s[D + 'attention/location_features_convolution/kernel'] = (31, 1, 32)
+        s[D + 'attention/location_features_convolution/bias'] = (32,)
+        s[D + 'attention/location_features_layer/kernel'] = (32, A)
+    else:
+        raise ValueError("unsupported attention_type %r" % at)
+    R = hp['dec_rnn_size']
+    s[D + 'concat_projection/kernel'] = (H + mem, R)
+    s[D + 'concat_projection/bias'] = (R,)
+    for i in range(hp['dec_layer_num']):
+        _gru_shapes(s, D + 'cell_%d/gru_cell' % (i + 1), R, R)
+    s[D + 'output_projection/kernel'] = (R, nm * hp['reduction_factor'])
+    s[D + 'output_projection/bias'] = (nm * hp['reduction_factor'],)
+    assert hp['post_proj_sizes'][-1] == nm, "post CBHG residual needs proj_sizes[-1] == num_mels"
+    _cbhg_shapes(s, 'post_cbhg', nm, hp['post_bank_size'], hp['post_bank_channel_size'], hp['post_proj_sizes'],
+                 hp['post_proj_width'], hp['post_highway_depth'], hp['post_rnn_size'])
+    n = 'dense' if nd == 0 else 'dense_%d' % nd
+    s[n + '/kernel'] = (2 * hp['post_rnn_size'], hp['num_freq'])
+    s[n + '/bias'] = (hp['num_freq'],)
+    return {P + k: v for k, v in s.items()}
+
+
+def make_taco_weights(hp, num_speakers, seed=4321):
+    """Seeded synthetic Tacotron weights: Glorot-uniform kernels, TF-default-like special cases (GRU gate bias 1,
+    highway T bias -1, batch-norm statistics near identity but not identity), small random biases so that every
+    bias path is exercised, attention score bias -1.5 so that the monotonic alignment advances slowly."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name, shp in taco_weight_shapes(hp, num_speakers).items():
+        if name.endswith('embedding'):
+            w = np.clip(rng.randn(*shp), -2, 2) * 0.5
+        elif name.endswith('/gamma'):
+            w = rng.uniform(0.8, 1.2, shp)
+        elif name.endswith('/moving_variance'):
+            w = rng.uniform(0.5, 1.5, shp)
+        elif name.endswith('/beta') or name.endswith('/moving_mean'):
+            w = rng.uniform(-0.1, 0.1, shp)
+        elif name.endswith('attention_g'):
+            w = np.sqrt(1.0 / hp['attention_size']) * 4.0
+        elif name.endswith('attention_score_bias'):
+            w = -1.5
+        elif name.endswith('/bias') or name.endswith('attention_b') or name.endswith('attention_bias'):
+            w = rng.uniform(-0.05, 0.05, shp)
+            if name.endswith('gates/bias'):
+                w += 1.0
+            if '/T/bias' in name:
+                w -= 1.0
+        elif len(shp) == 1:
+            lim = np.sqrt(6.0 / (1 + shp[0]))
+            w = rng.uniform(-lim, lim, shp)
+        else:
+            rf = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
+            lim = np.sqrt(6.0 / (rf * shp[-2] + rf * shp[-1]))
+            w = rng.uniform(-lim, lim, shp)
+        out[name] = np.asarray(w, dtype=np.float32)
+    return out

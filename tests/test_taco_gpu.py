@@ -1,0 +1,138 @@
+"""GPU parity tests of the Tacotron path: libtaco_b200.so (through the C ABI, via the Tacotron class) against the
+numpy oracle on the same seeded inputs and against the committed golden fixtures.  Tolerance: 1e-4 absolute on
+float mel / linear / alignment outputs (north_star); observed errors are printed in the assertion messages."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.taco_oracle import TacotronOracle
+from tacotron_wavenet_vocoder_korean_b200 import synth
+from tacotron_wavenet_vocoder_korean_b200.tacotron import Tacotron
+from tests.taco_helpers import Bag, CASES, case, make_batch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-4
+
+
+def run_cuda(hp, ns, w, ids, lens, spk, steps, manual=None, want_linear=True):
+    m = Tacotron(Bag(hp))
+    m.load_state_dict(w)
+    if manual is not None:
+        m.is_manual_attention, m.manual_alignments = True, manual
+    m.initialize(ids, lens, ns, spk, rnn_decoder_test_mode=True, n_steps=steps, want_linear=want_linear)
+    torch.cuda.synchronize()
+    return m
+
+
+def check(m, mel, lin, al, tol=TOL):
+    e_mel = np.abs(m.mel_outputs.cpu().numpy() - mel).max()
+    e_al = np.abs(m.alignments.cpu().numpy() - al).max()
+    e_lin = np.abs(m.linear_outputs.cpu().numpy() - lin).max() if m.linear_outputs is not None else 0.0
+    assert e_mel <= tol and e_al <= tol and e_lin <= tol, "max |err| mel %.3g linear %.3g alignments %.3g" % (e_mel, e_lin, e_al)
+    return e_mel, e_lin, e_al
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_tiny_cases_match_oracle(name):
+    hp, ns, w, ids, lens, spk, steps = case(name)
+    mel, lin, al = TacotronOracle(hp, w, ns).synthesize(ids, lens, spk, max_iters=steps)
+    m = run_cuda(hp, ns, w, ids, lens, spk, steps)
+    check(m, mel, lin, al)
+    inf = m.info()
+    assert inf['kernel_launches'] > 10 and inf['dec_grid'] == inf['sm_count']
+
+
+@pytest.mark.parametrize("name", ['tiny_mon_norm', 'tiny_loc_sen'])
+def test_matches_golden_fixture(name):
+    hp, ns, w, ids, lens, spk, steps = case(name)
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'taco_%s.npz' % name))
+    m = run_cuda(hp, ns, w, g['ids'], g['lens'], spk, steps)
+    check(m, g['mel'], g['linear'], g['alignments'])
+
+
+def test_intermediate_stages_match_oracle():
+    hp, ns, w, ids, lens, spk, steps = case('tiny_mon_norm')
+    taps = {}
+    TacotronOracle(hp, w, ns).synthesize(ids, lens, spk, max_iters=steps, taps=taps)
+    m = run_cuda(hp, ns, w, ids, lens, spk, steps)
+    pairs = [('enc_prenet', 'enc_prenet'), ('enc_bank', 'encoder_cbhg/bank'), ('enc_highway_in', 'encoder_cbhg/highway_in'),
+             ('enc_rnn_in', 'encoder_cbhg/rnn_in'), ('encoder_out', 'encoder_out'), ('post_bank', 'post_cbhg/bank'),
+             ('post_highway_in', 'post_cbhg/highway_in'), ('post_rnn_in', 'post_cbhg/rnn_in'), ('post_out', 'post_out')]
+    for cname, oname in pairs:
+        ref = taps[oname]
+        got = m.debug_tensor(cname, ref.shape)
+        err = np.abs(got - ref).max()
+        assert err <= TOL, "%s: max |err| %.3g" % (cname, err)
+
+
+def test_manual_alignments_override():
+    hp, ns, w, ids, lens, spk, steps = case('tiny_mon_norm')
+    N, T_in = ids.shape
+    man = np.zeros((N, steps, T_in), np.float32)
+    for t in range(steps):
+        man[:, t, min(t, T_in - 1)] = 1.0
+    mel, lin, al = TacotronOracle(hp, w, ns).synthesize(ids, lens, spk, manual_alignments=man, max_iters=steps)
+    m = run_cuda(hp, ns, w, ids, lens, spk, steps, manual=man)
+    check(m, mel, lin, al)
+
+
+def test_full_size_model_matches_oracle():
+    """The reference's hparams.py:124-166 shapes (7.07 M parameters), 4 sentences x 40 tokens x 30 decoder steps."""
+    hp = dict(synth.TACO_HP)
+    w = synth.make_taco_weights(hp, 2)
+    ids, lens, spk = make_batch(4, 40, seed=7)
+    steps = 30
+    mel, lin, al = TacotronOracle(hp, w, 2).synthesize(ids, lens, spk, max_iters=steps)
+    m = run_cuda(hp, 2, w, ids, lens, spk, steps)
+    check(m, mel, lin, al)
+    inf = m.info()
+    assert inf['rnn_weights_in_smem'] == 1 and inf['dec_phases_per_step'] == 13
+
+
+def test_full_size_loc_sen_matches_oracle():
+    hp = dict(synth.TACO_HP, attention_type='loc_sen')
+    w = synth.make_taco_weights(hp, 2)
+    ids, lens, spk = make_batch(3, 50, seed=8)
+    steps = 20
+    mel, lin, al = TacotronOracle(hp, w, 2).synthesize(ids, lens, spk, max_iters=steps)
+    m = run_cuda(hp, 2, w, ids, lens, spk, steps)
+    check(m, mel, lin, al)
+
+
+def test_properties_at_full_batch():
+    """cfg-3 size (32 sentences, 200 decoder steps): too slow for the numpy oracle, so size-independent properties:
+    rows are independent (a sentence synthesised alone gives the same mel as inside the batch), alignments are
+    non-negative, vanish past each sentence's length and each step's total mass is <= 1 (monotonic attention),
+    and the run is deterministic."""
+    hp = dict(synth.TACO_HP)
+    w = synth.make_taco_weights(hp, 2)
+    ids, lens, spk = make_batch(32, 60, seed=9, min_len=20)
+    m = run_cuda(hp, 2, w, ids, lens, spk, 200, want_linear=False)
+    mel = m.mel_outputs.cpu().numpy()
+    al = m.alignments.cpu().numpy()
+    assert mel.shape == (32, 1000, 80) and np.isfinite(mel).all()
+    assert (al >= 0).all() and (al.sum(1) <= 1 + 1e-4).all()
+    for n in range(32):
+        assert np.all(al[n, lens[n]:, :] == 0)
+    m2 = run_cuda(hp, 2, w, ids, lens, spk, 200, want_linear=False)
+    assert np.array_equal(m2.mel_outputs.cpu().numpy(), mel)
+    for n in (0, 5, 31):
+        m1 = run_cuda(hp, 2, w, ids[n:n + 1, :lens[n]], lens[n:n + 1], spk[n:n + 1], 200, want_linear=False)
+        e = np.abs(m1.mel_outputs.cpu().numpy()[0] - mel[n]).max()
+        assert e <= TOL, "row %d alone vs in batch: %.3g" % (n, e)
+
+
+def test_synthesizer_entry_point(tmp_path):
+    from synthesizer import Synthesizer
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    w = synth.make_taco_weights({k: getattr(hparams, k) for k in synth.TACO_HP}, 2)
+    s = Synthesizer()
+    s.load(None, num_speakers=2, weights=w)
+    res = s.synthesize(texts=['존경하는 독일 국민 여러분', '고국에 계신 국민 여러분'], base_path=str(tmp_path), speaker_ids=[0, 1])
+    assert len(res) == 2
+    for r in res:
+        assert r['mel'].shape[1] == 80 and r['mel'].shape[0] <= 1000 and os.path.exists(r['mel_path'])
+        assert np.array_equal(np.load(r['mel_path']), r['mel'])
