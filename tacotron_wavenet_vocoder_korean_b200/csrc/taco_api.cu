@@ -469,11 +469,18 @@ int taco_finalize(taco_handle *h) {
     const int smem = dec_smem_bytes(h, 1024, 1);
     if (smem > (int)prop.sharedMemPerBlockOptin)
         return fail(h, TACO_ERR_ARG, "decoder weight slices + staging (" + std::to_string(smem) + " B) exceed the shared memory of one SM");
-    CK(cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, taco_decoder_kernel));
+    const int dec_dyn_max = (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;   // static + dynamic share the opt-in limit
+    if (smem > dec_dyn_max)
+        return fail(h, TACO_ERR_ARG, "decoder weight slices + staging (" + std::to_string(smem) + " B) exceed the shared memory of one SM");
+    CK(cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_dyn_max));
     const int Umax = std::max(c.enc_rnn_size, c.post_rnn_size);
     const size_t rnn_smem = ((size_t)3 * Umax + (size_t)Umax * 3 * Umax) * sizeof(float);
     h->rnn_w_in_smem = rnn_smem <= prop.sharedMemPerBlockOptin ? 1 : 0;
-    CK(cudaFuncSetAttribute(taco_bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncGetAttributes(&fa, taco_bigru_kernel));
+    CK(cudaFuncSetAttribute(taco_bigru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes));
+    h->smem_optin = prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
     {
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, taco_decoder_kernel, DEC_THREADS, (size_t)smem));
@@ -536,9 +543,9 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     const size_t MT = (size_t)N * T_in, MP = (size_t)N * Tm;
     struct WS {
         float *emb, *pre[2], *spk, *spk_out[3 + TACO_MAX_DEC_LAYERS];
-        float *e_bank, *e_proj[2], *e_hw[2], *e_xp, *memory, *keys;
+        float *e_bank, *e_proj[2], *e_hw[3], *e_xp, *memory, *keys;
         float *db[DB_COUNT], *score, *state[2];
-        float *p_bank, *p_proj[2], *p_hw[2], *p_xp, *p_out;
+        float *p_bank, *p_proj[2], *p_hw[3], *p_xp, *p_out;
     } w;
     int enc_pre_max = c.embedding_size;
     for (int i = 0; i < c.n_enc_prenet; ++i) enc_pre_max = std::max(enc_pre_max, c.enc_prenet_sizes[i]);
@@ -564,6 +571,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         w.e_proj[1] = alloc(MT * e_proj_max);
         w.e_hw[0] = alloc(MT * c.enc_rnn_size);
         w.e_hw[1] = alloc(MT * c.enc_rnn_size);
+        w.e_hw[2] = h->enc.has_dense ? alloc(MT * c.enc_rnn_size) : nullptr;
         w.e_xp = alloc(MT * 6 * c.enc_rnn_size);
         w.memory = alloc(MT * mem, "encoder_out");
         w.keys = alloc(MT * A, "keys");
@@ -577,6 +585,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
             w.p_proj[1] = alloc(MP * p_proj_max);
             w.p_hw[0] = alloc(MP * c.post_rnn_size);
             w.p_hw[1] = alloc(MP * c.post_rnn_size);
+            w.p_hw[2] = h->post.has_dense ? alloc(MP * c.post_rnn_size) : nullptr;
             w.p_xp = alloc(MP * 6 * c.post_rnn_size);
             w.p_out = alloc(MP * 2 * c.post_rnn_size, "post_out");
         }
@@ -628,7 +637,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         return g;
     };
     auto cbhg = [&](const CbhgDev &D, const float *x, int B, int T, const float *before_highway, int ld_bh, const float *rnn_init,
-                    const int32_t *lens, float *bank, float *proj[2], float *hw[2], float *xp, float *out, const char *tag) {
+                    const int32_t *lens, float *bank, float *proj[2], float *hw[3], float *xp, float *out, const char *tag) {
         const size_t MM = (size_t)B * T;
         std::vector<GemmProb> grp;
         const int ldb = D.K * D.C;
@@ -647,9 +656,9 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
             cur = proj[i & 1];
             ld = D.proj[i].co;
         }
-        float *hcur = hw[0];
-        if (D.has_dense) {
-            gemm_group({mk(D.dense, cur, ld, hw[0], D.U, ACT_NONE)}, B, T);
+        float *hcur = hw[2];
+        if (D.has_dense) {   // hw[2] is not reused by the highway ping-pong, so the debug tap stays valid
+            gemm_group({mk(D.dense, cur, ld, hw[2], D.U, ACT_NONE)}, B, T);
         } else {
             // widths match: copy through a 1-tap identity is wasteful; read the projection output directly
             hcur = const_cast<float *>(cur);
