@@ -25,6 +25,7 @@ extern "C" {
 #define TACO_ERR_ARG (-1)
 #define TACO_ERR_STATE (-2)
 #define TACO_ERR_CUDA (-3)
+#define TACO_ERR_TIMEOUT (-4)    /* the persistent decoder kernel aborted on its barrier watchdog */
 
 #define TACO_MAX_PRENET 4
 #define TACO_MAX_PROJ 4
@@ -95,6 +96,8 @@ typedef struct taco_synth_args {
 
 /* Stream-ordered and asynchronous: returns after the last launch. */
 int taco_synthesize(taco_handle *h, const taco_synth_args *args, void *stream);
+/* Synchronises `stream` and reports TACO_ERR_TIMEOUT if the decoder's watchdog aborted the last launch. */
+int taco_sync_check(taco_handle *h, void *stream);
 /* Same through HOST buffers (ids in, mel/linear/alignments out), copies inside, synchronous. */
 int taco_synthesize_host(taco_handle *h, const taco_synth_args *args);
 

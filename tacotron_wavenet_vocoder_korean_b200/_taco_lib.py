@@ -46,7 +46,7 @@ class TacoSynthArgs(C.Structure):
 
 
 EXPORTS = ["taco_create", "taco_destroy", "taco_last_error", "taco_set_weight", "taco_finalize", "taco_get_info",
-           "taco_synthesize", "taco_synthesize_host", "taco_debug_get"]
+           "taco_synthesize", "taco_sync_check", "taco_synthesize_host", "taco_debug_get"]
 
 _lib = None
 
@@ -121,6 +121,7 @@ def lib():
         L.taco_finalize.argtypes = [H]
         L.taco_get_info.argtypes = [H, C.POINTER(TacoInfo)]
         L.taco_synthesize.argtypes = [H, C.POINTER(TacoSynthArgs), C.c_void_p]
+        L.taco_sync_check.argtypes = [H, C.c_void_p]
         L.taco_synthesize_host.argtypes = [H, C.POINTER(TacoSynthArgs)]
         L.taco_debug_get.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
         L.taco_debug_get.restype = C.c_int64

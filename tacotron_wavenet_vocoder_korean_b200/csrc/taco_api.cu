@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -66,8 +67,10 @@ struct taco_handle {
     // decoder plan
     DecParams dp_host;
     DecParams *dp_dev = nullptr;
+    long long *prof_dev = nullptr;            // in-kernel phase profile of the last decoder launch (TACO_PROFILE=1)
     float *dec_img = nullptr;
-    int dec_grid = 0, dec_smem = 0, dec_maxK = 0;
+    int dec_grid = 0, dec_smem = 0, dec_maxK = 0, dec_dyn_max = 0;
+    unsigned *barrier_dev = nullptr;
     size_t smem_optin = 0;
     int rnn_w_in_smem = 0;
 
@@ -249,10 +252,14 @@ int build_decoder(taco_handle *h) {
         DecPhase &ph = dp.ph[np++];
         ph.kind = PH_DENSE; ph.K = K; ph.N = N; ph.epi = epi;
         ph.ncp = (N + G - 1) / G;
-        ph.ncp4 = (ph.ncp + 3) & ~3;
+        ph.pad = ph.ncp <= 2 ? ph.ncp : ((ph.ncp + 3) & ~3);
         ph.nseg = (int)segs.size();
         int ks = 0;
-        for (int i = 0; i < ph.nseg; ++i) { ph.seg_buf[i] = segs[i].first; ph.seg_K[i] = segs[i].second; ks += segs[i].second; }
+        for (int i = 0; i < ph.nseg; ++i) {
+            ph.seg_buf[i] = segs[i].first; ph.seg_K[i] = segs[i].second; ks += segs[i].second;
+            // the candidate phase of a GRU re-reads the inputs its gates phase staged one barrier earlier
+            ph.seg_keep[i] = (epi == DE_CAND && i + 1 < ph.nseg) ? 1 : 0;
+        }
         if (ks != K) { h->err = "decoder: segment widths do not add up for " + kname; return false; }
         ph.out_buf = out_buf; ph.h_buf = h_buf; ph.res_in = res_in; ph.res_out = res_out; ph.U = U;
         h->dec_maxK = std::max(h->dec_maxK, K);
@@ -272,7 +279,7 @@ int build_decoder(taco_handle *h) {
         if (!add_dense(s + "/candidate/kernel", s + "/candidate/bias", ci + mem + H, H, DE_CAND, {{prev, ci}, {DB_CTX, mem}, {DB_RH, H}}, DB_HATT, -1, -1, -1, H))
             return TACO_ERR_STATE;
     }
-    if (!add_dense(D + "attention/query_layer/kernel", "", H, A, DE_LINEAR, {{DB_HATT, H}}, DB_Q, -1, -1, -1, 0)) return TACO_ERR_STATE;
+    if (!add_dense(D + "attention/query_layer/kernel", "", H, A, DE_QUERY, {{DB_HATT, H}}, DB_Q, -1, -1, -1, 0)) return TACO_ERR_STATE;
     dp.ph[np++].kind = PH_ATT_SCORE;
     dp.ph[np++].kind = PH_ATT_CTX;
     srcs.emplace_back();
@@ -289,15 +296,38 @@ int build_decoder(taco_handle *h) {
         return TACO_ERR_STATE;
     dp.n_phases = np;
 
+    // which input slots were final before the previous phase started (staged while waiting at the barrier)
+    {
+        int writer[DB_COUNT];
+        for (int b = 0; b < DB_COUNT; ++b) writer[b] = -100;
+        for (int i = 0; i < np; ++i) {
+            const DecPhase &ph = dp.ph[i];
+            if (ph.kind == PH_ATT_CTX) writer[DB_CTX] = i;
+            if (ph.kind != PH_DENSE) continue;
+            if (ph.epi == DE_RELU || ph.epi == DE_LINEAR) writer[ph.out_buf] = i;
+            if (ph.epi == DE_CAND) { writer[ph.out_buf] = i; if (ph.res_out >= 0) writer[ph.res_out] = i; }
+            if (ph.epi == DE_OUT) writer[DB_X] = i;
+        }
+        for (int i = 1; i < np; ++i) {
+            DecPhase &ph = dp.ph[i];
+            if (ph.kind != PH_DENSE) continue;
+            for (int sidx = 0; sidx < ph.nseg; ++sidx) {
+                const int b = ph.seg_buf[sidx];
+                const bool stable = b != DB_RH && b != DB_U && writer[b] != i - 1 && writer[b] != i;
+                ph.seg_pre[sidx] = (stable && !ph.seg_keep[sidx]) ? 1 : 0;
+            }
+        }
+    }
     // per-CTA shared-memory image
     int off = 0;
     for (int i = 0; i < np; ++i) {
         DecPhase &ph = dp.ph[i];
         if (ph.kind != PH_DENSE) continue;
+        off = (off + 3) & ~3;
         ph.w_off = off;
-        off += ph.K * ph.ncp4;
+        off += ph.K * ph.pad;
         ph.b_off = off;
-        off += ph.ncp4;
+        off += ph.pad;
     }
     dp.img_floats = off;
     std::vector<float> img((size_t)G * off, 0.f);
@@ -310,7 +340,7 @@ int build_decoder(taco_handle *h) {
             for (int cl = 0; cl < ph.ncp; ++cl) {
                 const int col = cta * ph.ncp + cl;
                 if (col >= ph.N) break;
-                for (int k = 0; k < ph.K; ++k) dst[ph.w_off + k * ph.ncp4 + cl] = s.W[(size_t)k * ph.N + col];
+                for (int k = 0; k < ph.K; ++k) dst[ph.w_off + k * ph.pad + cl] = s.W[(size_t)k * ph.N + col];
                 dst[ph.b_off + cl] = s.b[col];
             }
         }
@@ -359,14 +389,23 @@ int build_decoder(taco_handle *h) {
     return TACO_OK;
 }
 
-int dec_smem_bytes(const taco_handle *h, int T_in, int fslices) {
+struct DecSmem { int stage_floats, keys_floats, vals_floats; size_t bytes; };
+
+DecSmem dec_smem_plan(const taco_handle *h, int N, int T_in, int chunks, int fslices, size_t limit) {
     const DecParams &dp = h->dp_host;
     const int fs = (dp.mem + fslices - 1) / fslices;
+    const int cpos = (T_in + chunks - 1) / chunks;
     size_t stage = (size_t)h->dec_maxK * 32;
     stage = std::max(stage, (size_t)4 * T_in + (size_t)4 * fs + 16);
     stage = std::max(stage, (size_t)dp.A + T_in + 31 * 32 + 32 + 16);
-    const size_t fl = (size_t)((dp.img_floats + 3) & ~3) + DEC_WARPS * 4 * 32 + stage;
-    return (int)(fl * sizeof(float));
+    stage = (stage + 3) & ~(size_t)3;
+    const size_t base = (size_t)((dp.img_floats + 3) & ~3) + DEC_WARPS * 4 * 32 + 2 * (size_t)dp.A + stage;
+    DecSmem r{(int)stage, 0, 0, base * sizeof(float)};
+    // keep this CTA's key chunk / value slice in shared memory when every item has its own CTA and it fits
+    const size_t kf = (size_t)cpos * dp.A, vf = (size_t)T_in * fs;
+    if (N * chunks <= h->dec_grid && (base + kf) * sizeof(float) <= limit) { r.keys_floats = (int)kf; r.bytes += kf * sizeof(float); }
+    if (N * fslices <= h->dec_grid && r.bytes + vf * sizeof(float) <= limit) { r.vals_floats = (int)vf; r.bytes += vf * sizeof(float); }
+    return r;
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -404,6 +443,8 @@ void taco_destroy(taco_handle *h) {
     if (h->ws) cudaFree(h->ws);
     if (h->probs_dev) cudaFree(h->probs_dev);
     if (h->dp_dev) cudaFree(h->dp_dev);
+    if (h->prof_dev) cudaFree(h->prof_dev);
+    if (h->barrier_dev) cudaFree(h->barrier_dev);
     if (h->ids_lens_dev) cudaFree(h->ids_lens_dev);
     delete h;
 }
@@ -466,7 +507,7 @@ int taco_finalize(taco_handle *h) {
 
     // persistent decoder launch shape: one CTA per SM, co-resident (cooperative launch)
     h->dec_grid = h->sm_count;
-    const int smem = dec_smem_bytes(h, 1024, 1);
+    const int smem = (int)dec_smem_plan(h, 1, 1024, 1, 1, 0).bytes;
     if (smem > (int)prop.sharedMemPerBlockOptin)
         return fail(h, TACO_ERR_ARG, "decoder weight slices + staging (" + std::to_string(smem) + " B) exceed the shared memory of one SM");
     cudaFuncAttributes fa;
@@ -475,6 +516,8 @@ int taco_finalize(taco_handle *h) {
     if (smem > dec_dyn_max)
         return fail(h, TACO_ERR_ARG, "decoder weight slices + staging (" + std::to_string(smem) + " B) exceed the shared memory of one SM");
     CK(cudaFuncSetAttribute(taco_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dec_dyn_max));
+    h->dec_dyn_max = dec_dyn_max;
+    CK(cudaMalloc(&h->barrier_dev, 2 * sizeof(unsigned)));
     const int Umax = std::max(c.enc_rnn_size, c.post_rnn_size);
     const size_t rnn_smem = ((size_t)3 * Umax + (size_t)Umax * 3 * Umax) * sizeof(float);
     h->rnn_w_in_smem = rnn_smem <= prop.sharedMemPerBlockOptin ? 1 : 0;
@@ -527,7 +570,9 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     const int G = h->dec_grid;
     const int chunks = std::max(1, std::min(std::min(G / N, 8), std::max(1, T_in / 8)));
     const int fslices = std::max(1, std::min(std::min(G / N, 8), std::max(1, mem / 32)));
-    const int smem = dec_smem_bytes(h, T_in, fslices);
+    const DecSmem sp = dec_smem_plan(h, N, T_in, chunks, fslices, (size_t)h->dec_dyn_max);
+    const int smem = (int)sp.bytes;
+    if (smem > h->dec_dyn_max) return fail(h, TACO_ERR_ARG, "taco_synthesize: T_in too large for the decoder's shared-memory scratch");
     h->dec_smem = smem;
 
     // ---- workspace plan (bump allocator, two passes) ----
@@ -544,7 +589,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     struct WS {
         float *emb, *pre[2], *spk, *spk_out[3 + TACO_MAX_DEC_LAYERS];
         float *e_bank, *e_proj[2], *e_hw[3], *e_xp, *memory, *keys;
-        float *db[DB_COUNT], *score, *state[2];
+        float *db[DB_COUNT], *score, *state[2], *q_row;
         float *p_bank, *p_proj[2], *p_hw[3], *p_xp, *p_out;
     } w;
     int enc_pre_max = c.embedding_size;
@@ -576,6 +621,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         w.memory = alloc(MT * mem, "encoder_out");
         w.keys = alloc(MT * A, "keys");
         for (int b = 0; b < DB_COUNT; ++b) w.db[b] = db_width[b] ? alloc((size_t)tiles * db_width[b] * 32) : nullptr;
+        w.q_row = alloc((size_t)tiles * 32 * A);
         w.score = alloc(MT);
         w.state[0] = alloc(MT);
         w.state[1] = alloc(MT);
@@ -685,7 +731,8 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         const size_t sm = rp.w_in_smem ? need : (size_t)3 * D.U * sizeof(float);
         const int grid = std::min(2 * B, 2 * h->sm_count);
         ops.push_back([h, rp, sm, grid, st]() -> int {
-            taco_bigru_kernel<<<grid, 256, sm, st>>>(rp);
+            if (rp.U == 128) taco_bigru_reg_kernel<128><<<grid, 256, 0, st>>>(rp);     // recurrent weights in registers
+            else taco_bigru_kernel<<<grid, 256, sm, st>>>(rp);
             h->launches++;
             return cudaGetLastError() == cudaSuccess ? 0 : -1;
         });
@@ -731,6 +778,14 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     for (int b = 0; b < DB_COUNT; ++b) dp.buf[b] = w.db[b];
     dp.keys = w.keys; dp.values = w.memory; dp.lengths = lens_dev; dp.score = w.score; dp.state[0] = w.state[0]; dp.state[1] = w.state[1];
     dp.manual = a->manual_alignments_dev; dp.dec_out = a->mel_dev; dp.align = a->alignments_dev;
+    dp.q_row = w.q_row; dp.barrier = h->barrier_dev;
+    dp.stage_floats = sp.stage_floats; dp.keys_res = sp.keys_floats > 0; dp.vals_res = sp.vals_floats > 0;
+    dp.prof = nullptr;
+    if (getenv("TACO_PROFILE")) {
+        if (!h->prof_dev) CK(cudaMalloc(&h->prof_dev, (size_t)h->dec_grid * 8 * sizeof(long long)));
+        dp.prof = h->prof_dev;
+        h->taps["dec_prof"] = DevBuf{reinterpret_cast<float *>(h->prof_dev), (size_t)h->dec_grid * 16};
+    }
     DecInit di;
     memset(&di, 0, sizeof(di));
     di.n = 0;
@@ -742,6 +797,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     di.state0 = w.state[0]; di.N = N; di.tiles = tiles; di.T_in = T_in; di.dirac = c.attention_type != TACO_ATT_LOC_SEN;
     ops.push_back([h, dp, di, st, smem, G]() -> int {
         if (cudaMemcpyAsync(h->dp_dev, &dp, sizeof(dp), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        if (cudaMemsetAsync(h->barrier_dev, 0, 2 * sizeof(unsigned), st) != cudaSuccess) return -1;
         taco_dec_init_kernel<<<64, 256, 0, st>>>(di);
         h->launches++;
         const DecParams *arg = h->dp_dev;
@@ -809,11 +865,22 @@ int taco_synthesize_host(taco_handle *h, const taco_synth_args *a) {
     d.ids_dev = ids; d.mel_dev = mel; d.linear_dev = lin; d.alignments_dev = al; d.manual_alignments_dev = man;
     rc = taco_synthesize(h, &d, nullptr);
     if (rc != TACO_OK) return done();
-    CKH(cudaDeviceSynchronize());
+    rc = taco_sync_check(h, nullptr);
+    if (rc != TACO_OK) return done();
     CKH(cudaMemcpy(a->mel_dev, mel, n_mel * sizeof(float), cudaMemcpyDeviceToHost));
     if (n_lin) CKH(cudaMemcpy(a->linear_dev, lin, n_lin * sizeof(float), cudaMemcpyDeviceToHost));
     CKH(cudaMemcpy(a->alignments_dev, al, n_al * sizeof(float), cudaMemcpyDeviceToHost));
     return done();
+}
+
+int taco_sync_check(taco_handle *h, void *stream) {
+    if (!h) return TACO_ERR_ARG;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (!h->barrier_dev) return TACO_OK;
+    unsigned flags[2] = {0, 0};
+    CK(cudaMemcpy(flags, h->barrier_dev, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[1]) return fail(h, TACO_ERR_TIMEOUT, "the persistent decoder kernel aborted on its barrier watchdog");
+    return TACO_OK;
 }
 
 int64_t taco_debug_get(taco_handle *h, const char *name, float *host_out, int64_t n) {

@@ -13,11 +13,8 @@
 // the 1e-4 tolerance of north_star on float mel outputs leaves no room for bf16/tf32 tensor-core inputs in
 // a 200-step recurrence, and the GEMM-shaped encoder/post work is small (about 0.13 TFLOP for 32 sentences).
 #pragma once
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-
-namespace cg = cooperative_groups;
 
 namespace taco {
 
@@ -281,28 +278,122 @@ __global__ void __launch_bounds__(256) taco_bigru_kernel(const RnnParams p) {
     }
 }
 
+// Same recurrence with the recurrent weights in REGISTERS (U = 128: thread c of 256 owns gate column c, 128
+// registers, and half a candidate column, 64 registers), the next step's input projections prefetched during the
+// current step and a double-buffered state: three block barriers and no shared-memory weight traffic per step.
+template <int U>
+__global__ void __launch_bounds__(2 * U, 1) taco_bigru_reg_kernel(const RnnParams p) {
+    constexpr int U2 = 2 * U, UH = U / 2;
+    __shared__ __align__(16) float h_s[2][U];
+    __shared__ __align__(16) float rh_s[U];
+    __shared__ float u_s[U];
+    __shared__ float cpart[U];
+    const int dir = blockIdx.x & 1;
+    const int tid = threadIdx.x;
+    const int cc = tid & (U - 1), half = tid / U;
+    float wg[U], wc[UH];
+    {
+        const float *Wg = p.Wgh[dir], *Wc = p.Wch[dir];
+#pragma unroll
+        for (int k = 0; k < U; ++k) wg[k] = __ldg(Wg + (size_t)k * U2 + tid);
+#pragma unroll
+        for (int k = 0; k < UH; ++k) wc[k] = __ldg(Wc + (size_t)(half * UH + k) * U + cc);
+    }
+    for (int row = blockIdx.x >> 1; row < p.N; row += gridDim.x >> 1) {
+        const int len = p.lengths ? min(max(p.lengths[row], 0), p.T) : p.T;
+        __syncthreads();
+        if (tid < U) h_s[0][tid] = p.init ? p.init[(size_t)row * U2 + dir * U + tid] : 0.0f;
+        for (int i = tid; i < (p.T - len) * U; i += U2) {
+            const int t = len + i / U, c = i - (i / U) * U;
+            p.out[((size_t)row * p.T + t) * U2 + dir * U + c] = 0.0f;
+        }
+        __syncthreads();
+        float xg = 0.f, xc = 0.f;
+        if (len > 0) {
+            const int t0 = dir ? (len - 1) : 0;
+            const float *xp = p.XP + (((size_t)row * p.T + t0) * 2 + dir) * 3 * U;
+            xg = __ldg(xp + tid);
+            if (half == 0) xc = __ldg(xp + U2 + cc);
+        }
+        int cur = 0;
+        for (int s = 0; s < len; ++s) {
+            const int t = dir ? (len - 1 - s) : s;
+            float nxg = 0.f, nxc = 0.f;
+            if (s + 1 < len) {                       // prefetch the next step's input projections
+                const int tn = dir ? (t - 1) : (t + 1);
+                const float *xp = p.XP + (((size_t)row * p.T + tn) * 2 + dir) * 3 * U;
+                nxg = __ldg(xp + tid);
+                if (half == 0) nxc = __ldg(xp + U2 + cc);
+            }
+            const float *hc = h_s[cur];
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < U; k += 4) {
+                const float4 hv = *reinterpret_cast<const float4 *>(&hc[k]);
+                a0 = fmaf(hv.x, wg[k + 0], a0);
+                a1 = fmaf(hv.y, wg[k + 1], a1);
+                a2 = fmaf(hv.z, wg[k + 2], a2);
+                a3 = fmaf(hv.w, wg[k + 3], a3);
+            }
+            const float g = sigmoidf_(xg + ((a0 + a1) + (a2 + a3)));
+            if (half == 0) rh_s[cc] = g * hc[cc];
+            else u_s[cc] = g;
+            __syncthreads();
+            a0 = a1 = a2 = a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < UH; k += 4) {
+                const float4 rv = *reinterpret_cast<const float4 *>(&rh_s[half * UH + k]);
+                a0 = fmaf(rv.x, wc[k + 0], a0);
+                a1 = fmaf(rv.y, wc[k + 1], a1);
+                a2 = fmaf(rv.z, wc[k + 2], a2);
+                a3 = fmaf(rv.w, wc[k + 3], a3);
+            }
+            const float part = (a0 + a1) + (a2 + a3);
+            if (half == 1) cpart[cc] = part;
+            __syncthreads();
+            if (half == 0) {
+                const float cand = tanhf(xc + (part + cpart[cc]));
+                const float u = u_s[cc];
+                const float hn = u * hc[cc] + (1.0f - u) * cand;
+                h_s[cur ^ 1][cc] = hn;
+                p.out[((size_t)row * p.T + t) * U2 + dir * U + cc] = hn;
+            }
+            __syncthreads();
+            cur ^= 1;
+            xg = nxg;
+            xc = nxc;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Persistent decoder.
 //
 // Activations live feature-major in tiles of 32 sentences: buf[tile][feature][32], so a warp whose lane is the
-// sentence reads them conflict-free and every CTA stages a phase's whole input with coalesced 16 B loads.
+// sentence reads them conflict-free and every CTA stages a phase's whole input with coalesced 16 B copies.
 // Every dense phase is weight-stationary: CTA c owns columns [c*ncp, (c+1)*ncp) of the phase's matrix, resident in
-// shared memory for the whole launch (image built by taco_finalize).  Inside a CTA warp w sums the K-slice
-// [w*kper, (w+1)*kper) in increasing k; the 8 slice sums are added in increasing w, then the bias.
+// shared memory for the whole launch (image built by taco_finalize).  Inside a CTA warp w stages and sums the
+// K-slice [w*kper, (w+1)*kper) in increasing k; the 8 slice sums are added in increasing w, then the bias.
+// Between dependent phases the grid meets at a release/acquire counter barrier; inputs that were already final
+// before the previous phase (recurrent states) are copied into shared memory while the CTA waits there.
+// The attention phases keep their slice of the keys / values resident in shared memory when it fits.
 enum { PH_DENSE = 0, PH_ATT_SCORE = 1, PH_ATT_CTX = 2 };
-enum { DE_RELU = 0, DE_LINEAR = 1, DE_GATES = 2, DE_CAND = 3, DE_OUT = 4 };
+enum { DE_RELU = 0, DE_LINEAR = 1, DE_GATES = 2, DE_CAND = 3, DE_OUT = 4, DE_QUERY = 5 };
 enum { DB_X = 0, DB_P0, DB_P1, DB_P2, DB_P3, DB_CTX, DB_HATT, DB_RH, DB_U, DB_Q, DB_O0, DB_O1, DB_O2, DB_O3, DB_O4,
        DB_H1, DB_H2, DB_H3, DB_H4, DB_COUNT };
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_MAX_PHASES = 24;
+constexpr long long DEC_WATCHDOG_CYCLES = 6000000000LL;   // ~3 s: a lost CTA aborts the launch instead of hanging the GPU
 
 struct DecPhase {
     int kind;                 // PH_*
     int K, N;                 // dense: input features, output columns
-    int ncp, ncp4;            // columns per CTA, padded to a multiple of 4
-    int w_off, b_off;         // float offsets into the CTA's shared-memory image: [K][ncp4] then [ncp4]
+    int ncp, pad;             // columns per CTA; row stride of the CTA's weight slice (1, 2 or a multiple of 4)
+    int w_off, b_off;         // float offsets into the CTA's shared-memory image: [K][pad] then [pad]
     int nseg, seg_buf[3], seg_K[3];
+    int seg_keep[3];          // 1: this slot still holds the same, unmodified buffer from the previous dense phase (tiles == 1)
+    int seg_pre[3];           // 1: this slot's buffer was final before the PREVIOUS phase started: staged during the barrier
     int epi;                  // DE_*
     int out_buf;              // RELU/LINEAR: destination; GATES: unused; CAND: h buffer (in/out); OUT: DB_X
     int h_buf;                // GATES: state h (r*h -> DB_RH, u -> DB_U)
@@ -318,8 +409,11 @@ struct DecParams {
     int OD, nm;               // decoder output width (num_mels*r), num_mels
     int chunks, fslices;      // attention work split per sentence
     int img_floats;           // per-CTA image size (floats)
+    int stage_floats;         // staging area (floats)
+    int keys_res, vals_res;   // 1: this CTA's key chunk / value slice stays in shared memory (one item per CTA)
     const float *img;         // (grid, img_floats)
     float *buf[DB_COUNT];     // feature-major activation tiles
+    float *q_row;             // (tiles*32, A) processed query, row-major for the score phase
     const float *keys;        // (N, T_in, A)
     const float *values;      // (N, T_in, mem), zero past the length
     const int32_t *lengths;   // device (N)
@@ -331,7 +425,23 @@ struct DecParams {
     const float *manual;      // (N, n_steps, T_in) or null
     float *dec_out;           // (N, n_steps, OD)
     float *align;             // (N, T_in, n_steps)
+    unsigned *barrier;        // [0] arrival counter (zeroed before the launch), [1] abort flag
+    long long *prof;          // optional (grid, 8) cycle counters: stage, dot, dense total, score, ctx, barrier, all
 };
+
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");   // .cg: L2 only, never a stale L1 line
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -360,14 +470,38 @@ __device__ __forceinline__ void warp_scan_inplace(float *s, int n, int lane) {
     if (lane > 0) for (int i = b; i < e; ++i) s[i] += base;
 }
 
+// One warp copies rows [kb, ke) of a dense phase's input (segments are contiguous [K_s][32] blocks in global
+// memory) into the staging area with 16 B cp.async; `mode` selects the slots: 0 = every slot that is not already
+// valid (kept from the previous phase or prefetched), 1 = only the prefetchable slots.
+__device__ __forceinline__ void stage_rows(const DecParams &P, const DecPhase &ph, float *stage, int tile, int kb, int ke, int lane,
+                                           bool keep_ok, bool pre_done, int mode) {
+    int koff = 0;
+    for (int s = 0; s < ph.nseg; ++s) {
+        const int Ks = ph.seg_K[s];
+        bool want;
+        if (mode == 1) want = ph.seg_pre[s] != 0;
+        else want = !((ph.seg_keep[s] && keep_ok) || (ph.seg_pre[s] && pre_done));
+        const int sb = max(kb, koff), se = min(ke, koff + Ks);
+        if (want && sb < se) {
+            const float *src = P.buf[ph.seg_buf[s]] + ((size_t)tile * Ks + (sb - koff)) * 32;
+            float *dst = stage + sb * 32;
+            const int n4 = (se - sb) * 8;
+            for (int i = lane; i < n4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+        }
+        koff += Ks;
+    }
+}
+
 __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecParams *__restrict__ Pg) {
-    cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) float dsm[];
     __shared__ DecParams P;
+    __shared__ float s_red[2];
+    __shared__ int s_abort;
     {
         const int *src = reinterpret_cast<const int *>(Pg);
         int *dst = reinterpret_cast<int *>(&P);
         for (int i = threadIdx.x; i < (int)(sizeof(DecParams) / 4); i += blockDim.x) dst[i] = src[i];
+        if (threadIdx.x == 0) s_abort = 0;
     }
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -375,12 +509,40 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
 
     float *img = dsm;                                  // img_floats (rounded up to 4)
     float *red = img + ((P.img_floats + 3) & ~3);      // DEC_WARPS * 4 * 32
-    float *stage = red + DEC_WARPS * 4 * 32;           // max(maxK*32, attention scratch)
+    float *nv_s = red + DEC_WARPS * 4 * 32;            // A
+    float *ab_s = nv_s + P.A;                          // A
+    float *stage = ab_s + P.A;                         // stage_floats
+    float *keys_s = stage + P.stage_floats;            // chunk positions * A when keys_res
+    const int cpos = (P.T_in + P.chunks - 1) / P.chunks;
+    const int fs = (P.mem + P.fslices - 1) / P.fslices;
+    float *vals_s = keys_s + (P.keys_res ? cpos * P.A : 0);   // T_in * fs when vals_res
     for (int i = tid; i < P.img_floats; i += DEC_THREADS) img[i] = __ldg(P.img + (size_t)cta * P.img_floats + i);
+    for (int i = tid; i < P.A; i += DEC_THREADS) { nv_s[i] = __ldg(P.nv + i); ab_s[i] = __ldg(P.ab + i); }
+    if (P.keys_res && cta < P.N * P.chunks) {
+        const int n = cta / P.chunks, ch = cta - n * P.chunks;
+        const int j0 = ch * cpos, j1 = min(P.T_in, j0 + cpos);
+        const float *src = P.keys + ((size_t)n * P.T_in + j0) * P.A;
+        for (int i = tid; i < (j1 - j0) * P.A; i += DEC_THREADS) keys_s[i] = __ldg(src + i);
+    }
+    if (P.vals_res && cta < P.N * P.fslices) {
+        const int n = cta / P.fslices, sl = cta - n * P.fslices;
+        const int f0 = sl * fs, nf = min(P.mem, f0 + fs) - f0;
+        for (int i = tid; i < P.T_in * nf; i += DEC_THREADS) {
+            const int j = i / nf, f = i - j * nf;
+            vals_s[j * fs + f] = __ldg(P.values + ((size_t)n * P.T_in + j) * P.mem + f0 + f);
+        }
+    }
     __syncthreads();
 
-    for (int step = 0; step < P.n_steps; ++step) {
+    int staged_at = -2;    // global phase index at which this CTA last staged a dense phase's inputs
+    int prefetched_for = -2;
+    bool aborted = false;
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // in-kernel phase profile (cycles of thread 0), written when P.prof != null
+    const long long t_begin = clock64();
+    for (int step = 0; step < P.n_steps && !aborted; ++step) {
         for (int pi = 0; pi < P.n_phases; ++pi) {
+            const int gpi = step * P.n_phases + pi;
+            const long long t_ph = clock64();
             const DecPhase &ph = P.ph[pi];
             if (ph.kind == PH_DENSE) {
                 const int c_begin = cta * ph.ncp;
@@ -389,39 +551,60 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                     const float *Ws = img + ph.w_off;
                     const float *bs = img + ph.b_off;
                     const int kper = (ph.K + DEC_WARPS - 1) / DEC_WARPS;
-                    const int kb = warp * kper, ke = min(ph.K, kb + kper);
+                    const int kb = min(ph.K, warp * kper), ke = min(ph.K, kb + kper);
                     for (int tile = 0; tile < P.tiles; ++tile) {
-                        // stage the inputs: segments are contiguous [K_s][32] blocks
-                        __syncthreads();
-                        int koff = 0;
-                        for (int s = 0; s < ph.nseg; ++s) {
-                            const int n4 = ph.seg_K[s] * 8;
-                            const float4 *src = reinterpret_cast<const float4 *>(P.buf[ph.seg_buf[s]] + (size_t)tile * ph.seg_K[s] * 32);
-                            float4 *dst = reinterpret_cast<float4 *>(stage + koff * 32);
-                            for (int i = tid; i < n4; i += DEC_THREADS) dst[i] = __ldcg(src + i);
-                            koff += ph.seg_K[s];
-                        }
-                        __syncthreads();
+                        if (tile > 0) __syncthreads();            // epilogue readers of the previous tile are done
+                        stage_rows(P, ph, stage, tile, kb, ke, lane, P.tiles == 1 && staged_at == gpi - 1,
+                                   P.tiles == 1 && prefetched_for == gpi, 0);
+                        cp_async_wait_all();
+                        __syncwarp();
+                        staged_at = gpi;
+                        const long long t_st = clock64();
+                        pt[0] += t_st - t_ph;
                         for (int c0 = 0; c0 < ncols; c0 += 4) {
-                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-                            for (int k = kb; k < ke; ++k) {
-                                const float a = stage[k * 32 + lane];
-                                const float4 w = *reinterpret_cast<const float4 *>(&Ws[k * ph.ncp4 + c0]);
-                                a0 = fmaf(a, w.x, a0);
-                                a1 = fmaf(a, w.y, a1);
-                                a2 = fmaf(a, w.z, a2);
-                                a3 = fmaf(a, w.w, a3);
+                            const long long t_c0 = clock64();
+                            const int cl = c0 + warp;                 // epilogue column of this warp (warps 0..3)
+                            const int col = c_begin + cl;
+                            const bool ev = warp < 4 && cl < ncols;
+                            // operands of the epilogue that live in global memory: start the loads before the dot loop
+                            float pu = 0.f, phv = 0.f, po = 0.f;
+                            if (ev && ph.epi == DE_CAND) {
+                                const size_t idx = ((size_t)tile * ph.N + col) * 32 + lane;
+                                pu = __ldcg(&P.buf[DB_U][idx]);
+                                phv = __ldcg(&P.buf[ph.out_buf][idx]);
+                                if (ph.res_out >= 0) po = __ldcg(&P.buf[ph.res_in][idx]);
                             }
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                            if (ph.pad >= 4) {
+#pragma unroll 8
+                                for (int k = kb; k < ke; ++k) {
+                                    const float a = stage[k * 32 + lane];
+                                    const float4 w = *reinterpret_cast<const float4 *>(&Ws[k * ph.pad + c0]);
+                                    a0 = fmaf(a, w.x, a0);
+                                    a1 = fmaf(a, w.y, a1);
+                                    a2 = fmaf(a, w.z, a2);
+                                    a3 = fmaf(a, w.w, a3);
+                                }
+                            } else if (ph.pad == 2) {
+#pragma unroll 8
+                                for (int k = kb; k < ke; ++k) {
+                                    const float a = stage[k * 32 + lane];
+                                    const float2 w = *reinterpret_cast<const float2 *>(&Ws[k * 2]);
+                                    a0 = fmaf(a, w.x, a0);
+                                    a1 = fmaf(a, w.y, a1);
+                                }
+                            } else {
+#pragma unroll 8
+                                for (int k = kb; k < ke; ++k) a0 = fmaf(stage[k * 32 + lane], Ws[k], a0);
+                            }
+                            pt[1] += clock64() - t_c0;
                             if (c0 > 0) __syncthreads();
                             red[(warp * 4 + 0) * 32 + lane] = a0;
                             red[(warp * 4 + 1) * 32 + lane] = a1;
                             red[(warp * 4 + 2) * 32 + lane] = a2;
                             red[(warp * 4 + 3) * 32 + lane] = a3;
                             __syncthreads();
-                            if (warp < 4 && c0 + warp < ncols) {
-                                const int cl = c0 + warp;                 // column within the CTA's slice
-                                const int col = c_begin + cl;
+                            if (ev) {
                                 float v = 0.f;
 #pragma unroll
                                 for (int w = 0; w < DEC_WARPS; ++w) v += red[(w * 4 + warp) * 32 + lane];
@@ -434,10 +617,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                                     case DE_LINEAR:
                                         P.buf[ph.out_buf][((size_t)tile * ph.N + col) * 32 + lane] = v;
                                         break;
+                                    case DE_QUERY:
+                                        P.q_row[ti * ph.N + col] = v;
+                                        break;
                                     case DE_GATES: {
                                         const float g = sigmoidf_(v);
                                         if (col < ph.U) {
-                                            const float hv = __ldcg(&P.buf[ph.h_buf][((size_t)tile * ph.U + col) * 32 + lane]);
+                                            // the state h is the last staged segment: rows [K-U, K)
+                                            const float hv = stage[(ph.K - ph.U + col) * 32 + lane];
                                             P.buf[DB_RH][((size_t)tile * ph.U + col) * 32 + lane] = g * hv;
                                         } else {
                                             P.buf[DB_U][((size_t)tile * ph.U + (col - ph.U)) * 32 + lane] = g;
@@ -447,11 +634,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                                     case DE_CAND: {
                                         const size_t idx = ((size_t)tile * ph.N + col) * 32 + lane;
                                         const float c = tanhf(v);
-                                        const float u = __ldcg(&P.buf[DB_U][idx]);
-                                        const float hv = __ldcg(&P.buf[ph.out_buf][idx]);
-                                        const float hn = u * hv + (1.0f - u) * c;
+                                        const float hn = pu * phv + (1.0f - pu) * c;
                                         P.buf[ph.out_buf][idx] = hn;
-                                        if (ph.res_out >= 0) P.buf[ph.res_out][idx] = __ldcg(&P.buf[ph.res_in][idx]) + hn;
+                                        if (ph.res_out >= 0) P.buf[ph.res_out][idx] = po + hn;
                                         break;
                                     }
                                     case DE_OUT: {
@@ -470,15 +655,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                 float *st_s = q_s + P.A;            // T_in (loc_sen: previous cumulative alignments)
                 float *cw_s = st_s + P.T_in;        // 31*32 conv kernel + 32 bias (loc_sen)
                 const int nitems = P.N * P.chunks;
-                const int cpos = (P.T_in + P.chunks - 1) / P.chunks;
                 const float *st_prev = P.state[step & 1];
                 for (int item = cta; item < nitems; item += G) {
                     const int n = item / P.chunks, ch = item - n * P.chunks;
                     const int len = min(max(__ldg(P.lengths + n), 0), P.T_in);
                     const int j0 = ch * cpos, j1 = min(P.T_in, j0 + cpos);
                     __syncthreads();
-                    for (int k = tid; k < P.A; k += DEC_THREADS)
-                        q_s[k] = __ldcg(&P.buf[DB_Q][((size_t)(n >> 5) * P.A + k) * 32 + (n & 31)]);
+                    for (int k = tid; k < P.A; k += DEC_THREADS) q_s[k] = __ldcg(P.q_row + (size_t)n * P.A + k);
                     if (P.att_type == 2) {
                         for (int j = tid; j < P.T_in; j += DEC_THREADS) st_s[j] = __ldcg(st_prev + (size_t)n * P.T_in + j);
                         for (int i = tid; i < 31 * 32; i += DEC_THREADS) cw_s[i] = __ldg(P.loc_conv_w + i);
@@ -498,17 +681,17 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                                 }
                                 f += cw_s[31 * 32 + lane];
                             }
-                            const float *kr = P.keys + ((size_t)n * P.T_in + j) * P.A;
+                            const float *kr = P.keys_res ? keys_s + (size_t)(j - j0) * P.A : P.keys + ((size_t)n * P.T_in + j) * P.A;
                             float part = 0.f;
                             for (int k = lane; k < P.A; k += 32) {
-                                float e = __ldg(kr + k) + q_s[k];
+                                float e = kr[k] + q_s[k];
                                 if (P.att_type == 2) {
                                     float loc = 0.f;
                                     for (int c = 0; c < 32; ++c) loc = fmaf(__shfl_sync(0xffffffffu, f, c), __ldg(P.loc_w + c * P.A + k), loc);
                                     e += loc;
                                 }
-                                e += __ldg(P.ab + k);
-                                part = fmaf(__ldg(P.nv + k), tanhf(e), part);
+                                e += ab_s[k];
+                                part = fmaf(nv_s[k], tanhf(e), part);
                             }
                             s = warp_sum(part) + P.score_bias;
                         }
@@ -523,9 +706,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                 float *w1 = pv + P.T_in;            // T_in: work
                 float *w2 = w1 + P.T_in;            // T_in: work
                 float *part = w2 + P.T_in;          // 4 * fs partial sums
-                __shared__ float s_red[2];
                 const int nitems = P.N * P.fslices;
-                const int fs = (P.mem + P.fslices - 1) / P.fslices;
                 const float *st_prev = P.state[step & 1];
                 float *st_next = P.state[(step + 1) & 1];
                 for (int item = cta; item < nitems; item += G) {
@@ -603,8 +784,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                         const int len = min(max(__ldg(P.lengths + n), 0), T_in);
                         if (g < groups) {
                             float acc = 0.f;
-                            for (int j = g; j < len; j += groups)
-                                acc = fmaf(sc[j], __ldg(P.values + ((size_t)n * T_in + j) * P.mem + f0 + f), acc);
+                            if (P.vals_res) {
+                                for (int j = g; j < len; j += groups) acc = fmaf(sc[j], vals_s[j * fs + f], acc);
+                            } else {
+                                const float *vp = P.values + (size_t)n * T_in * P.mem + f0 + f;
+#pragma unroll 4
+                                for (int j = g; j < len; j += groups) acc = fmaf(sc[j], __ldg(vp + (size_t)j * P.mem), acc);
+                            }
                             part[g * nf + f] = acc;
                         }
                         __syncthreads();
@@ -616,8 +802,42 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                     }
                 }
             }
-            grid.sync();
+            // ---- grid-wide barrier: release/acquire counter; state inputs of the next phase are staged meanwhile ----
+            const long long t_bar = clock64();
+            if (ph.kind == PH_ATT_SCORE) pt[3] += t_bar - t_ph;
+            else if (ph.kind == PH_ATT_CTX) pt[4] += t_bar - t_ph;
+            else pt[2] += t_bar - t_ph;
+            __syncthreads();
+            if (pi + 1 < P.n_phases && P.tiles == 1) {
+                const DecPhase &nx = P.ph[pi + 1];
+                if (nx.kind == PH_DENSE && (nx.seg_pre[0] | nx.seg_pre[1] | nx.seg_pre[2]) && cta * nx.ncp < nx.N) {
+                    const int kper = (nx.K + DEC_WARPS - 1) / DEC_WARPS;
+                    const int kb = min(nx.K, warp * kper), ke = min(nx.K, kb + kper);
+                    stage_rows(P, nx, stage, 0, kb, ke, lane, false, false, 1);
+                    prefetched_for = gpi + 1;
+                }
+            }
+            if (tid == 0) {
+                red_release_add(P.barrier, 1u);
+                const unsigned target = (unsigned)(gpi + 1) * (unsigned)G;
+                const long long t0 = clock64();
+                unsigned spins = 0;
+                while ((int)(ld_acquire_u32(P.barrier) - target) < 0) {
+                    if ((++spins & 1023u) == 0) {
+                        if (ld_acquire_u32(P.barrier + 1) != 0u) { s_abort = 1; break; }
+                        if (clock64() - t0 > DEC_WATCHDOG_CYCLES) { atomicExch(P.barrier + 1, 1u); s_abort = 1; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            pt[5] += clock64() - t_bar;
+            if (s_abort) { aborted = true; break; }
         }
+    }
+    cp_async_wait_all();
+    if (P.prof && tid == 0) {
+        pt[6] = clock64() - t_begin;
+        for (int i = 0; i < 8; ++i) P.prof[(size_t)cta * 8 + i] = pt[i];
     }
 }
 

@@ -116,6 +116,9 @@ class Tacotron(object):
         rc = _taco_lib.lib().taco_synthesize(self._h, C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise self._err("taco_synthesize", rc)
+        rc = _taco_lib.lib().taco_sync_check(self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise self._err("taco_sync_check", rc)
         # TacoTestHelper (helpers.py:35-41): stop after the first step at which every sentence has emitted an
         # all-zero output; dynamic_decode keeps evaluating finished rows, so truncating afterwards is equivalent.
         if n_steps is None:
