@@ -67,3 +67,39 @@ def test_scatter_generate_gather_world2():
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) is True
+
+
+# ---- end-to-end text -> wav job (pipeline.py) -----------------------------------------------------------
+class _FakeTTS(object):
+    def synthesize(self, texts, speaker_ids, **kw):
+        return [np.full(3 * len(t) + s, float(len(t)), np.float32) for t, s in zip(texts, speaker_ids)]
+
+
+def _job_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tacotron_wavenet_vocoder_korean_b200 import pipeline
+    texts = ['가' * n for n in (5, 1, 9, 3, 7)] if rank == 0 else None
+    spk = [0, 1, 0, 1, 1] if rank == 0 else None
+    out = pipeline.run_job(_FakeTTS, texts, spk, src=0)
+    if rank == 0:
+        ret.put([o.tolist() for o in out])
+    dist.destroy_process_group()
+
+
+def test_text_job_shards_and_gathers_in_order_world2():
+    from tacotron_wavenet_vocoder_korean_b200 import pipeline
+    a = pipeline.shard_sentences(['a' * n for n in (5, 1, 9, 3, 7)], 2)
+    assert sorted(i for r in a for i in r) == [0, 1, 2, 3, 4]
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_job_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp = [[float(n)] * (3 * n + s) for n, s in zip((5, 1, 9, 3, 7), (0, 1, 0, 1, 1))]
+    assert out == exp

