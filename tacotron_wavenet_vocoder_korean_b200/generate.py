@@ -62,6 +62,26 @@ def create_seed(filename, sample_rate, quantization_channels, window_size, scala
     return mu_law_encode(torch.from_numpy(audio), quantization_channels).cpu().numpy().astype(np.float32)
 
 
+def load_checkpoint(checkpoint_dir, synthetic=None):
+    """utils/__init__.py:75-90 `load(saver, sess, logdir)`: the TF checkpoint named by `<dir>/checkpoint` (or the newest
+    `model.ckpt-<step>.index`) is read with tf_bundle (no TensorFlow); `weights.npz` keyed by the same variable names
+    is the fallback interchange file; `synthetic` (a callable) supplies seeded weights for benchmarks."""
+    from . import tf_bundle
+    if synthetic is not None:
+        return synthetic()
+    prefix = tf_bundle.checkpoint_state(checkpoint_dir)
+    if prefix is not None and os.path.exists(prefix + '.index'):
+        print("  Checkpoint found: {}".format(prefix))
+        print("  Global step was: {}".format(tf_bundle.global_step_of(prefix)))
+        return tf_bundle.load_variables(prefix)
+    wpath = os.path.join(checkpoint_dir, 'weights.npz')
+    if not os.path.exists(wpath):
+        raise FileNotFoundError('no model.ckpt-<step>.index / weights.npz in %s; pass --synthetic_weights for seeded '
+                                'random weights' % checkpoint_dir)
+    print('Restoring model from {}'.format(checkpoint_dir))
+    return dict(np.load(wpath))
+
+
 def main(argv=None):
     import torch
     from .hparams import hparams, load_hparams
@@ -91,15 +111,7 @@ def main(argv=None):
                   global_condition_cardinality=config.gc_cardinality, local_condition_channels=hparams.num_mels,
                   upsample_factor=hparams.upsample_factor)
     net = WaveNetModel(train_mode=False, **kwargs)
-    wpath = os.path.join(config.checkpoint_dir, 'weights.npz')
-    if config.synthetic_weights or not os.path.exists(wpath):
-        if not config.synthetic_weights:
-            raise FileNotFoundError('%s not found (TF tensor-bundle checkpoints are not readable here); '
-                                    'pass --synthetic_weights for seeded random weights' % wpath)
-        state = synth.make_weights(**kwargs)
-    else:
-        print('Restoring model from {}'.format(config.checkpoint_dir))
-        state = dict(np.load(wpath))
+    state = load_checkpoint(config.checkpoint_dir, None if not config.synthetic_weights else (lambda: synth.make_weights(**kwargs)))
     net.load_state_dict(state)
     net.queue_initializer()
 

@@ -9,8 +9,9 @@ What is kept: text -> ids (text_to_sequence + _prepare_inputs), input_lengths = 
 end trim (:235-256) and `np.save(mel)` next to the output (:279-280) -- the `.npy` generate.py takes as --mel.
 What is not: Griffin-Lim (`inv_linear_spectrogram`, a separate vocoder), alignment
 plots (matplotlib) and the manual-attention post-passes, which crash in the reference (SURVEY.md App. E-6);
-`base_alignment_path` (fed manual alignments) is supported.  The checkpoint is `weights[-<step>].npz` keyed by TF
-variable names + `params.json` in `load_path` (the TF tensor-bundle reader is SURVEY.md's next-4).
+`base_alignment_path` (fed manual alignments) is supported.  The checkpoint is the reference's own
+`model.ckpt-<step>.{index,data-00000-of-00001}` (read by tf_bundle.py, no TensorFlow) or `weights[-<step>].npz` keyed by
+the TF variable names, next to `params.json` in `load_path`.
 """
 import argparse
 import datetime
@@ -19,7 +20,7 @@ import os
 import numpy as np
 
 from .hparams import hparams, load_hparams, PARAMS_NAME
-from .tacotron import create_model, get_most_recent_checkpoint
+from .tacotron import create_model, get_most_recent_checkpoint, load_weights
 from .text import text_to_sequence, prepare_inputs
 
 
@@ -62,15 +63,13 @@ class Synthesizer(object):
         if weights is None:
             if os.path.isdir(checkpoint_path):
                 load_path = checkpoint_path
-                checkpoint_path = (os.path.join(load_path, "weights-%d.npz" % checkpoint_step) if checkpoint_step is not None
-                                   else get_most_recent_checkpoint(load_path))
+                checkpoint_path = get_most_recent_checkpoint(load_path, checkpoint_step)
             else:
                 load_path = os.path.dirname(checkpoint_path)
             if os.path.exists(os.path.join(load_path, PARAMS_NAME)):
                 load_hparams(hparams, load_path)
             print('Loading checkpoint: %s' % checkpoint_path)
-            with np.load(checkpoint_path) as f:
-                weights = {k: f[k] for k in f.files}
+            weights = load_weights(checkpoint_path)
         print('Constructing model: %s' % model_name)
         self.model = create_model(hparams)
         self.model.load_state_dict(weights)
