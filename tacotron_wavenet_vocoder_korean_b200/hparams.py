@@ -27,6 +27,9 @@ hparams = HParams(
     dilations=[1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 5,
     residual_channels=32, dilation_channels=32, quantization_channels=256, out_channels=30,
     skip_channels=512, use_biases=True, initial_filter_width=32, upsample_factor=[5, 5, 12],
+    # wavenet training (hparams.py:54-55,84-94)
+    l2_regularization_strength=0, sample_size=15000, wavenet_batch_size=8, wavenet_learning_rate=1e-3, wavenet_decay_rate=0.5,
+    wavenet_decay_steps=300000, wavenet_clip_gradients=False, optimizer='adam',
     # tacotron (hparams.py:124-166)
     cleaners='korean_cleaners', model_type='deepvoice', speaker_embedding_size=16, embedding_size=256, dropout_prob=0.5,
     enc_prenet_sizes=[256, 128], enc_bank_size=16, enc_bank_channel_size=128, enc_maxpool_width=2, enc_highway_depth=4,

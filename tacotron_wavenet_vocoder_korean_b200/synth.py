@@ -114,6 +114,14 @@ def tiny_mol(batch_size=2):
                 global_condition_cardinality=3, local_condition_channels=20, upsample_factor=[2, 3])
 
 
+def tiny_train(batch_size=3):
+    """Small MoL model for training-step parity (all channel counts multiples of 8, as the bf16 GEMMs want)."""
+    return dict(batch_size=batch_size, dilations=[1, 2, 4, 1, 2, 4], filter_width=2, residual_channels=16,
+                dilation_channels=32, skip_channels=64, quantization_channels=256, out_channels=30,
+                use_biases=True, scalar_input=True, initial_filter_width=8, global_condition_channels=8,
+                global_condition_cardinality=3, local_condition_channels=24, upsample_factor=[2, 3])
+
+
 def tiny_mulaw(batch_size=2):
     """Small unconditioned mu-law model for fast parity tests."""
     return dict(batch_size=batch_size, dilations=[1, 2, 4, 8], filter_width=2, residual_channels=16,

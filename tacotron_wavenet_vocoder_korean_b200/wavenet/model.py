@@ -131,6 +131,10 @@ class WaveNetModel(object):
 
     def load_state_dict(self, state):
         """Restore of the non-queue variables (generate.py:157-161): {tf_variable_name: array}."""
+        if self.train_mode:
+            self._state = {k: np.array(v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+                           for k, v in state.items() if 'queue' not in k and 'ExponentialMovingAverage' not in k}
+            self._trainer = None
         with self._dev_guard():
             for name, arr in state.items():
                 if 'queue' in name or 'ExponentialMovingAverage' in name or name.startswith('optimizer'):
@@ -294,10 +298,57 @@ class WaveNetModel(object):
         """Counterpart of sess.run(net.queue_initializer), generate.py:163."""
         self._inc = None
 
-    def add_loss(self, *_a, **_k):
-        raise NotImplementedError("training (wavenet/model.py:247-312) is outside the generation hot path "
-                                  "(SURVEY.md section 8f, next-3)")
+    # ------------------------------------------------------------------ training (SURVEY.md 8f next-3)
+    def trainer(self, sample_size, dtype='bf16'):
+        """The libwn_train_b200 step for crops of `sample_size` samples, created on first use and seeded with the loaded
+        state dict (or TF-default initialisers: Glorot-uniform kernels, zero biases -- tf.global_variables_initializer,
+        train_vocoder.py:129-130)."""
+        from .train import WaveNetTrainer
+        from .. import synth
+        tr = getattr(self, '_trainer', None)
+        if tr is None or tr.sample_size != int(sample_size) or tr.dtype != dtype:
+            kw = dict(batch_size=self.batch_size, dilations=self.dilations, filter_width=self.filter_width,
+                      residual_channels=self.residual_channels, dilation_channels=self.dilation_channels,
+                      skip_channels=self.skip_channels, quantization_channels=self.quantization_channels,
+                      out_channels=self.out_channels, use_biases=self.use_biases, scalar_input=self.scalar_input,
+                      initial_filter_width=self.initial_filter_width, global_condition_channels=self.global_condition_channels,
+                      global_condition_cardinality=self.global_condition_cardinality,
+                      local_condition_channels=self.local_condition_channels, upsample_factor=self.upsample_factor)
+            state = tr.state_dict() if tr is not None else getattr(self, '_state', None)
+            new = WaveNetTrainer(sample_size, dtype=dtype, device=self.device, **kw)
+            new.load_state_dict(state if state is not None else synth.make_weights(bias_scale=0.0, **kw))
+            if tr is not None:
+                new.global_step = tr.global_step
+            self._trainer = new
+        return self._trainer
 
-    def add_optimizer(self, *_a, **_k):
-        raise NotImplementedError("training (wavenet/model.py:314-346) is outside the generation hot path "
-                                  "(SURVEY.md section 8f, next-3)")
+    def add_loss(self, input_batch, local_condition=None, global_condition_batch=None, l2_regularization_strength=None,
+                 name='wavenet', dtype='bf16'):
+        """wavenet/model.py:247-312, evaluated eagerly together with its gradients (the reference builds a symbolic loss and
+        lets `optimizer.compute_gradients` differentiate it, :327).  Sets and returns `self.loss` (1-element CUDA tensor)."""
+        if not self.train_mode:
+            raise RuntimeError("add_loss needs WaveNetModel(train_mode=True)")
+        x = torch.as_tensor(input_batch)
+        tr = self.trainer(x.reshape(self.batch_size, -1).shape[1], dtype)
+        self.loss = tr.loss_and_grads(x, local_condition, global_condition_batch, l2_regularization_strength)
+        return self.loss
+
+    def add_optimizer(self, hparams, global_step=None):
+        """wavenet/model.py:314-346: exponential-decay Adam (+ optional clip_by_global_norm(1.)) followed by the EMA update.
+        Sets `self.optimize`, a callable applying ONE update from the gradients of the last add_loss (`sess.run(net.optimize)`,
+        train_vocoder.py:169); `global_step` (an int) overrides the trainer's own counter."""
+        from .train import learning_rate_at
+        if getattr(self, '_trainer', None) is None:
+            raise RuntimeError("add_optimizer supposes that add_loss has been called (wavenet/model.py:315)")
+        tr = self._trainer
+        if global_step is not None:
+            tr.global_step = int(global_step)
+        get = (lambda k, d=None: hparams.get(k, d)) if isinstance(hparams, dict) else (lambda k, d=None: getattr(hparams, k, d))
+        clip = 1.0 if get('wavenet_clip_gradients', False) else 0.0
+
+        def optimize(grad_scale=1.0):
+            self.learning_rate = learning_rate_at(hparams, tr.global_step)
+            tr.apply(self.learning_rate, grad_scale=grad_scale, clip_norm=clip)
+            return tr.global_step
+        self.optimize = optimize
+        return optimize

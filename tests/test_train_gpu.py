@@ -1,0 +1,156 @@
+# coding: utf-8
+"""GPU parity of the WaveNet training step (libwn_train_b200.so through its C ABI) against oracle/train_oracle.py.
+fp32 mode must agree to 1e-4 (north_star tolerance on float outputs); bf16 mode -- the performance configuration of
+BASELINE configs[3] -- is checked for closeness of loss and gradient direction, and by an overfitting property."""
+import numpy as np
+import pytest
+import torch
+
+from tacotron_wavenet_vocoder_korean_b200 import synth
+from tests.train_helpers import train_case, rel_err, cosine
+
+pytestmark = pytest.mark.gpu
+
+HP = dict(wavenet_learning_rate=1e-3, wavenet_decay_rate=0.5, wavenet_decay_steps=300000, wavenet_clip_gradients=False)
+
+
+def _trainer(kw, T, dtype, w):
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.train import WaveNetTrainer
+    tr = WaveNetTrainer(T, dtype=dtype, **kw)
+    tr.load_state_dict(w)
+    return tr
+
+
+def _oracle(kw, w):
+    from oracle import train_oracle as to
+    return to.TorchWaveNetTrain(w, **kw)
+
+
+VARIANTS = {
+    'full': {},
+    'no_lc': dict(local_condition_channels=None, upsample_factor=None),
+    'no_gc': dict(global_condition_channels=None, global_condition_cardinality=None),
+    'no_bias': dict(use_biases=False),
+    'wide': dict(residual_channels=32, dilation_channels=16, skip_channels=32, initial_filter_width=32, dilations=[1, 2, 4, 8, 16]),
+}
+
+
+@pytest.mark.parametrize('variant', sorted(VARIANTS))
+def test_fp32_loss_logits_and_every_gradient_match_oracle(variant):
+    kw = dict(synth.tiny_train(3), **VARIANTS[variant])
+    T = 96 if variant != 'wide' else 120
+    w, wav, mel, gc = train_case(kw, T)
+    l2 = 0.01 if variant == 'full' else None
+    Lo, go = _oracle(kw, w).loss_and_grads(wav, mel, gc, l2)
+    tr = _trainer(kw, T, 'fp32', w)
+    L = float(tr.loss_and_grads(wav, mel, gc, l2).item())
+    raw_o = _oracle(kw, w).raw_output(wav, mel, gc)[0].detach().numpy().reshape(-1, kw['out_channels'])
+    raw = tr.debug_get('raw_output').reshape(-1, kw['out_channels'])
+    assert np.abs(raw - raw_o).max() <= 1e-4                      # north_star: 1e-4 on MoL logits
+    assert abs(L - Lo) <= 1e-4 * max(1.0, abs(Lo))
+    g = tr.state_dict('grads')
+    assert set(g) == set(go)
+    bad = {k: rel_err(g[k], go[k]) for k in go if np.abs(g[k] - go[k]).max() > 2e-4 * max(1e-2, np.abs(go[k]).max())}
+    assert not bad, bad
+
+
+def test_state_dict_round_trip_and_layout():
+    kw = synth.tiny_train(2)
+    w, *_ = train_case(kw, 48)
+    tr = _trainer(kw, 48, 'fp32', w)
+    got = tr.state_dict()
+    assert list(got) == list(synth.weight_shapes(**kw))          # tf.trainable_variables() order
+    assert all(np.array_equal(got[k], w[k]) for k in w)
+    ema = tr.state_dict('ema')
+    assert all(np.array_equal(ema[k], w[k]) for k in w)          # shadows start at the initial values
+    i = tr.info()
+    assert i['n_trainable'] == sum(int(np.prod(v.shape)) for v in w.values())
+    assert i['receptive_field'] == 2 * (1 + 2 + 4) + 1 + 7 and i['output_width'] == 48 - i['receptive_field']
+
+
+def test_adam_decay_ema_steps_match_oracle():
+    from oracle import train_oracle as to
+    kw = synth.tiny_train(2)
+    T = 72
+    w, wav, mel, gc = train_case(kw, T)
+    tr = _trainer(kw, T, 'fp32', w)
+    hp = dict(HP, wavenet_decay_steps=2)                           # make the decay visible within 3 steps
+    params = {k: v.astype(np.float64) for k, v in w.items()}
+    m = {k: np.zeros_like(v) for k, v in params.items()}
+    v = {k: np.zeros_like(vv) for k, vv in params.items()}
+    ema = {k: vv.copy() for k, vv in params.items()}
+    for step in range(3):
+        _, g = to.TorchWaveNetTrain({k: a.astype(np.float32) for k, a in params.items()}, **kw).loss_and_grads(wav, mel, gc)
+        to.adam_ema_step(params, g, m, v, ema, step + 1, to.learning_rate(1e-3, step, 2, 0.5))
+        tr.train_step(wav, mel, gc, hp)
+    got, got_ema = tr.state_dict(), tr.state_dict('ema')
+    for k in params:
+        assert np.abs(got[k] - params[k]).max() <= 3e-5, k
+        assert np.abs(got_ema[k] - ema[k]).max() <= 1e-5, k
+    assert tr.global_step == 3
+
+
+def test_clip_by_global_norm():
+    from oracle import train_oracle as to
+    kw = synth.tiny_train(2)
+    T = 72
+    w, wav, mel, gc = train_case(kw, T)
+    w = {k: v * (4.0 if k.endswith('conv1d_2/kernel') else 1.0) for k, v in w.items()}    # make the norm exceed 1
+    _, g = _oracle(kw, w).loss_and_grads(wav, mel, gc)
+    gn = np.sqrt(sum(float((x.astype(np.float64) ** 2).sum()) for x in g.values()))
+    tr = _trainer(kw, T, 'fp32', w)
+    tr.train_step(wav, mel, gc, dict(HP, wavenet_clip_gradients=True))
+    m = tr.state_dict('adam_m')
+    k = 'wavenet/conv1d_1/kernel'
+    np.testing.assert_allclose(m[k], 0.1 * g[k] / max(gn, 1.0), rtol=2e-3, atol=1e-7)
+
+
+def test_bf16_step_close_to_fp32_oracle():
+    kw = synth.tiny_train(3)
+    T = 96
+    w, wav, mel, gc = train_case(kw, T)
+    Lo, go = _oracle(kw, w).loss_and_grads(wav, mel, gc)
+    tr = _trainer(kw, T, 'bf16', w)
+    L = float(tr.loss_and_grads(wav, mel, gc).item())
+    assert abs(L - Lo) <= 3e-2 * max(1.0, abs(Lo))
+    g = tr.state_dict('grads')
+    big = [k for k in go if np.linalg.norm(go[k]) > 1e-3]
+    worst = min(cosine(g[k], go[k]) for k in big)
+    assert worst >= 0.98, {k: cosine(g[k], go[k]) for k in big if cosine(g[k], go[k]) < 0.98}
+
+
+def test_bf16_overfits_one_batch_at_reference_layer_sizes():
+    """30-layer R=D=128 S=512 model (BASELINE configs[3] layers) on a short crop: the loss must fall steadily when the
+    same batch is repeated, and stay finite."""
+    kw = synth.cfg2(2)
+    T = 3600
+    w, wav, mel, gc = train_case(kw, T)
+    tr = _trainer(kw, T, 'bf16', w)
+    hp = dict(HP, wavenet_learning_rate=1e-3)
+    losses = [float(tr.train_step(wav, mel, gc, hp).item()) for _ in range(12)]
+    assert all(np.isfinite(losses))
+    assert losses[-1] < losses[0] - 0.3, losses
+    i = tr.info()
+    assert i['gemm_launches'] > 0 and i['kernel_launches'] > 0 and i['flops_per_step'] > 0
+
+
+def test_wavenet_model_add_loss_add_optimizer_surface():
+    """The reference's call sequence (train_vocoder.py:100-123,169) on the drop-in class."""
+    from tacotron_wavenet_vocoder_korean_b200.wavenet import WaveNetModel
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    kw = synth.tiny_train(2)
+    T = 72
+    w, wav, mel, gc = train_case(kw, T)
+    net = WaveNetModel(train_mode=True, **kw)
+    net.load_state_dict(w)
+    net.add_loss(input_batch=torch.from_numpy(wav)[:, :, None], local_condition=mel, global_condition_batch=gc,
+                 l2_regularization_strength=None, dtype='fp32')
+    first = float(net.loss.item())
+    Lo, _ = _oracle(kw, w).loss_and_grads(wav, mel, gc)
+    assert abs(first - Lo) <= 1e-4 * max(1.0, abs(Lo))
+    net.add_optimizer(hparams, global_step=0)
+    for _ in range(5):
+        net.optimize()
+        net.add_loss(wav, mel, gc, dtype='fp32')
+    assert float(net.loss.item()) < first
+    assert abs(net.learning_rate - 1e-3 * 0.5 ** (4 / 300000.0)) < 1e-9

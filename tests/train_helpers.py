@@ -1,0 +1,34 @@
+"""Seeded inputs for the training-step parity tests (same arrays go to oracle/train_oracle.py and to the CUDA path)."""
+import numpy as np
+
+from tacotron_wavenet_vocoder_korean_b200 import synth
+
+
+def train_case(kw, T, seed=11, weight_seed=1234):
+    """-> weights, wav (N,T), mel (N,T/hop,C) or None, gc ids (N) or None."""
+    rs = np.random.RandomState(seed)
+    N = kw['batch_size']
+    w = synth.make_weights(seed=weight_seed, **kw)
+    t = np.arange(T)[None, :]
+    wav = 0.6 * np.sin(2 * np.pi * t * rs.uniform(0.01, 0.05, (N, 1)) + rs.uniform(0, 6, (N, 1))) + 0.15 * rs.randn(N, T)
+    wav = np.clip(wav, -1, 1).astype(np.float32)
+    wav[0, T - 3] = -1.0           # exercise the y < -0.999 / y > 0.999 branches of the loss
+    wav[N - 1, T - 2] = 1.0
+    mel = gc = None
+    if kw.get('local_condition_channels'):
+        hop = int(np.prod(kw['upsample_factor']))
+        assert T % hop == 0
+        mel = np.clip(rs.randn(N, T // hop, kw['local_condition_channels']) * 1.5, -4, 4).astype(np.float32)
+    if kw.get('global_condition_channels'):
+        gc = (np.arange(N) % kw['global_condition_cardinality']).astype(np.int32)
+    return w, wav, mel, gc
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-300))
