@@ -644,7 +644,7 @@ void wnt_destroy(wnt_handle *h) {
     }
     if (h->lt) cublasLtDestroy(h->lt);
     auto fr = [](void *p) { if (p) cudaFree(p); };
-    fr(h->Pc);
+    if (h->bf) fr(h->Pc);   // fp32: Pc aliases the caller's parameter buffer
     for (auto p : h->U) fr(p);
     for (auto p : h->dU) fr(p);
     for (auto p : h->X) fr(p);

@@ -130,9 +130,9 @@ def test_product_never_touches_the_oracle():
             assert not re.search(r'^\s*(from|import)\s+oracle', open(p).read(), flags=re.M)
 
 
-def test_training_entry_points_are_explicitly_out_of_scope():
+def test_training_entry_points_need_train_mode_and_a_loss_first():
     net = WaveNetModel(train_mode=False, **synth.tiny_mol())
-    with pytest.raises(NotImplementedError):
-        net.add_loss(None)
-    with pytest.raises(NotImplementedError):
-        net.add_optimizer(None, None)
+    with pytest.raises(RuntimeError):
+        net.add_loss(None)                      # generation-mode model (wavenet/model.py:26 train_mode)
+    with pytest.raises(RuntimeError):
+        net.add_optimizer(None, None)           # "Supposes that initialize function has already been called" (:315)

@@ -117,6 +117,19 @@ def test_loss_gradient_matches_finite_differences():
     assert np.all(m.loss_and_grads(wav, mel, gc, None)[1][k] == 0)
 
 
+def test_fp32_gradient_noise_floor():
+    """Why the GPU gradient tolerance is 2e-3 and not 1e-4: cdf_plus - cdf_min (mixture.py:60) cancels in fp32, so the
+    fp32 evaluation of the reference graph already differs from the fp64 one by a few 1e-4 relative per tensor."""
+    from tests.train_helpers import train_case, rel_err
+    kw = synth.tiny_train(3)
+    w, wav, mel, gc = train_case(kw, 96)
+    L32, g32 = to.TorchWaveNetTrain(w, **kw).loss_and_grads(wav, mel, gc)
+    L64, g64 = to.TorchWaveNetTrain(w, dtype=torch.float64, **kw).loss_and_grads(wav, mel, gc)
+    assert abs(L32 - L64) < 1e-4 * abs(L64)
+    errs = [rel_err(g32[k], g64[k]) for k in g64 if np.linalg.norm(g64[k]) > 0]
+    assert 5e-5 < max(errs) < 2e-3
+
+
 # ---- C ABI surface (no GPU needed) -----------------------------------------------------------------------------------
 def test_train_cabi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'wn_train_b200.h')).read()
