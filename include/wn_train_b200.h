@@ -60,6 +60,7 @@ typedef struct wnt_info {
     int32_t mel_frames;           /* local-condition frames per crop = sample_size / prod(upsample_factor) */
     int64_t gemm_launches, kernel_launches;   /* launched by this handle so far */
     double flops_per_step;        /* tensor-core GEMM flops of one forward+backward */
+    int64_t fused_launches;       /* launches of the fused tcgen05 layer kernel (R = D = 128, bf16); 0 = cuBLASLt path only */
 } wnt_info;
 
 typedef struct wnt_handle wnt_handle;

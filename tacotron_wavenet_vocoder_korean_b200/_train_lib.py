@@ -25,7 +25,8 @@ class WntConfig(C.Structure):
 class WntInfo(C.Structure):
     _fields_ = [("n_params", C.c_int64), ("n_weights", C.c_int64), ("n_trainable", C.c_int64), ("workspace_bytes", C.c_int64),
                 ("receptive_field", C.c_int32), ("output_width", C.c_int32), ("rows_per_crop", C.c_int32), ("mel_frames", C.c_int32),
-                ("gemm_launches", C.c_int64), ("kernel_launches", C.c_int64), ("flops_per_step", C.c_double)]
+                ("gemm_launches", C.c_int64), ("kernel_launches", C.c_int64), ("flops_per_step", C.c_double),
+                ("fused_launches", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -19,6 +20,7 @@
 
 #include "../../include/wn_train_b200.h"
 #include "wn_train_kernels.cuh"
+#include "wn_train_fused.cuh"
 
 using namespace wnt;
 
@@ -85,6 +87,13 @@ struct wnt_handle {
     bool count_flops = false;
     bool have_step = false;
     int sm_count = 148;
+    // fused tcgen05 forward (R = D = 128, bf16)
+    bool fused = false;
+    void *Xall = nullptr;             // all layer inputs stacked: (L*M, R) -- one TMA tensor map
+    bf16 *WfgT = nullptr, *WdT = nullptr;
+    CUtensorMap map_x, map_lc, map_wfg, map_wd;
+    unsigned *fused_err = nullptr;
+    int64_t fused_launches = 0;
 };
 
 namespace {
@@ -300,7 +309,42 @@ int refresh_copy_t(wnt_handle *h, cudaStream_t st) {
 }
 int refresh_copy(wnt_handle *h, cudaStream_t st) {
     if (!h->bf) return WNT_OK;
-    return refresh_copy_t<bf16>(h, st);
+    CKR(refresh_copy_t<bf16>(h, st));
+    if (h->fused) {
+        const long tot = (long)h->L * (wntf::NFG * wntf::KTOT + wntf::ND * wntf::ND);
+        wntf::transpose_weights_kernel<<<grid_for(tot, EW_THREADS, 8 * h->sm_count), EW_THREADS, 0, st>>>(
+            h->P, h->o_layer_w, h->layer_w_stride, h->o_wfg, h->o_wlc, h->o_wd, h->L, h->C, h->WfgT, h->WdT);
+        KCHECK();
+    }
+    return WNT_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// bf16 row-major (rows, cols) tensor, box = (box_rows, 64 columns), 128-byte swizzle, out-of-bounds elements read as zero
+int make_map(wnt_handle *h, EncodeTiledFn enc, CUtensorMap *m, void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows}, es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, WNT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %llu x %llu tensor", (int)r, (unsigned long long)rows, (unsigned long long)cols);
+    return WNT_OK;
+}
+
+int setup_fused(wnt_handle *h) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(h, WNT_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    EncodeTiledFn enc = (EncodeTiledFn)fn;
+    CKR(make_map(h, enc, &h->map_x, h->Xall, (uint64_t)h->L * h->M, 128, wntf::TILE_M));
+    if (h->C) CKR(make_map(h, enc, &h->map_lc, h->LC, (uint64_t)h->M, (uint64_t)h->C, wntf::TILE_M));
+    else h->map_lc = h->map_x;
+    CKR(make_map(h, enc, &h->map_wfg, h->WfgT, (uint64_t)h->L * wntf::NFG, wntf::KTOT, wntf::NFG));
+    CKR(make_map(h, enc, &h->map_wd, h->WdT, (uint64_t)h->L * wntf::ND, wntf::ND, wntf::ND));
+    CK(cudaFuncSetAttribute(wntf::layer_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::SMEM_BYTES));
+    return WNT_OK;
 }
 
 // ---- the step ---------------------------------------------------------------------------------------------------------
@@ -354,6 +398,26 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
         const long off = h->off[l], m = M - off;
         const T *Xl = (const T *)h->X[l];
         const T *W = Pc + lw(l);
+        if (h->fused) {
+            wntf::FusedArgs fa;
+            fa.l = l; fa.d = d; fa.off = (int)off; fa.SL = h->SL; fa.OW = h->OW; fa.T0 = T0; fa.LD = LD; fa.zs_col0 = l * D;
+            fa.do_dense = l + 1 < L ? 1 : 0; fa.has_lc = C ? 1 : 0;
+            fa.M = M; fa.x_row0 = (long)l * M;
+            fa.bias = ub ? P + lb(l) + h->o_bfg : nullptr;
+            fa.gcb = G ? h->GCB + (size_t)l * N * D2 : nullptr;
+            fa.bd = ub ? P + lb(l) + h->o_bd : nullptr;
+            fa.Xl = (const bf16 *)h->X[l];
+            fa.Xn = l + 1 < L ? (bf16 *)h->X[l + 1] : nullptr;
+            fa.TS = (bf16 *)h->TS[l];
+            fa.Zs = (bf16 *)h->Zs;
+            fa.err = h->fused_err;
+            const unsigned tiles = (unsigned)((m + wntf::TILE_M - 1) / wntf::TILE_M);
+            wntf::layer_fwd_fused_kernel<<<tiles, wntf::THREADS, wntf::SMEM_BYTES, st>>>(h->map_x, h->map_lc, h->map_wfg, h->map_wd, fa);
+            KCHECK();
+            h->fused_launches++;
+            if (h->count_flops) h->flops += 2.0 * (double)m * (D2 * (2.0 * R + C) + (l + 1 < L ? (double)D * R : 0.0));
+            continue;
+        }
         float *FG = h->FG32 + off * D2;
         CKR(gemm(h, st, false, false, m, D2, R, Xl + (off - d) * R, R, W + h->o_wfg, D2, ts, 0.f, FG, D2, FG, D2, f32));
         CKR(gemm(h, st, false, false, m, D2, R, Xl + off * R, R, W + h->o_wfg + (int64_t)R * D2, D2, ts, 1.f, FG, D2, FG, D2, f32));
@@ -593,9 +657,16 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     }
     h->X.assign(h->L, nullptr);
     h->TS.assign(h->L, nullptr);
+    h->fused = h->bf && h->R == 128 && h->D == 128 && h->C <= 128 && getenv("WNT_NO_FUSED") == nullptr;
+    A_(h->Xall, (size_t)h->L * M * h->R * e);
     for (int l = 0; l < h->L; ++l) {
-        A_(h->X[l], (size_t)M * h->R * e);
+        h->X[l] = (char *)h->Xall + (size_t)l * M * h->R * e;
         A_(h->TS[l], (size_t)M * D2 * e);
+    }
+    if (h->fused) {
+        A_(h->WfgT, (size_t)h->L * wntf::NFG * wntf::KTOT * 2);
+        A_(h->WdT, (size_t)h->L * wntf::ND * wntf::ND * 2);
+        A_(h->fused_err, 16);
     }
     A_(h->Zs, (size_t)Mo * LD * e);
     A_(h->dZs, (size_t)Mo * LD * e);
@@ -621,6 +692,7 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     A_(h->lt_ws, h->lt_ws_bytes);
 #undef A_
     if (cublasLtCreate(&h->lt) != CUBLAS_STATUS_SUCCESS) { h->err = "cublasLtCreate failed"; return bail(WNT_ERR_CUBLAS); }
+    if (h->fused) { int r_ = setup_fused(h); if (r_) return bail(r_); }
     {
         const size_t sm = ((size_t)h->ifw * h->R + 128 + h->ifw) * sizeof(float);
         if (sm > 48 * 1024) {
@@ -647,7 +719,7 @@ void wnt_destroy(wnt_handle *h) {
     if (h->bf) fr(h->Pc);   // fp32: Pc aliases the caller's parameter buffer
     for (auto p : h->U) fr(p);
     for (auto p : h->dU) fr(p);
-    for (auto p : h->X) fr(p);
+    fr(h->Xall); fr(h->WfgT); fr(h->WdT); fr(h->fused_err);
     for (auto p : h->TS) fr(p);
     void *all[] = {h->LC, h->dLC32, h->Zs, h->dZs, h->Z, h->T1, h->T2, h->dC1, h->dTot, h->dY, h->dXb, h->dFG, h->FG32, h->TOT, h->dT32, h->Y,
                    h->dX32, h->dZ32, h->GCB, h->SB, h->bsum, h->dbs, h->acc, h->lt_ws};
@@ -668,6 +740,7 @@ int wnt_get_info(const wnt_handle *h, wnt_info *info) {
     info->gemm_launches = h->gemm_launches;
     info->kernel_launches = h->kernel_launches;
     info->flops_per_step = h->flops;
+    info->fused_launches = h->fused_launches;
     return WNT_OK;
 }
 

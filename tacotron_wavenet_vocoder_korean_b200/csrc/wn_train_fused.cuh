@@ -1,0 +1,338 @@
+// wn_train_fused.cuh -- fused forward of ONE dilation layer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA),
+// for the flagship shape R = D = 128 (BASELINE configs[3]); any other shape runs the cuBLASLt path of wn_train.cu.
+//
+// Reference arithmetic (wavenet/model.py:66-101, train mode), per output row (n, tau >= off_l):
+//     [f | g] = x[tau-d] . Wfg[0] + x[tau] . Wfg[1] + lc[tau-off_l] . Wlc + b + gc[n]          (K = 128 + 128 + C)
+//     z = tanh(f) * sigmoid(g);   x_next[tau] = x[tau] + z . Wd + bd;   skip operand <- z for the last OW steps
+//
+// One CTA = one tile of 128 consecutive rows (absolute-time layout of wn_train_kernels.cuh), 2 CTAs per SM:
+//   warp 0   TMA producer: six 64-wide K blocks -- (x[tau-d], x[tau], lc) x 2 -- of A (128 x 64, bf16) and of the
+//            K-major transposed weights B (256 x 64), 128B-swizzled, through a 2-stage full/empty mbarrier ring; then
+//            the dense weights Wd^T into the freed stage.
+//   warp 1   allocates 256 TMEM columns; one lane issues tcgen05.mma (M=128, N=256, K=16) x 24 into TMEM columns
+//            [0,256), commits to `acc1_full`; later 8 x (N=128) for the dense 1x1 into columns [0,128) -> `acc2_full`.
+//   warps 2-5  epilogue: thread = row (TMEM lane).  tcgen05.ld f/g -> + bias + gc -> tanh.approx / sigmoid -> tanh,
+//            sigmoid to TS (for the backward pass), z to the skip operand and -- 128B-swizzled, as a K-major A operand --
+//            to shared memory for the dense MMA; then acc2 + x[tau] + bd -> x_next.
+// The fp32 pre-activations never exist in HBM: the cuBLASLt path moves 4.1 GB per layer for them, this kernel ~0.6 GB.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wntf {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int TILE_M = 128, KB = 64, NFG = 256, ND = 128, NKB = 6;       // rows per tile, K block, N of the two MMAs, K blocks
+constexpr int A_BYTES = TILE_M * KB * 2, B_BYTES = NFG * KB * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 16 KB + 32 KB
+constexpr int N_STAGES = 2;
+constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + 1024;                 // + slack for the 1024 B alignment
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int KTOT = 384;                                                // K of the transposed filter|gate weights (zero padded)
+
+struct FusedArgs {
+    int l, d, off, SL, OW, T0, LD, zs_col0, do_dense, has_lc;
+    long M, x_row0;               // rows per layer buffer; first row of layer l inside the stacked X tensor
+    const float *bias;            // (2D) fp32 [filter | gate] or null
+    const float *gcb;             // (N, 2D) fp32 or null
+    const float *bd;              // (R) fp32 or null
+    const bf16 *Xl;               // layer input, (M, 128)
+    bf16 *Xn;                     // layer output (M, 128), unused if !do_dense
+    bf16 *TS;                     // (M, 256): tanh | sigmoid
+    bf16 *Zs;                     // (N*OW, LD) concatenated skip operand
+    unsigned *err;                // set to 1 if a barrier wait timed out
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  ~2 s at 2 GHz, then flag + trap (the launch fails with an error).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned *err) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) atomicExch(err, 1u);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, both operands K-major
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, one swizzle atom (64 bf16) along K:
+// start address >> 4 in bits [0,14), stride byte offset (8 rows x 128 B = 1024) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B (2) in [61,64); the leading byte offset is unused for this layout (cute/arch/mma_sm100_desc.hpp).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (kind::f16): D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
+// N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_lc,
+                       const __grid_constant__ CUtensorMap map_wfg, const __grid_constant__ CUtensorMap map_wd, const FusedArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[N_STAGES], empty_bar[N_STAGES], acc1_full, z_ready, wd_full, acc2_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row0 = (long)a.off + (long)blockIdx.x * TILE_M;      // first row of the tile inside the layer buffers
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < N_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc1_full, 1);
+        mbar_init(&z_ready, 128);
+        mbar_init(&wd_full, 1);
+        mbar_init(&acc2_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const int nkb = a.has_lc ? NKB : 4;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % N_STAGES, ph = (kb / N_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1, a.err);
+                uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                if (kb < 2) tma_load_2d(sa, &map_x, &full_bar[s], kb * KB, (int)(a.x_row0 + row0 - a.d));
+                else if (kb < 4) tma_load_2d(sa, &map_x, &full_bar[s], (kb - 2) * KB, (int)(a.x_row0 + row0));
+                else tma_load_2d(sa, &map_lc, &full_bar[s], (kb - 4) * KB, (int)(row0 - a.off));
+                tma_load_2d(sb, &map_wfg, &full_bar[s], kb * KB, a.l * NFG);
+            }
+            if (a.do_dense) {
+                mbar_wait(&acc1_full, 0, a.err);                 // every filter|gate MMA has finished reading both stages
+                uint8_t *sw = smem + 1 * STAGE_BYTES;
+                mbar_expect_tx(&wd_full, 2 * ND * KB * 2);
+                tma_load_2d(sw, &map_wd, &wd_full, 0, a.l * ND);
+                tma_load_2d(sw + ND * KB * 2, &map_wd, &wd_full, KB, a.l * ND);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const int nkb = a.has_lc ? NKB : 4;
+            const uint32_t idesc1 = instr_desc(TILE_M, NFG);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % N_STAGES, ph = (kb / N_STAGES) & 1;
+                mbar_wait(&full_bar[s], ph, a.err);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint64_t da = smem_desc(sa), db = smem_desc(sb);
+#pragma unroll
+                for (int k = 0; k < KB / 16; ++k)
+                    tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kb | k) != 0 ? 1u : 0u);   // +32 B per K=16 step
+                tc_commit(&empty_bar[s]);
+            }
+            tc_commit(&acc1_full);
+            if (a.do_dense) {
+                mbar_wait(&wd_full, 0, a.err);
+                mbar_wait(&z_ready, 0, a.err);
+                tc_fence_after();
+                const uint32_t idesc2 = instr_desc(TILE_M, ND);
+                const uint32_t sz = smem_u32(smem), sw = smem_u32(smem + STAGE_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t da = smem_desc(sz + kb * A_BYTES), db = smem_desc(sw + kb * (ND * KB * 2));
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k)
+                        tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (kb | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&acc2_full);
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = row =====================
+        const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                             // row inside the tile == TMEM lane
+        const long row = row0 + r;
+        const bool valid = row < a.M;
+        const int n = valid ? (int)(row / a.T0) : 0;
+        const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const float *gb = a.gcb ? a.gcb + (size_t)n * NFG : nullptr;
+        const bool skip_row = valid && tau >= a.SL;
+        bf16 *zs_row = skip_row ? a.Zs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
+        bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
+
+        mbar_wait(&acc1_full, 0, a.err);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            const int c0 = j * 16;
+            float f[16], g[16];
+            tc_ld16(tlane + c0, f);
+            tc_ld16(tlane + 128 + c0, g);
+            tc_ld_wait();
+            uint32_t th_p[8], sg_p[8], z_p[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float f0 = f[i], f1 = f[i + 1], g0 = g[i], g1 = g[i + 1];
+                if (a.bias) {
+                    f0 += __ldg(a.bias + c0 + i); f1 += __ldg(a.bias + c0 + i + 1);
+                    g0 += __ldg(a.bias + 128 + c0 + i); g1 += __ldg(a.bias + 128 + c0 + i + 1);
+                }
+                if (gb) {
+                    f0 += __ldg(gb + c0 + i); f1 += __ldg(gb + c0 + i + 1);
+                    g0 += __ldg(gb + 128 + c0 + i); g1 += __ldg(gb + 128 + c0 + i + 1);
+                }
+                const float t0 = tanh_fast(f0), t1 = tanh_fast(f1);
+                const float s0 = fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f), s1 = fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f);
+                th_p[i >> 1] = pack2(t0, t1);
+                sg_p[i >> 1] = pack2(s0, s1);
+                z_p[i >> 1] = pack2(t0 * s0, t1 * s1);
+            }
+            if (valid) {
+                uint4 *pt = reinterpret_cast<uint4 *>(ts_row + c0), *ps = reinterpret_cast<uint4 *>(ts_row + 128 + c0);
+                pt[0] = make_uint4(th_p[0], th_p[1], th_p[2], th_p[3]);
+                pt[1] = make_uint4(th_p[4], th_p[5], th_p[6], th_p[7]);
+                ps[0] = make_uint4(sg_p[0], sg_p[1], sg_p[2], sg_p[3]);
+                ps[1] = make_uint4(sg_p[4], sg_p[5], sg_p[6], sg_p[7]);
+                if (skip_row) {
+                    uint4 *pz = reinterpret_cast<uint4 *>(zs_row + c0);
+                    pz[0] = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
+                    pz[1] = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
+                }
+            }
+            if (a.do_dense) {
+                // z as the K-major, 128B-swizzled A operand of the dense MMA: K block c0/64, 16-byte chunk index XOR (row & 7)
+                uint8_t *zt = smem + (c0 >> 6) * A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                const int ch = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4 *>(zt + (((ch) ^ (r & 7)) << 4)) = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
+                *reinterpret_cast<uint4 *>(zt + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
+            }
+        }
+        if (a.do_dense) {
+            tc_fence_before();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of z -> visible to the tensor core
+            mbar_arrive(&z_ready);
+            mbar_wait(&acc2_full, 0, a.err);
+            tc_fence_after();
+            const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND;
+            bf16 *xn_row = a.Xn + (size_t)(valid ? row : 0) * ND;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                const int c0 = j * 16;
+                float v[16];
+                tc_ld16(tlane + c0, v);
+                tc_ld_wait();
+                if (valid) {
+                    const uint4 x0 = *reinterpret_cast<const uint4 *>(x_row + c0), x1 = *reinterpret_cast<const uint4 *>(x_row + c0 + 8);
+                    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    uint32_t o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
+                        float v0 = v[2 * i] + __low2float(xb), v1 = v[2 * i + 1] + __high2float(xb);
+                        if (a.bd) {
+                            v0 += __ldg(a.bd + c0 + 2 * i);
+                            v1 += __ldg(a.bd + c0 + 2 * i + 1);
+                        }
+                        o[i] = pack2(v0, v1);
+                    }
+                    uint4 *po = reinterpret_cast<uint4 *>(xn_row + c0);
+                    po[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    po[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// K-major (transposed) bf16 copies of the per-layer kernels, rebuilt whenever the parameters change:
+//   WfgT (L*256, 384): row = l*256 + n (n: filter 0..127 | gate 128..255), column k: [0,128) tap x[tau-d], [128,256) tap x[tau],
+//                      [256, 256+C) local condition, zero beyond;   WdT (L*128, 128): row = l*128 + r, column = d.
+__global__ void transpose_weights_kernel(const float *__restrict__ P, long o_layer_w, long stride, long o_wfg, long o_wlc, long o_wd, int L,
+                                         int C, bf16 *__restrict__ WfgT, bf16 *__restrict__ WdT) {
+    const long tot1 = (long)L * NFG * KTOT, tot2 = (long)L * ND * ND;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot1 + tot2; e += (long)gridDim.x * blockDim.x) {
+        if (e < tot1) {
+            const int k = (int)(e % KTOT);
+            const long rn = e / KTOT;
+            const int n = (int)(rn % NFG), l = (int)(rn / NFG);
+            const float *W = P + o_layer_w + stride * l;
+            float v = 0.f;
+            if (k < 256) v = W[o_wfg + (long)k * NFG + n];               // (2, R, 2D) flattened: row k = tap*128 + r
+            else if (k - 256 < C) v = W[o_wlc + (long)(k - 256) * NFG + n];
+            WfgT[e] = __float2bfloat16_rn(v);
+        } else {
+            const long e2 = e - tot1;
+            const int dch = (int)(e2 % ND);
+            const long rr = e2 / ND;
+            const int r = (int)(rr % ND), l = (int)(rr / ND);
+            WdT[e2] = __float2bfloat16_rn(P[o_layer_w + stride * l + o_wd + (long)dch * ND + r]);   // Wd is (D, R) row-major
+        }
+    }
+}
+
+}  // namespace wntf

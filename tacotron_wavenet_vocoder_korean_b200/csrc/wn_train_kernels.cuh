@@ -36,6 +36,21 @@ __device__ __forceinline__ void st1(bf16 *p, size_t i, float v) { p[i] = __float
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
 
+// Gate non-linearities: exact libdevice functions in fp32 mode; in bf16 mode the result is rounded to 8 mantissa bits
+// anyway, so one MUFU.TANH each (tanh.approx.f32, |rel err| < 2^-10.9) -- sigmoid(x) = 0.5*tanh(x/2) + 0.5.
+template <typename T> struct Act {
+    static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float sigm_(float x) { return sigmoidf_(x); }
+};
+template <> struct Act<bf16> {
+    static __device__ __forceinline__ float tanh_(float x) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    static __device__ __forceinline__ float sigm_(float x) { return fmaf(0.5f, tanh_(0.5f * x), 0.5f); }
+};
+
 constexpr int EW_THREADS = 256;
 
 // Column-pair tiling shared by the row-wise kernels: `cols` is a power of two in [2, 512]; thread -> (row lane, 2 columns).
@@ -216,8 +231,8 @@ __global__ void gate_fwd_kernel(const float *__restrict__ FG, const float *__res
             const float *gb = gcb + (size_t)n * D2;
             f.x += gb[t.c]; f.y += gb[t.c + 1]; g.x += gb[D + t.c]; g.y += gb[D + t.c + 1];
         }
-        const float2 th = make_float2(tanhf(f.x), tanhf(f.y));
-        const float2 sg = make_float2(sigmoidf_(g.x), sigmoidf_(g.y));
+        const float2 th = make_float2(Act<T>::tanh_(f.x), Act<T>::tanh_(f.y));
+        const float2 sg = make_float2(Act<T>::sigm_(g.x), Act<T>::sigm_(g.y));
         st2(TS, (size_t)row * D2 + t.c, th);
         st2(TS, (size_t)row * D2 + D + t.c, sg);
         const float2 z = make_float2(th.x * sg.x, th.y * sg.y);
