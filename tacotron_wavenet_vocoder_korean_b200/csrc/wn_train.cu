@@ -401,7 +401,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
         if (h->fused) {
             wntf::FusedArgs fa;
             fa.l = l; fa.d = d; fa.off = (int)off; fa.SL = h->SL; fa.OW = h->OW; fa.T0 = T0; fa.LD = LD; fa.zs_col0 = l * D;
-            fa.do_dense = l + 1 < L ? 1 : 0; fa.has_lc = C ? 1 : 0;
+            fa.do_dense = l + 1 < L ? 1 : 0; fa.has_lc = C ? 1 : 0; fa.N = N;
             fa.M = M; fa.x_row0 = (long)l * M;
             fa.bias = ub ? P + lb(l) + h->o_bfg : nullptr;
             fa.gcb = G ? h->GCB + (size_t)l * N * D2 : nullptr;

@@ -11,7 +11,7 @@
 //            the dense weights Wd^T into the freed stage.
 //   warp 1   allocates 256 TMEM columns; one lane issues tcgen05.mma (M=128, N=256, K=16) x 24 into TMEM columns
 //            [0,256), commits to `acc1_full`; later 8 x (N=128) for the dense 1x1 into columns [0,128) -> `acc2_full`.
-//   warps 2-5  epilogue: thread = row (TMEM lane).  tcgen05.ld f/g -> + bias + gc -> tanh.approx / sigmoid -> tanh,
+//   warps 2-9  epilogue: thread = (row = TMEM lane, half of the channels).  tcgen05.ld f/g -> + bias + gc -> tanh.approx / sigmoid -> tanh,
 //            sigmoid to TS (for the backward pass), z to the skip operand and -- 128B-swizzled, as a K-major A operand --
 //            to shared memory for the dense MMA; then acc2 + x[tau] + bd -> x_next.
 // The fp32 pre-activations never exist in HBM: the cuBLASLt path moves 4.1 GB per layer for them, this kernel ~0.6 GB.
@@ -29,12 +29,13 @@ constexpr int TILE_M = 128, KB = 64, NFG = 256, ND = 128, NKB = 6;       // rows
 constexpr int A_BYTES = TILE_M * KB * 2, B_BYTES = NFG * KB * 2, STAGE_BYTES = A_BYTES + B_BYTES;   // 16 KB + 32 KB
 constexpr int N_STAGES = 2;
 constexpr int SMEM_BYTES = N_STAGES * STAGE_BYTES + 1024;                 // + slack for the 1024 B alignment
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;                  // two warps per TMEM lane quadrant, each takes half the columns
+constexpr int THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 256;
 constexpr int KTOT = 384;                                                // K of the transposed filter|gate weights (zero padded)
 
 struct FusedArgs {
-    int l, d, off, SL, OW, T0, LD, zs_col0, do_dense, has_lc;
+    int l, d, off, SL, OW, T0, LD, zs_col0, do_dense, has_lc, N;
     long M, x_row0;               // rows per layer buffer; first row of layer l inside the stacked X tensor
     const float *bias;            // (2D) fp32 [filter | gate] or null
     const float *gcb;             // (N, 2D) fp32 or null
@@ -126,6 +127,8 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[N_STAGES], empty_bar[N_STAGES], acc1_full, z_ready, wd_full, acc2_full;
     __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[2][NFG];      // layer bias + global-condition vector of the (at most two) sentences a tile touches
+    __shared__ __align__(16) float s_bd[ND];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long row0 = (long)a.off + (long)blockIdx.x * TILE_M;      // first row of the tile inside the layer buffers
@@ -136,7 +139,7 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&acc1_full, 1);
-        mbar_init(&z_ready, 128);
+        mbar_init(&z_ready, EPI_THREADS);
         mbar_init(&wd_full, 1);
         mbar_init(&acc2_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,15 +209,26 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
         }
     } else {
-        // ===================== epilogue: thread = row =====================
+        // ===================== epilogue: thread = (row, column half) =====================
         const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                        // which 64 of the 128 channels
         const int r = q * 32 + lane;                             // row inside the tile == TMEM lane
         const long row = row0 + r;
         const bool valid = row < a.M;
-        const int n = valid ? (int)(row / a.T0) : 0;
+        const int n0 = (int)(row0 / a.T0);
+        const int n = valid ? (int)(row / a.T0) : n0;
         const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float *gb = a.gcb ? a.gcb + (size_t)n * NFG : nullptr;
+        {   // stage bias (+ gc) for sentences n0 and n0+1, and the dense bias, while the MMAs run
+            const int t = threadIdx.x - 64;
+            const float b = a.bias ? a.bias[t] : 0.f;
+            const int n1 = min(n0 + 1, a.N - 1);
+            s_bias[0][t] = b + (a.gcb ? a.gcb[(size_t)n0 * NFG + t] : 0.f);
+            s_bias[1][t] = b + (a.gcb ? a.gcb[(size_t)n1 * NFG + t] : 0.f);
+            if (t < ND) s_bd[t] = a.bd ? a.bd[t] : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        }
+        const float *sb = s_bias[n - n0];
         const bool skip_row = valid && tau >= a.SL;
         bf16 *zs_row = skip_row ? a.Zs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
         bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
@@ -222,29 +236,26 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         mbar_wait(&acc1_full, 0, a.err);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            const int c0 = j * 16;
+        for (int jj = 0; jj < 4; ++jj) {
+            const int c0 = (half * 4 + jj) * 16;
             float f[16], g[16];
             tc_ld16(tlane + c0, f);
             tc_ld16(tlane + 128 + c0, g);
             tc_ld_wait();
             uint32_t th_p[8], sg_p[8], z_p[8];
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                float f0 = f[i], f1 = f[i + 1], g0 = g[i], g1 = g[i + 1];
-                if (a.bias) {
-                    f0 += __ldg(a.bias + c0 + i); f1 += __ldg(a.bias + c0 + i + 1);
-                    g0 += __ldg(a.bias + 128 + c0 + i); g1 += __ldg(a.bias + 128 + c0 + i + 1);
+            for (int i = 0; i < 16; i += 4) {
+                const float4 bf4 = *reinterpret_cast<const float4 *>(sb + c0 + i), bg4 = *reinterpret_cast<const float4 *>(sb + 128 + c0 + i);
+                const float fb[4] = {bf4.x, bf4.y, bf4.z, bf4.w}, gbv[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
+#pragma unroll
+                for (int u = 0; u < 4; u += 2) {
+                    const float t0 = tanh_fast(f[i + u] + fb[u]), t1 = tanh_fast(f[i + u + 1] + fb[u + 1]);
+                    const float s0 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u] + gbv[u])), 0.5f);
+                    const float s1 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u + 1] + gbv[u + 1])), 0.5f);
+                    th_p[(i + u) >> 1] = pack2(t0, t1);
+                    sg_p[(i + u) >> 1] = pack2(s0, s1);
+                    z_p[(i + u) >> 1] = pack2(t0 * s0, t1 * s1);
                 }
-                if (gb) {
-                    f0 += __ldg(gb + c0 + i); f1 += __ldg(gb + c0 + i + 1);
-                    g0 += __ldg(gb + 128 + c0 + i); g1 += __ldg(gb + 128 + c0 + i + 1);
-                }
-                const float t0 = tanh_fast(f0), t1 = tanh_fast(f1);
-                const float s0 = fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f), s1 = fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f);
-                th_p[i >> 1] = pack2(t0, t1);
-                sg_p[i >> 1] = pack2(s0, s1);
-                z_p[i >> 1] = pack2(t0 * s0, t1 * s1);
             }
             if (valid) {
                 uint4 *pt = reinterpret_cast<uint4 *>(ts_row + c0), *ps = reinterpret_cast<uint4 *>(ts_row + 128 + c0);
@@ -270,30 +281,29 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             tc_fence_before();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of z -> visible to the tensor core
             mbar_arrive(&z_ready);
-            mbar_wait(&acc2_full, 0, a.err);
-            tc_fence_after();
             const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND;
             bf16 *xn_row = a.Xn + (size_t)(valid ? row : 0) * ND;
-#pragma unroll 1
-            for (int j = 0; j < 8; ++j) {
-                const int c0 = j * 16;
+            // residual input of this thread's 64 channels: issued before the wait so the loads overlap the dense MMA
+            uint4 xr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
+            mbar_wait(&acc2_full, 0, a.err);
+            tc_fence_after();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (half * 4 + jj) * 16;
                 float v[16];
                 tc_ld16(tlane + c0, v);
                 tc_ld_wait();
-                if (valid) {
-                    const uint4 x0 = *reinterpret_cast<const uint4 *>(x_row + c0), x1 = *reinterpret_cast<const uint4 *>(x_row + c0 + 8);
-                    const uint32_t xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                    uint32_t o[8];
+                const uint32_t xs[8] = {xr[2 * jj].x, xr[2 * jj].y, xr[2 * jj].z, xr[2 * jj].w, xr[2 * jj + 1].x, xr[2 * jj + 1].y, xr[2 * jj + 1].z, xr[2 * jj + 1].w};
+                uint32_t o[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
-                        float v0 = v[2 * i] + __low2float(xb), v1 = v[2 * i + 1] + __high2float(xb);
-                        if (a.bd) {
-                            v0 += __ldg(a.bd + c0 + 2 * i);
-                            v1 += __ldg(a.bd + c0 + 2 * i + 1);
-                        }
-                        o[i] = pack2(v0, v1);
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
+                    const float v0 = v[2 * i] + __low2float(xb) + s_bd[c0 + 2 * i], v1 = v[2 * i + 1] + __high2float(xb) + s_bd[c0 + 2 * i + 1];
+                    o[i] = pack2(v0, v1);
+                }
+                if (valid) {
                     uint4 *po = reinterpret_cast<uint4 *>(xn_row + c0);
                     po[0] = make_uint4(o[0], o[1], o[2], o[3]);
                     po[1] = make_uint4(o[4], o[5], o[6], o[7]);
