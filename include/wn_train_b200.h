@@ -76,7 +76,8 @@ int wnt_get_info(const wnt_handle *h, wnt_info *info);
 int wnt_bind(wnt_handle *h, float *params_dev, float *grads_dev, float *adam_m_dev, float *adam_v_dev, float *ema_dev);
 
 /* Saver.restore / Saver.save by TF variable name (utils/__init__.py:62-90).  `which`: 0 params, 1 grads, 2 EMA shadow,
- * 3 Adam m, 4 Adam v.  `host` holds n floats in the TF shape.  Setting which = 0 also refreshes the compute copy. */
+ * 3 Adam m, 4 Adam v.  `host` holds n floats in the TF shape.  After writing parameters (which = 0) call
+ * wnt_params_changed once to refresh the compute-dtype copy. */
 int wnt_set_tensor(wnt_handle *h, int which, const char *name, const float *host, int64_t n);
 int64_t wnt_get_tensor(wnt_handle *h, int which, const char *name, float *host, int64_t n);   /* returns the size */
 /* Variable names, '\n'-separated, in tf.trainable_variables() order; returns the string length (copies at most n). */

@@ -27,7 +27,7 @@ def main():
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
-    from tacotron_wavenet_vocoder_korean_b200 import synth
+    from tacotron_wavenet_vocoder_korean_b200 import synth, dist as wdist
     from tacotron_wavenet_vocoder_korean_b200.wavenet.train import WaveNetTrainer
     from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -39,6 +39,7 @@ def main():
     kw = synth.cfg2(a.batch)
     tr = WaveNetTrainer(a.samples, dtype=a.dtype, **kw)
     tr.load_state_dict(synth.make_weights(**kw))
+    tr.sync_params(0)
     rs = np.random.RandomState(100 + rank)
     t = np.arange(a.samples)[None, :]
     wav = np.clip(0.5 * np.sin(2 * np.pi * t * rs.uniform(0.005, 0.05, (a.batch, 1))) + 0.1 * rs.randn(a.batch, a.samples), -1, 1).astype(np.float32)
@@ -61,10 +62,7 @@ def main():
         e0.record()
         loss = tr.loss_and_grads(wav_d, mel_d, gc_d)
         e1.record()
-        scale = 1.0
-        if world > 1:
-            dist.all_reduce(tr.grads)
-            scale = 1.0 / world
+        scale, _ = wdist.allreduce_mean_(tr.grads)
         e2.record()
         from tacotron_wavenet_vocoder_korean_b200.wavenet.train import learning_rate_at
         tr.apply(learning_rate_at(hp, tr.global_step), grad_scale=scale)
@@ -103,7 +101,7 @@ def main():
             "gemm_tflops_achieved": tf, "gemm_tflops_peak": peak, "gemm_flops_per_step": info['flops_per_step'],
             "trained_outputs_per_step": world * a.batch * info['output_width'], "scaling": "weak", "dtype": a.dtype,
             "loss_first_last": [float(losses[0].item()), float(losses[-1].item())],
-            "gemm_launches_per_step": info['gemm_launches'] // (a.warmup + a.steps), "kernel_launches_per_step": info['kernel_launches'] // (a.warmup + a.steps),
+            "gemm_launches_per_step": info['gemm_launches'] // (a.warmup + a.steps), "fused_tcgen05_launches_per_step": info['fused_launches'] // (a.warmup + a.steps), "kernel_launches_per_step": info['kernel_launches'] // (a.warmup + a.steps),
             "workspace_gb": info['workspace_bytes'] / 2 ** 30, "n_trainable": info['n_trainable'], "data": "synthetic"}))
     if world > 1:
         dist.destroy_process_group()

@@ -768,7 +768,6 @@ int wnt_set_tensor(wnt_handle *h, int which, const char *name, const float *host
     for (int o = 0; o < v.outer; ++o)
         CK(cudaMemcpy2D(base + v.base + o * v.outer_stride, (size_t)v.ld * 4, host + (size_t)o * v.rows * v.cols, (size_t)v.cols * 4, (size_t)v.cols * 4,
                         v.rows, cudaMemcpyHostToDevice));
-    if (which == 0) return refresh_copy(h, 0);
     return WNT_OK;
 }
 

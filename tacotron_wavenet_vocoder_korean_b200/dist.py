@@ -129,3 +129,28 @@ def generate_job(generate_group, state, mels, gc_ids, batch, hop, src=0, device=
         for k, w in zip(grp, res):
             waves[k] = np.asarray(w, np.float32)
     return gather_waveforms(mine, waves, meta, hop, dst=src, device=device)
+
+
+# ---- data-parallel training ------------------------------------------------------------
+def allreduce_mean_(flat_grads, loss=None):
+    """Data-parallel gradient exchange of the training step: ONE sum all-reduce of the flat fp32 gradient buffer (NCCL over
+    NVLink on the GPU box, gloo in the CPU tests); returns (grad_scale, mean loss).  The caller folds grad_scale = 1/world
+    into the Adam kernel instead of a separate pass over the buffer.  No-op without an initialised process group."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1.0, loss
+    world = dist.get_world_size()
+    dist.all_reduce(flat_grads)
+    if loss is not None:
+        loss = loss.clone()
+        dist.all_reduce(loss)
+        loss /= world
+    return 1.0 / world, loss
+
+
+def broadcast_flat_(flat_params, src=0):
+    """Every rank starts from rank `src`'s parameters (tf.train.Saver.restore on one worker + broadcast)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat_params, src=src)
+    return flat_params

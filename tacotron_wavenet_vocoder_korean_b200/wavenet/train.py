@@ -83,8 +83,10 @@ class WaveNetTrainer(object):
                     raise KeyError("variable %r missing from the state dict" % name)
                 a = np.ascontiguousarray(np.asarray(state[name], dtype=np.float32))
                 self._check(L.wnt_set_tensor(self._h, w, name.encode(), a.ctypes.data_as(C.c_void_p), a.size))
-            if which == 'params' and init_ema:
-                self.ema.copy_(self.params)
+            if which == 'params':
+                self._check(L.wnt_params_changed(self._h, self._stream()))
+                if init_ema:
+                    self.ema.copy_(self.params)
         return self
 
     def state_dict(self, which='params'):
@@ -145,19 +147,21 @@ class WaveNetTrainer(object):
     def train_step(self, input_batch, local_condition, global_condition_batch, hparams, l2_regularization_strength=None):
         """One `sess.run([global_step, loss, optimize])` (train_vocoder.py:169).  Under torch.distributed the gradients
         (and the reported loss) are averaged over ranks with one all_reduce of the flat buffer."""
-        import torch.distributed as dist
+        from .. import dist as wdist
         get = (lambda k, d=None: hparams.get(k, d)) if isinstance(hparams, dict) else (lambda k, d=None: getattr(hparams, k, d))
         loss = self.loss_and_grads(input_batch, local_condition, global_condition_batch, l2_regularization_strength)
-        scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads)
-            loss = loss.clone()
-            dist.all_reduce(loss)
-            loss /= dist.get_world_size()
-            scale = 1.0 / dist.get_world_size()
+        scale, loss = wdist.allreduce_mean_(self.grads, loss)
         lr = learning_rate_at(hparams, self.global_step)
         self.apply(lr, grad_scale=scale, clip_norm=1.0 if get('wavenet_clip_gradients', False) else 0.0)
         return loss
+
+    def sync_params(self, src=0):
+        """Broadcast rank `src`'s parameters / optimizer state to every rank and refresh the compute copy."""
+        from .. import dist as wdist
+        for t in (self.params, self.adam_m, self.adam_v, self.ema):
+            wdist.broadcast_flat_(t, src)
+        with torch.cuda.device(self.device):
+            self._check(_train_lib.lib().wnt_params_changed(self._h, self._stream()))
 
     def debug_get(self, name):
         L = _train_lib.lib()

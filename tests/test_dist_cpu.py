@@ -103,3 +103,38 @@ def test_text_job_shards_and_gathers_in_order_world2():
         assert p.exitcode == 0
     exp = [[float(n)] * (3 * n + s) for n, s in zip((5, 1, 9, 3, 7), (0, 1, 0, 1, 1))]
     assert out == exp
+
+
+# ---- data-parallel training exchange (dist.allreduce_mean_) -------------------------------------------------------------
+def _dp_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import torch
+    from tacotron_wavenet_vocoder_korean_b200 import dist as wdist
+    g = torch.arange(6, dtype=torch.float32) * (rank + 1)          # rank 0: [0..5], rank 1: 2*[0..5]
+    loss = torch.tensor([float(rank + 1)])
+    scale, mean_loss = wdist.allreduce_mean_(g, loss)
+    p = torch.full((4,), float(rank))
+    wdist.broadcast_flat_(p, src=1)
+    if rank == 0:
+        ret.put((scale, g.tolist(), float(mean_loss), float(loss), p.tolist()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_exchange_world2():
+    import torch
+    from tacotron_wavenet_vocoder_korean_b200 import dist as wdist
+    g = torch.ones(3)
+    assert wdist.allreduce_mean_(g, None) == (1.0, None) and g.tolist() == [1.0, 1.0, 1.0]     # no process group: no-op
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    scale, g, mean_loss, own_loss, p0 = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert scale == 0.5 and g == [0.0, 3.0, 6.0, 9.0, 12.0, 15.0]     # SUM in the buffer, 1/world folded into Adam
+    assert mean_loss == 1.5 and own_loss == 1.0 and p0 == [1.0] * 4
