@@ -319,13 +319,246 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of one dilation layer, two tcgen05 kernels sharing one skeleton (tile = 128 rows, N = 128 accumulator columns,
+// 3-stage TMA ring of 64-wide K blocks, 8 epilogue warps = (row, half of the channels)):
+//
+//  MODE_GATE  dz = dx_next . Wd^T (K = 128)  ->  + skip-path gradient dZs (last OW steps)  ->  gate backward with the saved
+//             tanh / sigmoid  ->  dFG = [dz*sg*(1-th^2) | dz*th*sg*(1-sg)] (exact zeros for tau < off_l), z = th*sg
+//             re-materialised for the dense weight gradient.  Replaces cast + GEMM + gate_bwd_kernel of the cuBLASLt path.
+//  MODE_DX    dx[tau] = dx_next[tau] + dFG[tau] . Wfg[1]^T + dFG[tau+d] . Wfg[0]^T  as ONE K = 512 GEMM over two row offsets
+//             of dFG, residual added in the epilogue, bf16 out.  Replaces two fp32 read-modify-write GEMMs.
+// Rows run from s_l = off_l - d (the layer's input start) so that rows [s_l, off_l) are (re)written every step.
+constexpr int BW_STAGES = 3, BW_A_BYTES = TILE_M * KB * 2, BW_B_BYTES = ND * KB * 2, BW_STAGE_BYTES = BW_A_BYTES + BW_B_BYTES;   // 16 + 16 KB
+constexpr int BW_SMEM_BYTES = BW_STAGES * BW_STAGE_BYTES + 1024;
+constexpr int BW_TMEM_COLS = 128;
+constexpr int MODE_GATE = 0, MODE_DX = 1;
+
+struct BwdArgs {
+    int l, d, off, s, SL, OW, T0, LD, zs_col0, has_dense;
+    long M;
+    const bf16 *TS;      // (M, 256) tanh | sigmoid                       MODE_GATE
+    const bf16 *dZs;     // (N*OW, LD) gradient of the skip operand        MODE_GATE
+    bf16 *dFG;           // (M, 256) out                                   MODE_GATE
+    bf16 *Z;             // (M, 128) out, may be null                      MODE_GATE
+    const bf16 *dXin;    // (M, 128) gradient w.r.t. the layer output      MODE_DX (residual)
+    bf16 *dXout;         // (M, 128) gradient w.r.t. the layer input       MODE_DX
+    unsigned *err;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 2)
+layer_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const BwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[BW_STAGES], empty_bar[BW_STAGES], acc_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long row0 = (long)a.s + (long)blockIdx.x * TILE_M;
+    const int nkb = MODE == MODE_GATE ? (a.has_dense ? 2 : 0) : 8;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < BW_STAGES; ++st) {
+            mbar_init(&full_bar[st], 1);
+            mbar_init(&empty_bar[st], 1);
+        }
+        mbar_init(&acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BW_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % BW_STAGES, ph = (kb / BW_STAGES) & 1;
+                mbar_wait(&empty_bar[st], ph ^ 1, a.err);
+                uint8_t *sa = smem + st * BW_STAGE_BYTES, *sb = sa + BW_A_BYTES;
+                mbar_expect_tx(&full_bar[st], BW_STAGE_BYTES);
+                if (MODE == MODE_GATE) tma_load_2d(sa, &map_a, &full_bar[st], kb * KB, (int)row0);
+                else tma_load_2d(sa, &map_a, &full_bar[st], (kb & 3) * KB, (int)(row0 + (kb >= 4 ? a.d : 0)));
+                tma_load_2d(sb, &map_b, &full_bar[st], kb * KB, a.l * ND);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = instr_desc(TILE_M, ND);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % BW_STAGES, ph = (kb / BW_STAGES) & 1;
+                mbar_wait(&full_bar[st], ph, a.err);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + st * BW_STAGE_BYTES), sb = sa + BW_A_BYTES;
+                const uint64_t da = smem_desc(sa), db = smem_desc(sb);
+#pragma unroll
+                for (int k = 0; k < KB / 16; ++k) tc_mma(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                tc_commit(&empty_bar[st]);
+            }
+            tc_commit(&acc_full);
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const long row = row0 + r;
+        const bool valid = row < a.M;
+        const int n = valid ? (int)(row / a.T0) : 0;
+        const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (MODE == MODE_GATE) {
+            const bool live = valid && tau >= a.off;                     // rows before the layer's first output carry exact zeros
+            const bool skip_row = live && tau >= a.SL;
+            const bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
+            const bf16 *dzs_row = skip_row ? a.dZs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
+            bf16 *dfg_row = a.dFG + (size_t)(valid ? row : 0) * NFG;
+            bf16 *z_row = a.Z ? a.Z + (size_t)(valid ? row : 0) * ND : nullptr;
+            // saved activations / skip gradient of this thread's 64 channels: issued before the accumulator wait
+            uint4 th_r[8], sg_r[8], dz_r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                th_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
+                sg_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + 128 + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
+                dz_r[i] = skip_row ? *reinterpret_cast<const uint4 *>(dzs_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
+            }
+            if (nkb > 0) {
+                mbar_wait(&acc_full, 0, a.err);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (half * 4 + jj) * 16;
+                float v[16];
+                if (nkb > 0) {
+                    tc_ld16(tlane + c0, v);
+                    tc_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
+                const uint32_t thw[8] = {th_r[2 * jj].x, th_r[2 * jj].y, th_r[2 * jj].z, th_r[2 * jj].w, th_r[2 * jj + 1].x, th_r[2 * jj + 1].y, th_r[2 * jj + 1].z, th_r[2 * jj + 1].w};
+                const uint32_t sgw[8] = {sg_r[2 * jj].x, sg_r[2 * jj].y, sg_r[2 * jj].z, sg_r[2 * jj].w, sg_r[2 * jj + 1].x, sg_r[2 * jj + 1].y, sg_r[2 * jj + 1].z, sg_r[2 * jj + 1].w};
+                const uint32_t dzw[8] = {dz_r[2 * jj].x, dz_r[2 * jj].y, dz_r[2 * jj].z, dz_r[2 * jj].w, dz_r[2 * jj + 1].x, dz_r[2 * jj + 1].y, dz_r[2 * jj + 1].z, dz_r[2 * jj + 1].w};
+                uint32_t df_p[8], dg_p[8], z_p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 tb = *reinterpret_cast<const __nv_bfloat162 *>(&thw[i]), sb2 = *reinterpret_cast<const __nv_bfloat162 *>(&sgw[i]),
+                                         zb = *reinterpret_cast<const __nv_bfloat162 *>(&dzw[i]);
+                    const float t0 = __low2float(tb), t1 = __high2float(tb), s0 = __low2float(sb2), s1 = __high2float(sb2);
+                    const float d0 = live ? v[2 * i] + __low2float(zb) : 0.f, d1 = live ? v[2 * i + 1] + __high2float(zb) : 0.f;
+                    df_p[i] = pack2(d0 * s0 * (1.f - t0 * t0), d1 * s1 * (1.f - t1 * t1));
+                    dg_p[i] = pack2(d0 * t0 * s0 * (1.f - s0), d1 * t1 * s1 * (1.f - s1));
+                    z_p[i] = pack2(t0 * s0, t1 * s1);
+                }
+                if (valid) {
+                    uint4 *pf = reinterpret_cast<uint4 *>(dfg_row + c0), *pg = reinterpret_cast<uint4 *>(dfg_row + 128 + c0);
+                    pf[0] = make_uint4(df_p[0], df_p[1], df_p[2], df_p[3]);
+                    pf[1] = make_uint4(df_p[4], df_p[5], df_p[6], df_p[7]);
+                    pg[0] = make_uint4(dg_p[0], dg_p[1], dg_p[2], dg_p[3]);
+                    pg[1] = make_uint4(dg_p[4], dg_p[5], dg_p[6], dg_p[7]);
+                    if (z_row) {
+                        uint4 *pz = reinterpret_cast<uint4 *>(z_row + c0);
+                        pz[0] = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
+                        pz[1] = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
+                    }
+                }
+            }
+        } else {
+            const bf16 *x_row = a.dXin + (size_t)(valid ? row : 0) * ND;
+            bf16 *o_row = a.dXout + (size_t)(valid ? row : 0) * ND;
+            uint4 xr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
+            mbar_wait(&acc_full, 0, a.err);
+            tc_fence_after();
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (half * 4 + jj) * 16;
+                float v[16];
+                tc_ld16(tlane + c0, v);
+                tc_ld_wait();
+                const uint32_t xs[8] = {xr[2 * jj].x, xr[2 * jj].y, xr[2 * jj].z, xr[2 * jj].w, xr[2 * jj + 1].x, xr[2 * jj + 1].y, xr[2 * jj + 1].z, xr[2 * jj + 1].w};
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
+                    o[i] = pack2(v[2 * i] + __low2float(xb), v[2 * i + 1] + __high2float(xb));
+                }
+                if (valid) {
+                    uint4 *po = reinterpret_cast<uint4 *>(o_row + c0);
+                    po[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    po[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BW_TMEM_COLS) : "memory");
+    }
+}
+
+// Per-sentence column sums of a bf16 (M, cols) matrix over the rows tau >= tau_min of each sentence, atomically added into
+// out (n, cols) (or out (cols) when per_sentence == 0): bias and global-condition gradients of the fused backward path.
+__global__ void colsum_bf16_kernel(const bf16 *__restrict__ in, float *__restrict__ out, int T0, int cols, int tau_min, int per_sentence, int CH) {
+    const int tpr = cols >> 3, rpp = blockDim.x / tpr, lr = threadIdx.x / tpr, c = (threadIdx.x - lr * tpr) * 8;
+    const int n = blockIdx.y, t0 = max(blockIdx.x * CH, tau_min), t1 = min(T0, (int)(blockIdx.x + 1) * CH);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int tau = t0 + lr; tau < t1; tau += rpp) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(in + ((size_t)n * T0 + tau) * cols + c);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+            s[2 * i] += __low2float(b);
+            s[2 * i + 1] += __high2float(b);
+        }
+    }
+    __shared__ float red[256 * 8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+    __syncthreads();
+    if (lr == 0) {
+        float *o = out + (per_sentence ? (size_t)n * cols : 0);
+        for (int i = 0; i < 8; ++i) {
+            float tot = 0.f;
+            for (int rr = 0; rr < rpp; ++rr) tot += red[(rr * tpr + threadIdx.x) * 8 + i];
+            atomicAdd(o + c + i, tot);
+        }
+    }
+}
+
 // K-major (transposed) bf16 copies of the per-layer kernels, rebuilt whenever the parameters change:
 //   WfgT (L*256, 384): row = l*256 + n (n: filter 0..127 | gate 128..255), column k: [0,128) tap x[tau-d], [128,256) tap x[tau],
 //                      [256, 256+C) local condition, zero beyond;   WdT (L*128, 128): row = l*128 + r, column = d.
+//   WdP (L*128, 128): Wd as stored (row = l*128 + d, column = r): B operand of dz = dx_next . Wd^T;
+//   WdxP (L*128, 512): row = l*128 + r, columns [0,256) = Wfg[1][r][:], [256,512) = Wfg[0][r][:]: B operand of the dx GEMM.
 __global__ void transpose_weights_kernel(const float *__restrict__ P, long o_layer_w, long stride, long o_wfg, long o_wlc, long o_wd, int L,
-                                         int C, bf16 *__restrict__ WfgT, bf16 *__restrict__ WdT) {
-    const long tot1 = (long)L * NFG * KTOT, tot2 = (long)L * ND * ND;
-    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot1 + tot2; e += (long)gridDim.x * blockDim.x) {
+                                         int C, bf16 *__restrict__ WfgT, bf16 *__restrict__ WdT, bf16 *__restrict__ WdP, bf16 *__restrict__ WdxP) {
+    const long tot1 = (long)L * NFG * KTOT, tot2 = (long)L * ND * ND, tot3 = (long)L * ND * 512;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot1 + 2 * tot2 + tot3; e += (long)gridDim.x * blockDim.x) {
+        if (e >= tot1 + tot2) {
+            if (e < tot1 + 2 * tot2) {
+                const long e3 = e - tot1 - tot2;
+                const long l = e3 / (ND * ND);
+                WdP[e3] = __float2bfloat16_rn(P[o_layer_w + stride * l + o_wd + (e3 - l * ND * ND)]);
+            } else {
+                const long e4 = e - tot1 - 2 * tot2;
+                const int k = (int)(e4 % 512);
+                const long rr = e4 / 512;
+                const int r = (int)(rr % ND);
+                const long l = rr / ND;
+                const int tap = k < 256 ? 1 : 0, cc = k & 255;
+                WdxP[e4] = __float2bfloat16_rn(P[o_layer_w + stride * l + o_wfg + ((long)tap * ND + r) * NFG + cc]);
+            }
+            continue;
+        }
         if (e < tot1) {
             const int k = (int)(e % KTOT);
             const long rn = e / KTOT;
