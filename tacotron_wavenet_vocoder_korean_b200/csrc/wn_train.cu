@@ -90,8 +90,10 @@ struct wnt_handle {
     // fused tcgen05 forward (R = D = 128, bf16)
     bool fused = false;
     void *Xall = nullptr;             // all layer inputs stacked: (L*M, R) -- one TMA tensor map
-    bf16 *WfgT = nullptr, *WdT = nullptr;
-    CUtensorMap map_x, map_lc, map_wfg, map_wd;
+    bf16 *WfgT = nullptr, *WdT = nullptr, *WdP = nullptr, *WdxP = nullptr;
+    bf16 *dXp[2] = {nullptr, nullptr};   // ping-pong gradient w.r.t. the layer outputs / inputs (fused backward, bf16)
+    bool fused_bwd = false, fused_persistent = true;
+    CUtensorMap map_x, map_lc, map_wfg, map_wd, map_dx[2], map_dfg, map_wdp, map_wdxp;
     unsigned *fused_err = nullptr;
     int64_t fused_launches = 0;
 };
@@ -311,9 +313,9 @@ int refresh_copy(wnt_handle *h, cudaStream_t st) {
     if (!h->bf) return WNT_OK;
     CKR(refresh_copy_t<bf16>(h, st));
     if (h->fused) {
-        const long tot = (long)h->L * (wntf::NFG * wntf::KTOT + wntf::ND * wntf::ND);
+        const long tot = (long)h->L * (wntf::NFG * wntf::KTOT + 2 * wntf::ND * wntf::ND + wntf::ND * 512);
         wntf::transpose_weights_kernel<<<grid_for(tot, EW_THREADS, 8 * h->sm_count), EW_THREADS, 0, st>>>(
-            h->P, h->o_layer_w, h->layer_w_stride, h->o_wfg, h->o_wlc, h->o_wd, h->L, h->C, h->WfgT, h->WdT);
+            h->P, h->o_layer_w, h->layer_w_stride, h->o_wfg, h->o_wlc, h->o_wd, h->L, h->C, h->WfgT, h->WdT, h->WdP, h->WdxP);
         KCHECK();
     }
     return WNT_OK;
@@ -344,6 +346,14 @@ int setup_fused(wnt_handle *h) {
     CKR(make_map(h, enc, &h->map_wfg, h->WfgT, (uint64_t)h->L * wntf::NFG, wntf::KTOT, wntf::NFG));
     CKR(make_map(h, enc, &h->map_wd, h->WdT, (uint64_t)h->L * wntf::ND, wntf::ND, wntf::ND));
     CK(cudaFuncSetAttribute(wntf::layer_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wntf::layer_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PF_SMEM_BYTES));
+    h->fused_persistent = getenv("WNT_NO_PERSISTENT") == nullptr;
+    for (int i = 0; i < 2; ++i) CKR(make_map(h, enc, &h->map_dx[i], h->dXp[i], (uint64_t)h->M, 128, wntf::TILE_M));
+    CKR(make_map(h, enc, &h->map_dfg, h->dFG, (uint64_t)h->M, 256, wntf::TILE_M));
+    CKR(make_map(h, enc, &h->map_wdp, h->WdP, (uint64_t)h->L * wntf::ND, wntf::ND, wntf::ND));
+    CKR(make_map(h, enc, &h->map_wdxp, h->WdxP, (uint64_t)h->L * wntf::ND, 512, wntf::ND));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
     return WNT_OK;
 }
 
@@ -412,7 +422,11 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             fa.Zs = (bf16 *)h->Zs;
             fa.err = h->fused_err;
             const unsigned tiles = (unsigned)((m + wntf::TILE_M - 1) / wntf::TILE_M);
-            wntf::layer_fwd_fused_kernel<<<tiles, wntf::THREADS, wntf::SMEM_BYTES, st>>>(h->map_x, h->map_lc, h->map_wfg, h->map_wd, fa);
+            if (h->fused_persistent)
+                wntf::layer_fwd_persistent_kernel<<<std::min<unsigned>(tiles, (unsigned)h->sm_count), wntf::PF_THREADS, wntf::PF_SMEM_BYTES, st>>>(
+                    h->map_x, h->map_lc, h->map_wfg, h->map_wd, fa, (int)tiles);
+            else
+                wntf::layer_fwd_fused_kernel<<<tiles, wntf::THREADS, wntf::SMEM_BYTES, st>>>(h->map_x, h->map_lc, h->map_wfg, h->map_wd, fa);
             KCHECK();
             h->fused_launches++;
             if (h->count_flops) h->flops += 2.0 * (double)m * (D2 * (2.0 * R + C) + (l + 1 < L ? (double)D * R : 0.0));
@@ -470,6 +484,8 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     CKR(gemm(h, st, false, true, Mo, LD, S, h->dTot, S, Pc + h->o_ws, S, ts, 0.f, h->dZs, LD, h->dZs, LD, ts));
     // ---- backward: dilation stack ----
     CK(cudaMemsetAsync(h->dX32, 0, (size_t)M * R * sizeof(float), st));
+    if (h->fused && h->fused_bwd)
+        for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->dXp[i], 0, (size_t)M * R * 2, st));
     if (C) CK(cudaMemsetAsync(h->dLC32, 0, (size_t)M * C * sizeof(float), st));
     CK(cudaMemsetAsync(h->SB, 0, (size_t)L * N * D2 * sizeof(float), st));
     for (int l = L - 1; l >= 0; --l) {
@@ -480,6 +496,42 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
         float *GW = Gr + lw(l);
         const bool dense = l + 1 < L;
         T *dXb = (T *)h->dXb, *dFG = (T *)h->dFG, *Zb = (T *)h->Z;
+        if (h->fused && h->fused_bwd) {
+            // tcgen05 path: dx travels between layers in bf16 (ping-pong buffers, zeroed once per step so that the rows before
+            // each layer's input start read as exact zeros); see wn_train_fused.cuh
+            const int cur = (L - 1 - l) & 1;
+            bf16 *dXn = h->dXp[cur], *dXo = h->dXp[cur ^ 1];
+            const long s_l = off - d;
+            const unsigned tiles = (unsigned)((M - s_l + wntf::TILE_M - 1) / wntf::TILE_M);
+            if (dense && ub) {
+                wntf::colsum_bf16_kernel<<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, 0, st>>>(dXn, Gr + lb(l) + h->o_bd, T0, R, 0, 0, CH);
+                KCHECK();
+            }
+            if (!dense) CK(cudaMemsetAsync(GW + h->o_wd, 0, (size_t)D * R * sizeof(float), st));
+            wntf::BwdArgs ba;
+            ba.l = l; ba.d = d; ba.off = (int)off; ba.s = (int)s_l; ba.SL = h->SL; ba.OW = h->OW; ba.T0 = T0; ba.LD = LD; ba.zs_col0 = l * D;
+            ba.has_dense = dense ? 1 : 0; ba.M = M;
+            ba.TS = (const bf16 *)h->TS[l]; ba.dZs = (const bf16 *)h->dZs; ba.dFG = (bf16 *)h->dFG; ba.Z = dense ? (bf16 *)h->Z : nullptr;
+            ba.dXin = dXn; ba.dXout = dXo; ba.err = h->fused_err;
+            wntf::layer_bwd_kernel<wntf::MODE_GATE><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba);
+            KCHECK();
+            wntf::colsum_bf16_kernel<<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, 0, st>>>((const bf16 *)h->dFG, h->SB + (size_t)l * N * D2, T0, D2, (int)off, 1, CH);
+            KCHECK();
+            const bf16 *Xb = (const bf16 *)h->X[l], *dF = (const bf16 *)h->dFG, *Zq = (const bf16 *)h->Z;
+            if (dense) CKR(gemm(h, st, true, false, D, R, m, Zq + off * D, D, dXn + off * R, R, ts, 0.f, GW + h->o_wd, R, GW + h->o_wd, R, f32));
+            CKR(gemm(h, st, true, false, R, D2, m, Xb + (off - d) * R, R, dF + off * D2, D2, ts, 0.f, GW + h->o_wfg, D2, GW + h->o_wfg, D2, f32));
+            CKR(gemm(h, st, true, false, R, D2, m, Xb + off * R, R, dF + off * D2, D2, ts, 0.f, GW + h->o_wfg + (int64_t)R * D2, D2,
+                     GW + h->o_wfg + (int64_t)R * D2, D2, f32));
+            if (C) {
+                CKR(gemm(h, st, true, false, C, D2, m, h->LC, C, dF + off * D2, D2, ts, 0.f, GW + h->o_wlc, D2, GW + h->o_wlc, D2, f32));
+                CKR(gemm(h, st, false, true, m, C, D2, dF + off * D2, D2, W + h->o_wlc, D2, ts, 1.f, h->dLC32, C, h->dLC32, C, f32));
+            }
+            wntf::layer_bwd_kernel<wntf::MODE_DX><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba);
+            KCHECK();
+            h->fused_launches += 2;
+            if (h->count_flops) h->flops += 2.0 * (double)(M - s_l) * ((dense ? (double)D * R : 0.0) + 2.0 * D2 * R);
+            continue;
+        }
         if (dense) {
             cast_colsum_kernel<T><<<grid_for(m, EW_THREADS / (R / 2), cap), EW_THREADS, 0, st>>>(h->dX32, dXb, ub ? Gr + lb(l) + h->o_bd : nullptr,
                                                                                               off, M, R);
@@ -510,7 +562,10 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     {
         CK(cudaMemsetAsync(Gr + h->o_wc, 0, (size_t)h->ifw * R * sizeof(float), st));
         const size_t sm = (size_t)(CH + h->ifw) * sizeof(float);
-        causal_bwd_kernel<<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, h->dX32, Gr + h->o_wc, h->T, T0, h->ifw, R, CH);
+        if (h->fused && h->fused_bwd)
+            causal_bwd_kernel<bf16><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, h->dXp[L & 1], Gr + h->o_wc, h->T, T0, h->ifw, R, CH);
+        else
+            causal_bwd_kernel<float><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, h->dX32, Gr + h->o_wc, h->T, T0, h->ifw, R, CH);
         KCHECK();
     }
     if (ub) {
@@ -666,6 +721,11 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     if (h->fused) {
         A_(h->WfgT, (size_t)h->L * wntf::NFG * wntf::KTOT * 2);
         A_(h->WdT, (size_t)h->L * wntf::ND * wntf::ND * 2);
+        A_(h->WdP, (size_t)h->L * wntf::ND * wntf::ND * 2);
+        A_(h->WdxP, (size_t)h->L * wntf::ND * 512 * 2);
+        A_(h->dXp[0], (size_t)M * h->R * 2);
+        A_(h->dXp[1], (size_t)M * h->R * 2);
+        h->fused_bwd = getenv("WNT_FUSED_BWD") != nullptr;   // opt-in: the one-tile-per-CTA backward kernels are correct but not yet faster than cuBLASLt
         A_(h->fused_err, 16);
     }
     A_(h->Zs, (size_t)Mo * LD * e);
@@ -719,7 +779,7 @@ void wnt_destroy(wnt_handle *h) {
     if (h->bf) fr(h->Pc);   // fp32: Pc aliases the caller's parameter buffer
     for (auto p : h->U) fr(p);
     for (auto p : h->dU) fr(p);
-    fr(h->Xall); fr(h->WfgT); fr(h->WdT); fr(h->fused_err);
+    fr(h->Xall); fr(h->WfgT); fr(h->WdT); fr(h->WdP); fr(h->WdxP); fr(h->dXp[0]); fr(h->dXp[1]); fr(h->fused_err);
     for (auto p : h->TS) fr(p);
     void *all[] = {h->LC, h->dLC32, h->Zs, h->dZs, h->Z, h->T1, h->T2, h->dC1, h->dTot, h->dY, h->dXb, h->dFG, h->FG32, h->TOT, h->dT32, h->Y,
                    h->dX32, h->dZ32, h->GCB, h->SB, h->bsum, h->dbs, h->acc, h->lt_ws};

@@ -97,6 +97,18 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                   "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, one swizzle atom (64 bf16) along K:
@@ -320,6 +332,240 @@ layer_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Persistent version of the forward kernel: one CTA per SM loops over tiles (tile = blockIdx.x + it*gridDim.x) with three
+// decoupled pipelines, so that TMA, tensor core and epilogue of DIFFERENT tiles overlap instead of running back to back:
+//   * a 3-stage shared-memory ring (48 KB per stage) that the producer keeps full ACROSS tile boundaries,
+//   * two 256-column TMEM accumulators: the filter|gate MMAs of tile it+1 run while the epilogue drains tile it,
+//   * the dense 1x1 of tile it is issued after the filter|gate MMAs of tile it+1 (its operand z comes from the epilogue) and
+//     accumulates into columns [0,128) of tile it's own buffer, which the gate epilogue has finished reading.
+// The dense weights Wd^T stay resident in shared memory for the whole launch; z has a dedicated 32 KB tile.
+constexpr int PF_STAGES = 3;
+constexpr int PF_OFF_WD = PF_STAGES * STAGE_BYTES;                    // 144 KB
+constexpr int PF_OFF_Z = PF_OFF_WD + 2 * ND * KB * 2;                  // + 32 KB
+constexpr int PF_SMEM_BYTES = PF_OFF_Z + 2 * A_BYTES + 1024;           // + 32 KB + alignment slack = 209 KB
+constexpr int PF_TMEM_COLS = 512;
+constexpr int PF_EPI_WARPS = 16, PF_EPI_THREADS = PF_EPI_WARPS * 32, PF_THREADS = 64 + PF_EPI_THREADS;   // four warps per TMEM lane quadrant, 32 channels each
+
+// 18 warps: the register file is split per SM sub-partition (16 K registers, 5 warps on the fullest one) -> at most 96 per thread
+__global__ void __launch_bounds__(PF_THREADS, 1)
+layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_lc,
+                            const __grid_constant__ CUtensorMap map_wfg, const __grid_constant__ CUtensorMap map_wd, const FusedArgs a, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[PF_STAGES], empty_bar[PF_STAGES], acc1_full[2], acc2_full[2], tmem_empty[2], z_ready, wd_full;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float s_bias[2][NFG];
+    __shared__ __align__(16) float s_bd[ND];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = a.has_lc ? NKB : 4;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PF_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc1_full[b], 1);
+            mbar_init(&acc2_full[b], 1);
+            mbar_init(&tmem_empty[b], PF_EPI_THREADS);
+        }
+        mbar_init(&z_ready, PF_EPI_THREADS);
+        mbar_init(&wd_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)PF_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            if (a.do_dense) {
+                mbar_expect_tx(&wd_full, 2 * ND * KB * 2);
+                tma_load_2d(smem + PF_OFF_WD, &map_wd, &wd_full, 0, a.l * ND);
+                tma_load_2d(smem + PF_OFF_WD + ND * KB * 2, &map_wd, &wd_full, KB, a.l * ND);
+            }
+            int g = 0;                                            // global K-block counter: the ring does not restart per tile
+            for (int it = 0; it < my_tiles; ++it) {
+                const long row0 = (long)a.off + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % PF_STAGES, ph = (g / PF_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1, a.err);
+                    uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (kb < 2) tma_load_2d(sa, &map_x, &full_bar[s], kb * KB, (int)(a.x_row0 + row0 - a.d));
+                    else if (kb < 4) tma_load_2d(sa, &map_x, &full_bar[s], (kb - 2) * KB, (int)(a.x_row0 + row0));
+                    else tma_load_2d(sa, &map_lc, &full_bar[s], (kb - 4) * KB, (int)(row0 - a.off));
+                    tma_load_2d(sb, &map_wfg, &full_bar[s], kb * KB, a.l * NFG);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = instr_desc(TILE_M, NFG), idesc2 = instr_desc(TILE_M, ND);
+            const uint32_t sz = smem_u32(smem + PF_OFF_Z), sw = smem_u32(smem + PF_OFF_WD);
+            int g = 0;
+            for (int it = 0; it <= my_tiles; ++it) {
+                if (it < my_tiles) {
+                    const int buf = it & 1;
+                    mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, a.err);        // epilogue has drained this accumulator (tile it-2)
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * NFG);
+                    for (int kb = 0; kb < nkb; ++kb, ++g) {
+                        const int s = g % PF_STAGES, ph = (g / PF_STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph, a.err);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+                        const uint64_t da = smem_desc(sa), db = smem_desc(sb);
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) tc_mma(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kb | k) != 0 ? 1u : 0u);
+                        tc_commit(&empty_bar[s]);
+                    }
+                    tc_commit(&acc1_full[buf]);
+                }
+                if (a.do_dense && it >= 1) {                      // dense 1x1 of the previous tile
+                    const int pt = it - 1, pbuf = pt & 1;
+                    if (pt == 0) mbar_wait(&wd_full, 0, a.err);
+                    mbar_wait(&z_ready, pt & 1, a.err);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(pbuf * NFG);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t da = smem_desc(sz + kb * A_BYTES), db = smem_desc(sw + kb * (ND * KB * 2));
+#pragma unroll
+                        for (int k = 0; k < KB / 16; ++k) tc_mma(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&acc2_full[pbuf]);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = (row, 32 of the 128 channels) =====================
+        const int q = warp & 3, qd = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const int cb = qd * 32;                                  // first channel of this thread
+        const int t = threadIdx.x - 64;
+        if (t < ND) s_bd[t] = a.bd ? a.bd[t] : 0.f;
+        int staged_n0 = -1;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            const long row0 = (long)a.off + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+            const long row = row0 + r;
+            const bool valid = row < a.M;
+            const int n0 = (int)(row0 / a.T0);
+            const int n = valid ? (int)(row / a.T0) : n0;
+            const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NFG);
+            if (n0 != staged_n0) {                               // uniform across the CTA: bias (+ gc) of sentences n0, n0+1
+                asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS) : "memory");  // everyone is done with the previous vectors
+                if (t < NFG) {
+                    const float b = a.bias ? a.bias[t] : 0.f;
+                    const int n1 = min(n0 + 1, a.N - 1);
+                    s_bias[0][t] = b + (a.gcb ? a.gcb[(size_t)n0 * NFG + t] : 0.f);
+                    s_bias[1][t] = b + (a.gcb ? a.gcb[(size_t)n1 * NFG + t] : 0.f);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS) : "memory");
+                staged_n0 = n0;
+            }
+            const float *sb = s_bias[n - n0];
+            const bool skip_row = valid && tau >= a.SL;
+            bf16 *zs_row = skip_row ? a.Zs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
+            bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
+            // residual input for the second epilogue: requested now, consumed after the dense MMA
+            const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND;
+            uint4 xr[4];
+            if (a.do_dense) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + cb + i * 8) : make_uint4(0, 0, 0, 0);
+            }
+            mbar_wait(&acc1_full[buf], (it >> 1) & 1, a.err);
+            tc_fence_after();
+            {
+                float f[32], g[32];
+                tc_ld32(tlane + cb, f);
+                tc_ld32(tlane + 128 + cb, g);
+                tc_ld_wait();
+                uint32_t th_p[16], sg_p[16], z_p[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bf4 = *reinterpret_cast<const float4 *>(sb + cb + i), bg4 = *reinterpret_cast<const float4 *>(sb + 128 + cb + i);
+                    const float fb[4] = {bf4.x, bf4.y, bf4.z, bf4.w}, gbv[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u += 2) {
+                        const float t0 = tanh_fast(f[i + u] + fb[u]), t1 = tanh_fast(f[i + u + 1] + fb[u + 1]);
+                        const float s0 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u] + gbv[u])), 0.5f);
+                        const float s1 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u + 1] + gbv[u + 1])), 0.5f);
+                        th_p[(i + u) >> 1] = pack2(t0, t1);
+                        sg_p[(i + u) >> 1] = pack2(s0, s1);
+                        z_p[(i + u) >> 1] = pack2(t0 * s0, t1 * s1);
+                    }
+                }
+                if (valid) {
+                    uint4 *pt = reinterpret_cast<uint4 *>(ts_row + cb), *ps = reinterpret_cast<uint4 *>(ts_row + 128 + cb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        pt[i] = make_uint4(th_p[4 * i], th_p[4 * i + 1], th_p[4 * i + 2], th_p[4 * i + 3]);
+                        ps[i] = make_uint4(sg_p[4 * i], sg_p[4 * i + 1], sg_p[4 * i + 2], sg_p[4 * i + 3]);
+                    }
+                    if (skip_row) {
+                        uint4 *pz = reinterpret_cast<uint4 *>(zs_row + cb);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) pz[i] = make_uint4(z_p[4 * i], z_p[4 * i + 1], z_p[4 * i + 2], z_p[4 * i + 3]);
+                    }
+                }
+                if (a.do_dense) {
+                    // z as the K-major, 128B-swizzled A operand of the dense MMA: K block cb/64, 16-byte chunk index XOR (row & 7)
+                    uint8_t *zt = smem + PF_OFF_Z + (cb >> 6) * A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                    const int ch = (cb & 63) >> 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4 *>(zt + (((ch + i) ^ (r & 7)) << 4)) = make_uint4(z_p[4 * i], z_p[4 * i + 1], z_p[4 * i + 2], z_p[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            if (a.do_dense) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&z_ready);
+                bf16 *xn_row = a.Xn + (size_t)(valid ? row : 0) * ND;
+                mbar_wait(&acc2_full[buf], (it >> 1) & 1, a.err);
+                tc_fence_after();
+                float v[32];
+                tc_ld32(tlane + cb, v);
+                tc_ld_wait();
+                const uint32_t xs[16] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w,
+                                         xr[2].x, xr[2].y, xr[2].z, xr[2].w, xr[3].x, xr[3].y, xr[3].z, xr[3].w};
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
+                    o[i] = pack2(v[2 * i] + __low2float(xb) + s_bd[cb + 2 * i], v[2 * i + 1] + __high2float(xb) + s_bd[cb + 2 * i + 1]);
+                }
+                if (valid) {
+                    uint4 *po = reinterpret_cast<uint4 *>(xn_row + cb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+                tc_fence_before();
+            }
+            mbar_arrive(&tmem_empty[buf]);                        // this accumulator may be overwritten by tile it+2
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)PF_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Backward of one dilation layer, two tcgen05 kernels sharing one skeleton (tile = 128 rows, N = 128 accumulator columns,
 // 3-stage TMA ring of 64-wide K blocks, 8 epilogue warps = (row, half of the channels)):
 //
@@ -417,21 +663,21 @@ layer_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const bf16 *dzs_row = skip_row ? a.dZs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
             bf16 *dfg_row = a.dFG + (size_t)(valid ? row : 0) * NFG;
             bf16 *z_row = a.Z ? a.Z + (size_t)(valid ? row : 0) * ND : nullptr;
-            // saved activations / skip gradient of this thread's 64 channels: issued before the accumulator wait
-            uint4 th_r[8], sg_r[8], dz_r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                th_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
-                sg_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + 128 + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
-                dz_r[i] = skip_row ? *reinterpret_cast<const uint4 *>(dzs_row + half * 64 + i * 8) : make_uint4(0, 0, 0, 0);
-            }
             if (nkb > 0) {
                 mbar_wait(&acc_full, 0, a.err);
                 tc_fence_after();
             }
-#pragma unroll
+#pragma unroll 1
             for (int jj = 0; jj < 4; ++jj) {
                 const int c0 = (half * 4 + jj) * 16;
+                // saved activations / skip gradient of these 16 channels first, so the loads fly while TMEM is read
+                uint4 th_r[2], sg_r[2], dz_r[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    th_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                    sg_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + 128 + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                    dz_r[i] = skip_row ? *reinterpret_cast<const uint4 *>(dzs_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                }
                 float v[16];
                 if (nkb > 0) {
                     tc_ld16(tlane + c0, v);
@@ -440,9 +686,9 @@ layer_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0.f;
                 }
-                const uint32_t thw[8] = {th_r[2 * jj].x, th_r[2 * jj].y, th_r[2 * jj].z, th_r[2 * jj].w, th_r[2 * jj + 1].x, th_r[2 * jj + 1].y, th_r[2 * jj + 1].z, th_r[2 * jj + 1].w};
-                const uint32_t sgw[8] = {sg_r[2 * jj].x, sg_r[2 * jj].y, sg_r[2 * jj].z, sg_r[2 * jj].w, sg_r[2 * jj + 1].x, sg_r[2 * jj + 1].y, sg_r[2 * jj + 1].z, sg_r[2 * jj + 1].w};
-                const uint32_t dzw[8] = {dz_r[2 * jj].x, dz_r[2 * jj].y, dz_r[2 * jj].z, dz_r[2 * jj].w, dz_r[2 * jj + 1].x, dz_r[2 * jj + 1].y, dz_r[2 * jj + 1].z, dz_r[2 * jj + 1].w};
+                const uint32_t thw[8] = {th_r[0].x, th_r[0].y, th_r[0].z, th_r[0].w, th_r[1].x, th_r[1].y, th_r[1].z, th_r[1].w};
+                const uint32_t sgw[8] = {sg_r[0].x, sg_r[0].y, sg_r[0].z, sg_r[0].w, sg_r[1].x, sg_r[1].y, sg_r[1].z, sg_r[1].w};
+                const uint32_t dzw[8] = {dz_r[0].x, dz_r[0].y, dz_r[0].z, dz_r[0].w, dz_r[1].x, dz_r[1].y, dz_r[1].z, dz_r[1].w};
                 uint32_t df_p[8], dg_p[8], z_p[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

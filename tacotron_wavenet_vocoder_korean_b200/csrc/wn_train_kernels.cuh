@@ -181,7 +181,8 @@ __global__ void causal_fwd_kernel(const float *__restrict__ wav, const float *__
 
 // dW[k][r] = sum_{n,tau} wav[n, tau + k] * dX[n, tau, r]   (atomic into pre-zeroed dW).  Thread -> (r, tap group).
 constexpr int CAUSAL_TAPS = 32;
-__global__ void causal_bwd_kernel(const float *__restrict__ wav, const float *__restrict__ dX, float *__restrict__ dW, int Tlen, int T0,
+template <typename TI>
+__global__ void causal_bwd_kernel(const float *__restrict__ wav, const TI *__restrict__ dX, float *__restrict__ dW, int Tlen, int T0,
                                   int ifw, int R, int CH) {
     extern __shared__ float sx[];   // CH + ifw
     const int n = blockIdx.y, t0 = blockIdx.x * CH, t1 = min(T0, t0 + CH);
@@ -196,7 +197,7 @@ __global__ void causal_bwd_kernel(const float *__restrict__ wav, const float *__
     for (int j = 0; j < CAUSAL_TAPS; ++j) acc[j] = 0.f;
     if (kg < KG) {
         for (int tau = t0; tau < t1; ++tau) {
-            const float v = dX[((size_t)n * T0 + tau) * R + r];
+            const float v = ld1(dX, ((size_t)n * T0 + tau) * R + r);
             const float *xs = sx + (tau - t0) + k0;
 #pragma unroll
             for (int j = 0; j < CAUSAL_TAPS; ++j)
