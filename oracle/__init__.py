@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE -- ctypes front-end of the CPU oracle (oracle/wn_oracle.c).
 
-PARITY UNPINNED: see the header of wn_oracle.c.  Only tests/, __graft_entry__.smoke()
+PARITY: pinned to the reference's own Python run on a numpy TF stand-in, TF kernels unpinned -- see the header of wn_oracle.c.  Only tests/, __graft_entry__.smoke()
 and bench.py's cpu_baseline / --impl reference legs may import this package; the
 product package never does.
 """

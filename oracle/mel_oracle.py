@@ -9,7 +9,9 @@ algorithms (librosa 0.6-0.7, the versions the reference's API use implies):
     FFT evaluated in float64 (y is float64 after scipy.signal.lfilter), result stored as complex64.
   * filters.mel(sr, n_fft, n_mels): Slaney mel scale (linear below 1 kHz, log above), triangular
     filters, Slaney area normalisation, fmin=0, fmax=sr/2, float32.
-PARITY UNPINNED against librosa itself; pinned against torch.stft and torchaudio.functional.melscale_fbanks
+PARITY: the reference's own utils/audio.py + hparams.py, run unmodified with librosa stubbed by the functions below
+(tests/golden/make_reference_audio_golden.py -> ref_audio.npz), is reproduced to 1e-5 (glue, constants, clipping, dB floor);
+librosa itself is UNPINNED: stft / filters.mel are pinned against torch.stft and torchaudio.functional.melscale_fbanks
 (tests/test_mel.py), which document librosa compatibility.
 """
 import numpy as np

@@ -7,7 +7,7 @@ It serves two purposes:
      libm/numpy transcendentals and BLAS summation order -> agreement to ~1e-5;
   2. the "reference-structure" CPU baseline (BASELINE.md section 3, B-ref).
 
-PARITY UNPINNED (no TensorFlow here; see wn_oracle.c header).
+PARITY: see wn_oracle.c header (pinned to the reference's own Python on a numpy TF stand-in; TF kernels unpinned).
 
 Reference lines followed: wavenet/model.py:41-46,49-64,66-101,102-111,112-167,181-212,
 215-245; wavenet/mixture.py:84-114; generate.py:184-233; wavenet/ops.py:22-47.

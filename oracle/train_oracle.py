@@ -2,7 +2,9 @@
 """TEST INFRASTRUCTURE -- torch (CPU, fp32/fp64, autograd) restatement of the reference's WaveNet TRAINING graph
 (SURVEY.md section 8f next-3).  Only tests/, __graft_entry__.smoke() and the CPU legs of the benchmarks may import it.
 
-PARITY UNPINNED against TensorFlow (not installable here; the reference ships no tests/goldens).  What is pinned in
+PARITY: the loss value is pinned to the reference's OWN add_loss (wavenet/model.py:247-312, run unmodified on the numpy TF
+stand-in tests/golden/tf_numpy_shim.py -> tests/golden/ref_train.npz, reproduced to 2e-5 incl. the L2 term and the per-layer
+lc alignment); TensorFlow's kernels and its autodiff are not installable here and stay unpinned.  Also pinned in
 tests/test_train_oracle.py: the MoL loss against an independent float64 numpy evaluation of mixture.py:27-81, the
 network forward against the incremental-generation oracle (teacher forcing: training logits at position t == the
 per-sample oracle's logits), Adam/decay/EMA against torch.optim.Adam and the closed forms.

@@ -2,13 +2,19 @@
  * oracle/wn_oracle.c -- TEST INFRASTRUCTURE.  CPU restatement (plain C) of the
  * reference's WaveNet incremental ("fast generation") sample loop.
  *
- * PARITY UNPINNED: the reference (hccho2/Tacotron-Wavenet-Vocoder-Korean) ships no
- * tests, golden vectors or checkpoints for this path and needs TensorFlow 1.x,
- * which cannot be installed here, so this restatement could not be checked against
- * outputs of the reference itself.  It is pinned only to (a) the few known-answer
- * values embedded in the reference's comments (tests/test_oracle_kat.py), (b) an
- * independent numpy restatement (oracle/np_oracle.py), and (c) torch's
- * conv_transpose2d for the upsampling network.
+ * PARITY: pinned to the reference's OWN Python, not to TensorFlow's kernels.  The reference
+ * (hccho2/Tacotron-Wavenet-Vocoder-Korean) ships no tests, golden vectors or checkpoints and
+ * needs TensorFlow 1.x, which cannot be installed here.  Its wavenet/model.py, mixture.py and
+ * ops.py are therefore imported unmodified from /root/reference and executed on a numpy
+ * stand-in for the TF API (tests/golden/tf_numpy_shim.py); the outputs are committed as
+ * tests/golden/ref_mol.npz / ref_mulaw.npz with the generating script
+ * (tests/golden/make_reference_goldens.py) and this oracle reproduces them to 2e-5 on the
+ * logits, samples and probabilities (tests/test_reference_pin.py), including every variable
+ * name / shape and the queue layout.  What stays UNPINNED is the arithmetic inside TF's own
+ * kernels (conv1d, conv2d_transpose, softmax, random_uniform), restated from their published
+ * definitions.  Further pins: (a) the known-answer values in the reference's comments,
+ * (b) an independent numpy restatement (oracle/np_oracle.py), (c) torch's conv_transpose2d
+ * for the upsampling network.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product never does.

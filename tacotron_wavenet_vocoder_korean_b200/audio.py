@@ -7,8 +7,10 @@ from scipy.io import wavfile
 def save_wav(wav, path, sr):
     """Peak-normalise to int16 and write (utils/audio.py:14-17).  Unlike the reference this does not
     scale the caller's array in place."""
-    wav = np.asarray(wav, dtype=np.float64)
-    wav = wav * (32767 / max(0.01, np.max(np.abs(wav)) if wav.size else 0.0))
+    wav = np.array(wav, copy=True)                     # same dtype as the caller's array: the reference scales a float32 waveform
+    if not np.issubdtype(wav.dtype, np.floating):      # in float32, and the int16 truncation depends on that (tests/test_reference_pin.py)
+        wav = wav.astype(np.float32)
+    wav *= 32767 / max(0.01, np.max(np.abs(wav)) if wav.size else 0.0)
     wavfile.write(path, sr, wav.astype(np.int16))
 
 

@@ -1,0 +1,393 @@
+# coding: utf-8
+"""TEST INFRASTRUCTURE -- a minimal eager numpy stand-in for the TensorFlow 1.x API surface that the reference's
+wavenet/model.py, wavenet/mixture.py and wavenet/ops.py touch, so that THE REFERENCE'S OWN PYTHON runs in this container
+(TensorFlow 1.x has no Python 3.12 wheel) and produces golden vectors for the oracle (tests/golden/make_reference_goldens.py).
+
+What this pins: everything the reference's code decides -- graph wiring, variable names and shapes (tf.layers auto-numbering,
+variable scopes), queue update order, slicing / alignment of the conditioning, the sampling formulas.  What it does NOT
+pin: the arithmetic inside TensorFlow's kernels, which is restated here from the published op definitions (conv1d as a sum of
+matmuls over taps, conv2d_transpose through torch.nn.functional.conv_transpose2d, softmax, ...), in numpy float32.
+
+Semantics: ops execute eagerly on numpy arrays.  TF1 graph construction + repeated `sess.run` is emulated by calling the
+reference's graph-building method once per step inside `graph_pass()`: variables (tf.Variable / tf.get_variable / layer
+kernels) are created on the first pass and REUSED BY NAME afterwards; name uniquification (`dilation_queue`,
+`dilation_queue_1`, ...; `conv1d`, `conv1d_1`, ...) restarts at every pass, so the i-th creation maps to the same variable.
+`tf.scatter_update` mutates the variable, which is how the fast-generation queues keep their state between steps.
+Initial values of trainable variables come from `set_initial_values({name: array})`; a name the reference asks for that is
+missing from that dict raises, which is what checks SURVEY.md Appendix B.
+"""
+import contextlib
+import sys
+import types
+
+import numpy as np
+
+float32, float64, int32, int64 = np.float32, np.float64, np.int32, np.int64
+
+
+class _Shape(list):
+    def as_list(self):
+        return list(self)
+
+
+class Tensor(np.ndarray):
+    """numpy array with the two TF tensor methods the reference calls."""
+
+    def get_shape(self):
+        return _Shape(self.shape)
+
+
+def _t(x, dtype=None):
+    a = np.asarray(x, dtype=dtype)
+    return a.view(Tensor)
+
+
+class _State(object):
+    def __init__(self):
+        self.variables = {}          # full name -> Tensor (mutable storage)
+        self.trainable = []          # names in creation order
+        self.initial = {}
+        self.scope = []              # variable-scope stack
+        self.counters = {}           # per-pass unique-name counters
+        self.uniforms = []           # queue for tf.random_uniform
+        self.created_order = []
+
+
+S = _State()
+
+
+def reset():
+    S.__init__()
+
+
+def set_initial_values(values):
+    S.initial = {k: np.asarray(v, np.float32) for k, v in values.items()}
+
+
+def push_uniforms(*arrays):
+    S.uniforms.extend(np.asarray(a, np.float32) for a in arrays)
+
+
+@contextlib.contextmanager
+def graph_pass():
+    """One emulated `sess.run`: unique-name counters restart so that creations map onto the existing variables."""
+    S.counters = {}
+    S.scope = []
+    yield
+
+
+def _scoped(name):
+    return '/'.join(S.scope + [name])
+
+
+def _unique(full):
+    n = S.counters.get(full, 0)
+    S.counters[full] = n + 1
+    return full if n == 0 else '%s_%d' % (full, n)
+
+
+def _make_variable(full, shape, trainable, init=None):
+    if full in S.variables:
+        v = S.variables[full]
+        if tuple(v.shape) != tuple(shape):
+            raise ValueError('variable %s re-created with shape %s (was %s)' % (full, tuple(shape), v.shape))
+        return v
+    if init is None:
+        if full not in S.initial:
+            raise KeyError('the reference created trainable variable %r %s, which the supplied weights do not contain' % (full, tuple(shape)))
+        init = S.initial[full]
+        if tuple(init.shape) != tuple(shape):
+            raise ValueError('variable %s: reference shape %s, supplied %s' % (full, tuple(shape), init.shape))
+    v = _t(np.array(init, np.float32, copy=True))
+    v.name = full + ':0'
+    S.variables[full] = v
+    S.created_order.append(full)
+    if trainable:
+        S.trainable.append(full)
+    return v
+
+
+# ---- scopes -----------------------------------------------------------------------------------------------------------
+AUTO_REUSE = 'auto_reuse'
+
+
+@contextlib.contextmanager
+def variable_scope(name, reuse=None, default_name=None):
+    S.scope.append(name)
+    try:
+        yield
+    finally:
+        S.scope.pop()
+
+
+@contextlib.contextmanager
+def name_scope(name, *a, **k):
+    yield
+
+
+@contextlib.contextmanager
+def control_dependencies(_):
+    yield
+
+
+# ---- variables --------------------------------------------------------------------------------------------------------
+def Variable(initial_value=None, name=None, trainable=True, dtype=None):
+    full = _unique(_scoped(name or 'Variable'))
+    return _make_variable(full, np.shape(initial_value), trainable, init=None if trainable else initial_value)
+
+
+def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True):
+    return _make_variable(_scoped(name), tuple(shape), trainable)
+
+
+def trainable_variables():
+    return [S.variables[n] for n in S.trainable]
+
+
+def variables_initializer(var_list):
+    def run():
+        for v in var_list:
+            v[...] = 0
+    return run
+
+
+def scatter_update(ref, indices, updates):
+    ref[np.asarray(indices)] = np.asarray(updates, ref.dtype)
+    return ref
+
+
+# ---- array ops --------------------------------------------------------------------------------------------------------
+def zeros(shape, dtype=np.float32):
+    return _t(np.zeros(shape, dtype))
+
+
+def range(*a):          # noqa: A001 (mirrors tf.range)
+    return _t(np.arange(*a))
+
+
+def shape(x):
+    return np.array(np.shape(x), np.int64)
+
+
+def reshape(x, shp):
+    return _t(np.reshape(np.asarray(x), [int(s) for s in shp]))
+
+
+def concat(values, axis):
+    return _t(np.concatenate([np.asarray(v) for v in values], axis=axis))
+
+
+def slice(x, begin, size):   # noqa: A001
+    x = np.asarray(x)
+    idx = tuple(np.s_[int(b):(None if int(s) == -1 else int(b) + int(s))] for b, s in zip(begin, size))
+    return _t(x[idx])
+
+
+def cast(x, dtype):
+    return _t(np.asarray(x).astype(dtype))
+
+
+def to_float(x):
+    return cast(x, np.float32)
+
+
+def to_int32(x):
+    # tf.to_int32 truncates toward zero
+    return _t(np.trunc(np.asarray(x)).astype(np.int32))
+
+
+def expand_dims(x, axis):
+    ax = axis[0] if isinstance(axis, (list, tuple)) else axis
+    return _t(np.expand_dims(np.asarray(x), ax))
+
+
+def squeeze(x, axis=None):
+    ax = tuple(axis) if isinstance(axis, (list, tuple)) else axis
+    return _t(np.squeeze(np.asarray(x), axis=ax))
+
+
+def tile(x, multiples):
+    return _t(np.tile(np.asarray(x), multiples))
+
+
+def one_hot(indices, depth, dtype=np.float32):
+    idx = np.asarray(indices).astype(np.int64)
+    out = np.zeros(idx.shape + (int(depth),), dtype)
+    np.put_along_axis(out, idx[..., None], 1, axis=-1)
+    return _t(out)
+
+
+def where(cond, a, b):
+    return _t(np.where(np.asarray(cond), np.asarray(a), np.asarray(b)))
+
+
+def argmax(x, axis):
+    return _t(np.argmax(np.asarray(x), axis=axis))
+
+
+# ---- math -------------------------------------------------------------------------------------------------------------
+def _un(fn):
+    return lambda x, *a, **k: _t(fn(np.asarray(x)))
+
+
+tanh = _un(np.tanh)
+exp = _un(np.exp)
+log = _un(np.log)
+log1p = _un(np.log1p)
+abs = _un(np.abs)          # noqa: A001
+sign = _un(np.sign)
+
+
+def sigmoid(x):
+    x = np.asarray(x)
+    return _t((1 / (1 + np.exp(-x))).astype(x.dtype))
+
+
+def maximum(a, b):
+    return _t(np.maximum(np.asarray(a), np.asarray(b, dtype=np.asarray(a).dtype)))
+
+
+def minimum(a, b):
+    return _t(np.minimum(np.asarray(a), np.asarray(b, dtype=np.asarray(a).dtype)))
+
+
+def reduce_sum(x, axis=None, keepdims=False):
+    return _t(np.sum(np.asarray(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_max(x, axis=None, keepdims=False):
+    return _t(np.max(np.asarray(x), axis=axis, keepdims=keepdims))
+
+
+def reduce_mean(x, axis=None):
+    return _t(np.mean(np.asarray(x), axis=axis, dtype=np.asarray(x).dtype))
+
+
+def add_n(xs):
+    out = np.asarray(xs[0])
+    for x in xs[1:]:
+        out = out + np.asarray(x)
+    return _t(out)
+
+
+def random_uniform(shp, minval=0, maxval=1, dtype=np.float32):
+    """The caller queues the draws (push_uniforms) so that reference and oracle consume the same random numbers."""
+    if not S.uniforms:
+        raise RuntimeError('tf.random_uniform called but no uniforms were queued')
+    u = S.uniforms.pop(0)
+    if tuple(u.shape) != tuple(int(s) for s in shp):
+        raise ValueError('queued uniforms have shape %s, the reference asked for %s' % (u.shape, tuple(shp)))
+    assert u.min() >= minval and u.max() <= maxval
+    return _t(u)
+
+
+class _NN(object):
+    relu = staticmethod(lambda x: _t(np.maximum(np.asarray(x), 0)))
+    sigmoid = staticmethod(sigmoid)
+
+    @staticmethod
+    def softplus(x):
+        x = np.asarray(x)
+        return _t(np.logaddexp(0, x).astype(x.dtype))
+
+    @staticmethod
+    def softmax(x, axis=-1):
+        x = np.asarray(x)
+        e = np.exp(x - x.max(axis=axis, keepdims=True))
+        return _t(e / e.sum(axis=axis, keepdims=True))
+
+    @staticmethod
+    def log_softmax(x, axis=-1):
+        x = np.asarray(x)
+        m = x - x.max(axis=axis, keepdims=True)
+        return _t(m - np.log(np.exp(m).sum(axis=axis, keepdims=True)))
+
+    @staticmethod
+    def embedding_lookup(table, ids):
+        return _t(np.asarray(table)[np.asarray(ids).astype(np.int64)])
+
+    @staticmethod
+    def softmax_cross_entropy_with_logits_v2(logits=None, labels=None):
+        ls = _NN.log_softmax(logits)
+        return _t(-(np.asarray(labels) * ls).sum(-1))
+
+    @staticmethod
+    def l2_loss(v):
+        return _t(np.sum(np.asarray(v) ** 2) / 2)
+
+
+nn = _NN()
+
+
+# ---- tf.layers --------------------------------------------------------------------------------------------------------
+def _layer_scope(name, default):
+    if name is not None:
+        return _scoped(name)
+    return _unique(_scoped(default))
+
+
+class _Layers(object):
+    @staticmethod
+    def conv1d(inputs, filters, kernel_size, padding='valid', dilation_rate=1, use_bias=True, name=None, strides=1):
+        x = np.asarray(inputs)
+        scope = _layer_scope(name, 'conv1d')
+        k = int(kernel_size)
+        W = _make_variable(scope + '/kernel', (k, x.shape[2], int(filters)), True)
+        if padding.lower() == 'same' and k != 1:
+            raise NotImplementedError("conv1d 'same' with kernel_size > 1 is not used by the reference")
+        d = int(dilation_rate)
+        t_out = x.shape[1] - d * (k - 1)
+        out = np.zeros((x.shape[0], t_out, int(filters)), np.float32)
+        for j in np.arange(k):
+            out = out + x[:, j * d:j * d + t_out, :] @ np.asarray(W)[j]
+        if use_bias:
+            out = out + np.asarray(_make_variable(scope + '/bias', (int(filters),), True))
+        return _t(out.astype(np.float32))
+
+    @staticmethod
+    def conv2d_transpose(inputs, filters, kernel_size, strides, padding='same', use_bias=True, name=None):
+        """NHWC, filters=1, kernel (F, fw), strides (F, 1), 'same' (model.py:107-108).  TF's 'same' transposed convolution with
+        an even width-2 kernel crops the END of the full output, i.e. keeps the first W columns."""
+        import torch
+        x = np.asarray(inputs)
+        if filters != 1 or x.shape[3] != 1 or padding.lower() != 'same' or use_bias or strides[1] != 1 or strides[0] != kernel_size[0]:
+            raise NotImplementedError('only the upsampling configuration of model.py:107-108')
+        scope = _layer_scope(name, 'conv2d_transpose')
+        K = _make_variable(scope + '/kernel', (kernel_size[0], kernel_size[1], 1, 1), True)
+        xt = torch.from_numpy(np.ascontiguousarray(x[..., 0]))[:, None]                       # N,1,H,W
+        kt = torch.from_numpy(np.ascontiguousarray(np.asarray(K)[:, :, 0, 0]))[None, None]     # 1,1,F,fw
+        y = torch.nn.functional.conv_transpose2d(xt, kt, stride=(int(strides[0]), 1))[..., :x.shape[2]]
+        return _t(y[:, 0].numpy()[..., None].astype(np.float32))
+
+
+layers = _Layers()
+
+
+# ---- things the reference touches but that do nothing here ---------------------------------------------------------------
+class _Summary(object):
+    @staticmethod
+    def scalar(*a, **k):
+        return None
+
+
+summary = _Summary()
+
+
+class _Train(object):
+    class ExponentialMovingAverage(object):
+        def __init__(self, decay):
+            self.decay = decay
+
+    AdamOptimizer = MomentumOptimizer = RMSPropOptimizer = object
+
+
+train = _Train()
+
+contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=lambda **k: None))
+
+
+def install():
+    """Registers this module as `tensorflow` (only in the process that generates the golden vectors)."""
+    me = sys.modules[__name__]
+    sys.modules['tensorflow'] = me
+    return me

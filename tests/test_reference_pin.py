@@ -1,0 +1,153 @@
+# coding: utf-8
+"""The oracle and the CUDA path against golden vectors produced by THE REFERENCE'S OWN wavenet/model.py, mixture.py and
+ops.py, executed on a numpy TensorFlow stand-in (tests/golden/tf_numpy_shim.py, tests/golden/make_reference_goldens.py).
+This pins everything the reference's Python decides (wiring, variable names/shapes, queue order, conditioning alignment,
+sampling formulas, loss construction); TensorFlow's own kernels are restated in the stand-in, hence tolerances of a few
+float32 ulps of the logits instead of bit equality."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import train_oracle as to
+from tacotron_wavenet_vocoder_korean_b200 import synth
+from tests.helpers import make_inputs, oracle_model
+from tests.train_helpers import train_case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+MULAW_LC = dict(synth.tiny_mulaw(), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8,
+                global_condition_cardinality=3)
+
+
+def test_variable_names_shapes_and_queues_are_the_reference_s():
+    g = np.load(os.path.join(GOLD, 'ref_mol.npz'))
+    kw = synth.tiny_mol()
+    assert sorted(g['variable_names'].tolist()) == sorted(synth.weight_shapes(**kw))
+    q = dict(zip(g['queue_names'].tolist(), g['queue_shapes'].tolist()))
+    assert q['wavenet/queue/causal_queue'] == str((2, kw['initial_filter_width'], 1))
+    assert q['wavenet/queue/local_condition_queue'] == str((2, 2, kw['local_condition_channels']))
+    # model.py:60 `'dilation_queue'.format(i)` has no placeholder: TF uniquifies the names
+    assert [n for n in g['queue_names'].tolist() if 'dilation' in n] == ['wavenet/queue/dilation_queue'] + \
+        ['wavenet/queue/dilation_queue_%d' % i for i in range(1, len(kw['dilations']))]
+    assert [q[n] for n in g['queue_names'].tolist() if 'dilation' in n] == [str((2, d + 1, kw['residual_channels'])) for d in kw['dilations']]
+    assert int(g['receptive_field']) == oracle.receptive_field(2, kw['dilations'], True, kw['initial_filter_width'])
+    g2 = np.load(os.path.join(GOLD, 'ref_mulaw.npz'))
+    assert sorted(g2['variable_names'].tolist()) == sorted(synth.weight_shapes(**MULAW_LC))
+
+
+def test_oracle_matches_reference_mol_path():
+    g = np.load(os.path.join(GOLD, 'ref_mol.npz'))
+    kw = synth.tiny_mol()
+    om = oracle_model(kw, synth.make_weights(**kw))
+    T = g['outputs'].shape[1]
+    inp = make_inputs(kw, T)
+    lc = om.upsample(inp['mel'])
+    np.testing.assert_allclose(lc, g['lc_up'], atol=2e-6)                                     # create_upsample (model.py:102-111)
+    s, lg = om.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.abs(lg - g['raw_output']).max() < 2e-5                                          # north_star tolerance is 1e-4
+    assert np.abs(s - g['outputs'][:, :, 0]).max() < 2e-5                                     # mixture.py:84-114 draw
+
+
+def test_oracle_matches_reference_mulaw_path():
+    g = np.load(os.path.join(GOLD, 'ref_mulaw.npz'))
+    kw = MULAW_LC
+    om = oracle_model(kw, synth.make_weights(**kw))
+    T = g['outputs'].shape[1]
+    inp = make_inputs(kw, T)
+    lc = om.upsample(inp['mel'])
+    np.testing.assert_allclose(lc, g['lc_up'], atol=2e-6)
+    _, lg = om.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    probs = np.stack([[oracle.softmax_probs(lg[n, t]) for t in range(T)] for n in range(lg.shape[0])])
+    assert np.abs(probs - g['outputs']).max() < 2e-6                                          # model.py:243 float64 softmax
+
+
+def test_training_loss_and_mu_law_match_reference_graph():
+    g = np.load(os.path.join(GOLD, 'ref_train.npz'))
+    kw = synth.tiny_train(3)
+    w, wav, mel, gc = train_case(kw, 96)
+    m = to.TorchWaveNetTrain(w, **kw)
+    assert abs(float(m.loss(wav, mel, gc).detach()) - float(g['loss'])) < 2e-5 * abs(float(g['loss']))
+    assert abs(float(m.loss(wav, mel, gc, 0.01).detach()) - float(g['loss_l2'])) < 2e-5 * abs(float(g['loss_l2']))
+    enc = oracle.mu_law_encode(g['mu_grid'], 256)
+    assert np.mean(enc != g['mu_encoded']) < 0.01 and np.abs(enc - g['mu_encoded']).max() <= 1   # cell-edge ties only
+    np.testing.assert_allclose(oracle.mu_law_decode(np.arange(256, dtype=np.float32), 256), g['mu_decoded'], atol=1e-6)
+
+
+# ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
+def test_cuda_generation_matches_reference_goldens(name):
+    import torch
+    from tacotron_wavenet_vocoder_korean_b200.wavenet import WaveNetModel
+    g = np.load(os.path.join(GOLD, name + '.npz'))
+    kw = synth.tiny_mol() if name == 'ref_mol' else MULAW_LC
+    net = WaveNetModel(train_mode=False, **kw)
+    net.load_state_dict(synth.make_weights(**kw))
+    T = g['outputs'].shape[1]
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    np.testing.assert_allclose(lc.cpu().numpy(), g['lc_up'], atol=2e-6)
+    s, lg = net.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    s, lg = s.cpu().numpy(), lg.cpu().numpy()
+    if name == 'ref_mol':
+        assert np.abs(lg - g['raw_output']).max() < 1e-4 and np.abs(s - g['outputs'][:, :, 0]).max() < 1e-4
+    else:
+        p = torch.softmax(torch.from_numpy(lg).double(), -1).float().numpy()
+        assert np.abs(p - g['outputs']).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_training_loss_matches_reference_graph():
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.train import WaveNetTrainer
+    g = np.load(os.path.join(GOLD, 'ref_train.npz'))
+    kw = synth.tiny_train(3)
+    w, wav, mel, gc = train_case(kw, 96)
+    tr = WaveNetTrainer(96, dtype='fp32', **kw)
+    tr.load_state_dict(w)
+    assert abs(float(tr.loss_and_grads(wav, mel, gc).item()) - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
+    assert abs(float(tr.loss_and_grads(wav, mel, gc, 0.01).item()) - float(g['loss_l2'])) < 1e-4 * abs(float(g['loss_l2']))
+
+
+# ---- utils/audio.py + hparams.py of the reference (tests/golden/make_reference_audio_golden.py) -----------------------------
+def test_hparams_mirror_the_reference_values():
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    g = np.load(os.path.join(GOLD, 'ref_audio.npz'))
+    for keys, vals in ((g['hparams_keys'], g['hparams_values']), (g['wn_keys'], g['wn_values'])):
+        for k, v in zip(keys.tolist(), vals.tolist()):
+            if k == 'use_lws':
+                assert v == 0.0
+                continue
+            assert float(getattr(hparams, k)) == v, k
+    assert list(hparams.dilations) == g['dilations'].tolist() and list(hparams.upsample_factor) == g['upsample_factor'].tolist()
+
+
+def test_mel_oracle_and_save_wav_match_reference_glue(tmp_path):
+    from scipy.io import wavfile
+    from oracle import mel_oracle
+    from tacotron_wavenet_vocoder_korean_b200 import audio
+    g = np.load(os.path.join(GOLD, 'ref_audio.npz'))
+    for i in range(3):
+        np.testing.assert_allclose(mel_oracle.melspectrogram(g['wav%d' % i]), g['mel%d' % i], atol=1e-5)
+    hp = mel_oracle.DEFAULTS
+    m = hp['max_abs_value']
+    S = g['norm_in']
+    np.testing.assert_allclose(np.clip(2 * m * ((S - hp['min_level_db']) / -hp['min_level_db']) - m, -m, m), g['norm_out'], atol=1e-12)
+    np.testing.assert_allclose(mel_oracle.preemphasis(g['wav0'][:64].astype(np.float64), 0.97), g['preemph'], atol=1e-7)
+    x = np.logspace(-7, 1, 33)
+    np.testing.assert_allclose(20 * np.log10(np.maximum(np.exp(hp['min_level_db'] / 20 * np.log(10)), x)), g['amp_to_db'], atol=1e-10)
+    for i in range(2):                                                     # utils/audio.py:14-17
+        p = str(tmp_path / 'x.wav')
+        audio.save_wav(g['save_in%d' % i], p, 24000)
+        sr, data = wavfile.read(p)
+        assert sr == 24000 and np.array_equal(data, g['save_out%d' % i])
+
+
+@pytest.mark.gpu
+def test_cuda_melspectrogram_matches_reference_glue():
+    from tacotron_wavenet_vocoder_korean_b200 import audio
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    g = np.load(os.path.join(GOLD, 'ref_audio.npz'))
+    for i in range(3):
+        got = audio.melspectrogram(g['wav%d' % i], hparams).cpu().numpy()
+        assert got.shape == g['mel%d' % i].shape and np.abs(got - g['mel%d' % i]).max() <= 1e-4
