@@ -2,7 +2,9 @@
 rows a15-a20, Appendix C).  Only tests/, __graft_entry__.smoke() and the CPU legs of the benchmarks may
 import it; the product package never does.
 
-PARITY UNPINNED: TensorFlow 1.x is not installable here and the reference ships neither tests nor
+PARITY: prenet + encoder/post CBHG (rows a15, a20) are pinned to the reference's own tacotron/modules.py run on the numpy TF
+stand-in (tests/golden/make_reference_taco_golden.py -> ref_taco_modules.npz, reproduced to 2e-5, tests/test_reference_pin.py).
+The attention decoder (rows a16-a19) is PARITY UNPINNED: TensorFlow 1.x is not installable here and the reference ships neither tests nor
 checkpoints, so the TF-internal pieces (tf.contrib.rnn.GRUCell, tf.contrib.seq2seq.BahdanauMonotonicAttention,
 dynamic_decode, tf.layers.conv1d/batch_normalization/max_pooling1d 'same' semantics,
 bidirectional_dynamic_rnn with sequence_length) are restated from their published definitions.  What can

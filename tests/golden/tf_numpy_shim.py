@@ -319,6 +319,62 @@ class _NN(object):
 nn = _NN()
 
 
+def split(x, num, axis):
+    return [_t(a) for a in np.split(np.asarray(x), num, axis=axis)]
+
+
+def truncated_normal_initializer(**k):
+    return None
+
+
+def constant_initializer(*a, **k):
+    return None
+
+
+class GRUCell(object):
+    """tf.contrib.rnn.GRUCell: [r, u] = sigmoid([x, h] Wg + bg); c = tanh([x, r*h] Wc + bc); h' = u*h + (1-u)*c.
+    Variables `<scope>/gru_cell/{gates,candidate}/{kernel,bias}` (third-party arithmetic, restated)."""
+
+    def __init__(self, num_units):
+        self.num_units = int(num_units)
+
+    def step(self, x, h, scope):
+        U = self.num_units
+        Wg = np.asarray(_make_variable(scope + '/gru_cell/gates/kernel', (x.shape[1] + U, 2 * U), True))
+        bg = np.asarray(_make_variable(scope + '/gru_cell/gates/bias', (2 * U,), True))
+        Wc = np.asarray(_make_variable(scope + '/gru_cell/candidate/kernel', (x.shape[1] + U, U), True))
+        bc = np.asarray(_make_variable(scope + '/gru_cell/candidate/bias', (U,), True))
+        g = 1 / (1 + np.exp(-(np.concatenate([x, h], 1) @ Wg + bg)))
+        r, u = g[:, :U], g[:, U:]
+        c = np.tanh(np.concatenate([x, r * h], 1) @ Wc + bc)
+        return (u * h + (1 - u) * c).astype(np.float32)
+
+
+def _bidirectional_dynamic_rnn(cell_fw, cell_bw, inputs, sequence_length=None, initial_state_fw=None, initial_state_bw=None, dtype=None):
+    """tf.nn.bidirectional_dynamic_rnn: outputs are zero past sequence_length and the state is carried through; the backward
+    direction runs over the reversed valid part (tf.reverse_sequence)."""
+    x = np.asarray(inputs)
+    N, T, _ = x.shape
+    L = np.full((N,), T) if sequence_length is None else np.asarray(sequence_length)
+    scope = _scoped('bidirectional_rnn')
+    outs = []
+    for cell, d, init in ((cell_fw, 'fw', initial_state_fw), (cell_bw, 'bw', initial_state_bw)):
+        h = np.zeros((N, cell.num_units), np.float32) if init is None else np.asarray(init, np.float32).copy()
+        out = np.zeros((N, T, cell.num_units), np.float32)
+        order = np.arange(T) if d == 'fw' else np.arange(T)[::-1]
+        for t in order:
+            live = (t < L)[:, None]
+            hn = cell.step(x[:, t], h, scope + '/' + d)
+            h = np.where(live, hn, h)
+            out[:, t] = np.where(live, hn, 0)
+        outs.append(_t(out))
+    return tuple(outs), None
+
+
+_NN.bidirectional_dynamic_rnn = staticmethod(_bidirectional_dynamic_rnn)
+_NN.tanh = staticmethod(lambda x: tanh(x))
+
+
 # ---- tf.layers --------------------------------------------------------------------------------------------------------
 def _layer_scope(name, default):
     if name is not None:
@@ -328,21 +384,61 @@ def _layer_scope(name, default):
 
 class _Layers(object):
     @staticmethod
-    def conv1d(inputs, filters, kernel_size, padding='valid', dilation_rate=1, use_bias=True, name=None, strides=1):
+    def conv1d(inputs, filters, kernel_size, padding='valid', dilation_rate=1, use_bias=True, name=None, strides=1, activation=None):
         x = np.asarray(inputs)
         scope = _layer_scope(name, 'conv1d')
         k = int(kernel_size)
         W = _make_variable(scope + '/kernel', (k, x.shape[2], int(filters)), True)
-        if padding.lower() == 'same' and k != 1:
-            raise NotImplementedError("conv1d 'same' with kernel_size > 1 is not used by the reference")
         d = int(dilation_rate)
+        if padding.lower() == 'same' and k != 1:
+            # TF 'SAME', stride 1: total padding k-1, the smaller half in front
+            assert d == 1
+            x = np.pad(x, ((0, 0), ((k - 1) // 2, (k - 1) - (k - 1) // 2), (0, 0)))
         t_out = x.shape[1] - d * (k - 1)
         out = np.zeros((x.shape[0], t_out, int(filters)), np.float32)
         for j in np.arange(k):
             out = out + x[:, j * d:j * d + t_out, :] @ np.asarray(W)[j]
         if use_bias:
             out = out + np.asarray(_make_variable(scope + '/bias', (int(filters),), True))
-        return _t(out.astype(np.float32))
+        out = _t(out.astype(np.float32))
+        return activation(out) if activation is not None else out
+
+    @staticmethod
+    def dense(inputs, units, activation=None, use_bias=True, name=None, bias_initializer=None, kernel_initializer=None):
+        x = np.asarray(inputs)
+        scope = _layer_scope(name, 'dense')
+        W = _make_variable(scope + '/kernel', (x.shape[-1], int(units)), True)
+        out = x @ np.asarray(W)
+        if use_bias:
+            out = out + np.asarray(_make_variable(scope + '/bias', (int(units),), True))
+        out = _t(out.astype(np.float32))
+        return activation(out) if activation is not None else out
+
+    @staticmethod
+    def dropout(inputs, rate=0.5, training=False, name=None):
+        if training and rate:
+            raise NotImplementedError('dropout in training mode')
+        return inputs
+
+    @staticmethod
+    def batch_normalization(inputs, training=False, epsilon=1e-3, name=None):
+        """Inference mode: (x - moving_mean) / sqrt(moving_variance + eps) * gamma + beta, eps = 1e-3 (tf.layers default)."""
+        if training:
+            raise NotImplementedError('batch_normalization in training mode')
+        x = np.asarray(inputs)
+        scope = _layer_scope(name, 'batch_normalization')
+        c = x.shape[-1]
+        g, b, m, v = (np.asarray(_make_variable(scope + '/' + n, (c,), True)) for n in ('gamma', 'beta', 'moving_mean', 'moving_variance'))
+        return _t(((x - m) / np.sqrt(v + np.float32(epsilon)) * g + b).astype(np.float32))
+
+    @staticmethod
+    def max_pooling1d(inputs, pool_size, strides, padding='valid'):
+        x = np.asarray(inputs)
+        if int(pool_size) != 2 or int(strides) != 1 or padding.lower() != 'same':
+            raise NotImplementedError('only max_pooling1d(2, 1, same) (modules.py:38)')
+        # 'SAME' pads one step at the END (with -inf): out[t] = max(x[t], x[t+1]), last step alone
+        nxt = np.concatenate([x[:, 1:], np.full_like(x[:, :1], -np.inf)], axis=1)
+        return _t(np.maximum(x, nxt))
 
     @staticmethod
     def conv2d_transpose(inputs, filters, kernel_size, strides, padding='same', use_bias=True, name=None):
@@ -383,11 +479,20 @@ class _Train(object):
 
 train = _Train()
 
-contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=lambda **k: None))
+contrib = types.SimpleNamespace(layers=types.SimpleNamespace(xavier_initializer=lambda **k: None), rnn=types.SimpleNamespace(GRUCell=GRUCell))
 
 
 def install():
     """Registers this module as `tensorflow` (only in the process that generates the golden vectors)."""
     me = sys.modules[__name__]
     sys.modules['tensorflow'] = me
+    # sub-modules the reference imports by path (tacotron/modules.py:5-7); only GRUCell is used by the functions run here
+    for name, attrs in (('tensorflow.contrib', {}), ('tensorflow.contrib.rnn', {'GRUCell': GRUCell}), ('tensorflow.python', {}),
+                        ('tensorflow.python.layers', {'core': None}), ('tensorflow.contrib.seq2seq', {}), ('tensorflow.contrib.seq2seq.python', {}),
+                        ('tensorflow.contrib.seq2seq.python.ops', {}),
+                        ('tensorflow.contrib.seq2seq.python.ops.attention_wrapper',
+                         dict.fromkeys(['_bahdanau_score', '_BaseAttentionMechanism', 'BahdanauAttention', 'AttentionWrapper', 'AttentionWrapperState']))):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules.setdefault(name, m)
     return me

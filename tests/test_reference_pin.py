@@ -151,3 +151,22 @@ def test_cuda_melspectrogram_matches_reference_glue():
     for i in range(3):
         got = audio.melspectrogram(g['wav%d' % i], hparams).cpu().numpy()
         assert got.shape == g['mel%d' % i].shape and np.abs(got - g['mel%d' % i]).max() <= 1e-4
+
+
+# ---- tacotron/modules.py of the reference: prenet + encoder / post CBHG (tests/golden/make_reference_taco_golden.py) ---------
+def test_taco_oracle_prenet_and_cbhg_match_reference_modules():
+    from oracle.taco_oracle import TacotronOracle
+    g = np.load(os.path.join(GOLD, 'ref_taco_modules.npz'))
+    hp = synth.taco_tiny()
+    w = synth.make_taco_weights(hp, 2)
+    assert set(g['variable_names'].tolist()) <= set(w)                       # every name the reference's code creates exists
+    o = TacotronOracle(hp, w, 2)
+    p = g['x_emb']
+    for i, _ in enumerate(hp['enc_prenet_sizes']):
+        p = np.maximum(o._dense(p, 'prenet/dense_%d' % (i + 1)), 0)
+    assert np.abs(p - g['prenet']).max() < 1e-5
+    enc = o.cbhg(p, g['lengths'], 'encoder_cbhg', hp['enc_bank_size'], hp['enc_proj_sizes'], hp['enc_highway_depth'], hp['enc_rnn_size'],
+                 g['before_highway'], g['rnn_init'])
+    assert np.abs(enc - g['encoder_out']).max() < 2e-5
+    post = o.cbhg(g['mel'], None, 'post_cbhg', hp['post_bank_size'], hp['post_proj_sizes'], hp['post_highway_depth'], hp['post_rnn_size'])
+    assert np.abs(post - g['post_out']).max() < 2e-5
