@@ -354,6 +354,8 @@ int setup_fused(wnt_handle *h) {
     CKR(make_map(h, enc, &h->map_wdxp, h->WdxP, (uint64_t)h->L * wntf::ND, 512, wntf::ND));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PB_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PB_SMEM_BYTES));
     return WNT_OK;
 }
 
@@ -504,7 +506,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             const long s_l = off - d;
             const unsigned tiles = (unsigned)((M - s_l + wntf::TILE_M - 1) / wntf::TILE_M);
             if (dense && ub) {
-                wntf::colsum_bf16_kernel<<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, 0, st>>>(dXn, Gr + lb(l) + h->o_bd, T0, R, 0, 0, CH);
+                wntf::colsum_bf16_kernel<<<dim3((T0 + 1023) / 1024, N), EW_THREADS, 0, st>>>(dXn, Gr + lb(l) + h->o_bd, T0, R, 0, 0, 1024);
                 KCHECK();
             }
             if (!dense) CK(cudaMemsetAsync(GW + h->o_wd, 0, (size_t)D * R * sizeof(float), st));
@@ -513,9 +515,13 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             ba.has_dense = dense ? 1 : 0; ba.M = M;
             ba.TS = (const bf16 *)h->TS[l]; ba.dZs = (const bf16 *)h->dZs; ba.dFG = (bf16 *)h->dFG; ba.Z = dense ? (bf16 *)h->Z : nullptr;
             ba.dXin = dXn; ba.dXout = dXo; ba.err = h->fused_err;
-            wntf::layer_bwd_kernel<wntf::MODE_GATE><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba);
+            const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)h->sm_count);
+            if (h->fused_persistent)
+                wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE><<<pgrid, wntf::PF_THREADS, wntf::PB_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba, (int)tiles);
+            else
+                wntf::layer_bwd_kernel<wntf::MODE_GATE><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba);
             KCHECK();
-            wntf::colsum_bf16_kernel<<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, 0, st>>>((const bf16 *)h->dFG, h->SB + (size_t)l * N * D2, T0, D2, (int)off, 1, CH);
+            wntf::colsum_bf16_kernel<<<dim3((T0 + 511) / 512, N), EW_THREADS, 0, st>>>((const bf16 *)h->dFG, h->SB + (size_t)l * N * D2, T0, D2, (int)off, 1, 512);
             KCHECK();
             const bf16 *Xb = (const bf16 *)h->X[l], *dF = (const bf16 *)h->dFG, *Zq = (const bf16 *)h->Z;
             if (dense) CKR(gemm(h, st, true, false, D, R, m, Zq + off * D, D, dXn + off * R, R, ts, 0.f, GW + h->o_wd, R, GW + h->o_wd, R, f32));
@@ -526,7 +532,10 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
                 CKR(gemm(h, st, true, false, C, D2, m, h->LC, C, dF + off * D2, D2, ts, 0.f, GW + h->o_wlc, D2, GW + h->o_wlc, D2, f32));
                 CKR(gemm(h, st, false, true, m, C, D2, dF + off * D2, D2, W + h->o_wlc, D2, ts, 1.f, h->dLC32, C, h->dLC32, C, f32));
             }
-            wntf::layer_bwd_kernel<wntf::MODE_DX><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba);
+            if (h->fused_persistent)
+                wntf::layer_bwd_persistent_kernel<wntf::MODE_DX><<<pgrid, wntf::PF_THREADS, wntf::PB_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba, (int)tiles);
+            else
+                wntf::layer_bwd_kernel<wntf::MODE_DX><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba);
             KCHECK();
             h->fused_launches += 2;
             if (h->count_flops) h->flops += 2.0 * (double)(M - s_l) * ((dense ? (double)D * R : 0.0) + 2.0 * D2 * R);
@@ -725,7 +734,7 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
         A_(h->WdxP, (size_t)h->L * wntf::ND * 512 * 2);
         A_(h->dXp[0], (size_t)M * h->R * 2);
         A_(h->dXp[1], (size_t)M * h->R * 2);
-        h->fused_bwd = getenv("WNT_FUSED_BWD") != nullptr;   // opt-in: the one-tile-per-CTA backward kernels are correct but not yet faster than cuBLASLt
+        h->fused_bwd = getenv("WNT_NO_FUSED_BWD") == nullptr;
         A_(h->fused_err, 16);
     }
     A_(h->Zs, (size_t)Mo * LD * e);

@@ -750,14 +750,214 @@ layer_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent versions of the two backward kernels: one CTA per SM, the layer's B operand (Wd: 32 KB, or [Wfg1 | Wfg0]: 128 KB)
+// is loaded ONCE and stays in shared memory, only A tiles stream through a 4-stage ring that runs ahead across tiles, two
+// 128-column TMEM accumulators decouple the MMAs of tile it+1 from the epilogue of tile it, 16 epilogue warps = (row, 32 channels).
+// Per 128-row tile the TMA traffic drops from 64 + 64 KB (MODE_GATE) / 256 + 128 KB... to the A operand alone.
+constexpr int PB_STAGES = 4;
+constexpr int PB_OFF_B = PB_STAGES * BW_A_BYTES;                       // 64 KB of A stages, then the resident B (up to 8 K blocks x 16 KB)
+constexpr int PB_SMEM_BYTES = PB_OFF_B + 8 * BW_B_BYTES + 1024;        // 193 KB
+constexpr int PB_TMEM_COLS = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(PF_THREADS, 1)
+layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const BwdArgs a, int n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[PB_STAGES], empty_bar[PB_STAGES], acc_full[2], tmem_empty[2], b_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = MODE == MODE_GATE ? (a.has_dense ? 2 : 0) : 8;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < PB_STAGES; ++st) {
+            mbar_init(&full_bar[st], 1);
+            mbar_init(&empty_bar[st], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&tmem_empty[b], PF_EPI_THREADS);
+        }
+        mbar_init(&b_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)PB_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            mbar_expect_tx(&b_full, nkb * BW_B_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + PB_OFF_B + kb * BW_B_BYTES, &map_b, &b_full, kb * KB, a.l * ND);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const long row0 = (long)a.s + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int st = g % PB_STAGES, ph = (g / PB_STAGES) & 1;
+                    mbar_wait(&empty_bar[st], ph ^ 1, a.err);
+                    mbar_expect_tx(&full_bar[st], BW_A_BYTES);
+                    if (MODE == MODE_GATE) tma_load_2d(smem + st * BW_A_BYTES, &map_a, &full_bar[st], kb * KB, (int)row0);
+                    else tma_load_2d(smem + st * BW_A_BYTES, &map_a, &full_bar[st], (kb & 3) * KB, (int)(row0 + (kb >= 4 ? a.d : 0)));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = instr_desc(TILE_M, ND);
+            mbar_wait(&b_full, 0, a.err);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1, a.err);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * ND);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int st = g % PB_STAGES, ph = (g / PB_STAGES) & 1;
+                    mbar_wait(&full_bar[st], ph, a.err);
+                    tc_fence_after();
+                    const uint64_t da = smem_desc(smem_u32(smem + st * BW_A_BYTES)), db = smem_desc(smem_u32(smem + PB_OFF_B + kb * BW_B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < KB / 16; ++k) tc_mma(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty_bar[st]);
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3, qd = (warp - 2) >> 2;
+        const int r = q * 32 + lane, cb = qd * 32;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int buf = it & 1;
+            const long row0 = (long)a.s + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+            const long row = row0 + r;
+            const bool valid = row < a.M;
+            const int n = valid ? (int)(row / a.T0) : 0;
+            const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
+            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ND);
+            if (MODE == MODE_GATE) {
+                const bool live = valid && tau >= a.off;
+                const bool skip_row = live && tau >= a.SL;
+                const bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
+                const bf16 *dzs_row = skip_row ? a.dZs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
+                bf16 *dfg_row = a.dFG + (size_t)(valid ? row : 0) * NFG;
+                bf16 *z_row = a.Z ? a.Z + (size_t)(valid ? row : 0) * ND : nullptr;
+                float v[32];
+                if (nkb > 0) {
+                    mbar_wait(&acc_full[buf], (it >> 1) & 1, a.err);
+                    tc_fence_after();
+                    tc_ld32(tlane + cb, v);
+                    tc_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[buf]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {                 // 16 channels at a time keeps the live set under 96 registers
+                    const int c0 = cb + hh * 16;
+                    uint4 th_r[2], sg_r[2], dz_r[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        th_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                        sg_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + 128 + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                        dz_r[i] = skip_row ? *reinterpret_cast<const uint4 *>(dzs_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                    }
+                    const uint32_t *thw = reinterpret_cast<const uint32_t *>(th_r), *sgw = reinterpret_cast<const uint32_t *>(sg_r),
+                                   *dzw = reinterpret_cast<const uint32_t *>(dz_r);
+                    uint32_t df_p[8], dg_p[8], z_p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __nv_bfloat162 tb = *reinterpret_cast<const __nv_bfloat162 *>(&thw[i]), sb2 = *reinterpret_cast<const __nv_bfloat162 *>(&sgw[i]),
+                                             zb = *reinterpret_cast<const __nv_bfloat162 *>(&dzw[i]);
+                        const float t0 = __low2float(tb), t1 = __high2float(tb), s0 = __low2float(sb2), s1 = __high2float(sb2);
+                        const float d0 = live ? v[hh * 16 + 2 * i] + __low2float(zb) : 0.f, d1 = live ? v[hh * 16 + 2 * i + 1] + __high2float(zb) : 0.f;
+                        df_p[i] = pack2(d0 * s0 * (1.f - t0 * t0), d1 * s1 * (1.f - t1 * t1));
+                        dg_p[i] = pack2(d0 * t0 * s0 * (1.f - s0), d1 * t1 * s1 * (1.f - s1));
+                        z_p[i] = pack2(t0 * s0, t1 * s1);
+                    }
+                    if (valid) {
+                        uint4 *pf = reinterpret_cast<uint4 *>(dfg_row + c0), *pg = reinterpret_cast<uint4 *>(dfg_row + 128 + c0);
+                        pf[0] = make_uint4(df_p[0], df_p[1], df_p[2], df_p[3]);
+                        pf[1] = make_uint4(df_p[4], df_p[5], df_p[6], df_p[7]);
+                        pg[0] = make_uint4(dg_p[0], dg_p[1], dg_p[2], dg_p[3]);
+                        pg[1] = make_uint4(dg_p[4], dg_p[5], dg_p[6], dg_p[7]);
+                        if (z_row) {
+                            uint4 *pz = reinterpret_cast<uint4 *>(z_row + c0);
+                            pz[0] = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
+                            pz[1] = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
+                        }
+                    }
+                }
+            } else {
+                const bf16 *x_row = a.dXin + (size_t)(valid ? row : 0) * ND;
+                bf16 *o_row = a.dXout + (size_t)(valid ? row : 0) * ND;
+                uint4 xr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + cb + i * 8) : make_uint4(0, 0, 0, 0);
+                mbar_wait(&acc_full[buf], (it >> 1) & 1, a.err);
+                tc_fence_after();
+                float v[32];
+                tc_ld32(tlane + cb, v);
+                tc_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[buf]);
+                const uint32_t *xs = reinterpret_cast<const uint32_t *>(xr);
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
+                    o[i] = pack2(v[2 * i] + __low2float(xb), v[2 * i + 1] + __high2float(xb));
+                }
+                if (valid) {
+                    uint4 *po = reinterpret_cast<uint4 *>(o_row + cb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)PB_TMEM_COLS) : "memory");
+    }
+}
+
 // Per-sentence column sums of a bf16 (M, cols) matrix over the rows tau >= tau_min of each sentence, atomically added into
 // out (n, cols) (or out (cols) when per_sentence == 0): bias and global-condition gradients of the fused backward path.
-__global__ void colsum_bf16_kernel(const bf16 *__restrict__ in, float *__restrict__ out, int T0, int cols, int tau_min, int per_sentence, int CH) {
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ in, float *__restrict__ out, int T0, int cols, int tau_min, int per_sentence, int CH) {
+    // thread -> (row lane, 8 columns); 4 independent 16-byte loads in flight per thread; one shared-memory transpose-reduce per block
     const int tpr = cols >> 3, rpp = blockDim.x / tpr, lr = threadIdx.x / tpr, c = (threadIdx.x - lr * tpr) * 8;
-    const int n = blockIdx.y, t0 = max(blockIdx.x * CH, tau_min), t1 = min(T0, (int)(blockIdx.x + 1) * CH);
+    const int n = blockIdx.y, t0 = max((int)blockIdx.x * CH, tau_min), t1 = min(T0, (int)(blockIdx.x + 1) * CH);
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int tau = t0 + lr; tau < t1; tau += rpp) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(in + ((size_t)n * T0 + tau) * cols + c);
+    const bf16 *base = in + (size_t)n * T0 * cols + c;
+    int tau = t0 + lr;
+    for (; tau + 3 * rpp < t1; tau += 4 * rpp) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4 *>(base + (size_t)(tau + u * rpp) * cols);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+                s[2 * i] += __low2float(b);
+                s[2 * i + 1] += __high2float(b);
+            }
+        }
+    }
+    for (; tau < t1; tau += rpp) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(base + (size_t)tau * cols);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -766,17 +966,16 @@ __global__ void colsum_bf16_kernel(const bf16 *__restrict__ in, float *__restric
             s[2 * i + 1] += __high2float(b);
         }
     }
-    __shared__ float red[256 * 8];
+    __shared__ float red[8][257];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+    for (int i = 0; i < 8; ++i) red[i][threadIdx.x] = s[i];
     __syncthreads();
-    if (lr == 0) {
-        float *o = out + (per_sentence ? (size_t)n * cols : 0);
-        for (int i = 0; i < 8; ++i) {
-            float tot = 0.f;
-            for (int rr = 0; rr < rpp; ++rr) tot += red[(rr * tpr + threadIdx.x) * 8 + i];
-            atomicAdd(o + c + i, tot);
-        }
+    // cols outputs, each the sum over the rpp row lanes: thread j < cols handles column j
+    if ((int)threadIdx.x < cols) {
+        const int grp = threadIdx.x >> 3, i = threadIdx.x & 7;
+        float tot = 0.f;
+        for (int rr = 0; rr < rpp; ++rr) tot += red[i][rr * tpr + grp];
+        atomicAdd(out + (per_sentence ? (size_t)n * cols : 0) + threadIdx.x, tot);
     }
 }
 
