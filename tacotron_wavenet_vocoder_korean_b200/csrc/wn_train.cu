@@ -354,8 +354,8 @@ int setup_fused(wnt_handle *h) {
     CKR(make_map(h, enc, &h->map_wdxp, h->WdxP, (uint64_t)h->L * wntf::ND, 512, wntf::ND));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PB_SMEM_BYTES));
-    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PB_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PbLayout<wntf::MODE_GATE>::SMEM));
+    CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PbLayout<wntf::MODE_DX>::SMEM));
     return WNT_OK;
 }
 
@@ -517,7 +517,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             ba.dXin = dXn; ba.dXout = dXo; ba.err = h->fused_err;
             const unsigned pgrid = std::min<unsigned>(tiles, (unsigned)h->sm_count);
             if (h->fused_persistent)
-                wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE><<<pgrid, wntf::PF_THREADS, wntf::PB_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba, (int)tiles);
+                wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE><<<pgrid, wntf::PF_THREADS, wntf::PbLayout<wntf::MODE_GATE>::SMEM, st>>>(h->map_dx[cur], h->map_wdp, ba, (int)tiles);
             else
                 wntf::layer_bwd_kernel<wntf::MODE_GATE><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dx[cur], h->map_wdp, ba);
             KCHECK();
@@ -533,7 +533,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
                 CKR(gemm(h, st, false, true, m, C, D2, dF + off * D2, D2, W + h->o_wlc, D2, ts, 1.f, h->dLC32, C, h->dLC32, C, f32));
             }
             if (h->fused_persistent)
-                wntf::layer_bwd_persistent_kernel<wntf::MODE_DX><<<pgrid, wntf::PF_THREADS, wntf::PB_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba, (int)tiles);
+                wntf::layer_bwd_persistent_kernel<wntf::MODE_DX><<<pgrid, wntf::PF_THREADS, wntf::PbLayout<wntf::MODE_DX>::SMEM, st>>>(h->map_dfg, h->map_wdxp, ba, (int)tiles);
             else
                 wntf::layer_bwd_kernel<wntf::MODE_DX><<<tiles, wntf::THREADS, wntf::BW_SMEM_BYTES, st>>>(h->map_dfg, h->map_wdxp, ba);
             KCHECK();

@@ -127,6 +127,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane that owns one row moves a whole 32-byte sector per instruction,
+// which is what makes the thread = row (= TMEM lane) epilogues sector-efficient without a shared-memory transpose.
+__device__ __forceinline__ void stg256(void *p, const uint32_t *v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                 "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ldg256(const void *p, uint32_t *v) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                 "=r"(v[6]), "=r"(v[7]) : "l"(p) : "memory");
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
@@ -481,10 +491,12 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
             // residual input for the second epilogue: requested now, consumed after the dense MMA
             const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND;
-            uint4 xr[4];
-            if (a.do_dense) {
+            uint32_t xs[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + cb + i * 8) : make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 16; ++i) xs[i] = 0u;
+            if (a.do_dense && valid) {
+                ldg256(x_row + cb, xs);
+                ldg256(x_row + cb + 16, xs + 8);
             }
             mbar_wait(&acc1_full[buf], (it >> 1) & 1, a.err);
             tc_fence_after();
@@ -509,16 +521,13 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                     }
                 }
                 if (valid) {
-                    uint4 *pt = reinterpret_cast<uint4 *>(ts_row + cb), *ps = reinterpret_cast<uint4 *>(ts_row + 128 + cb);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        pt[i] = make_uint4(th_p[4 * i], th_p[4 * i + 1], th_p[4 * i + 2], th_p[4 * i + 3]);
-                        ps[i] = make_uint4(sg_p[4 * i], sg_p[4 * i + 1], sg_p[4 * i + 2], sg_p[4 * i + 3]);
-                    }
+                    stg256(ts_row + cb, th_p);
+                    stg256(ts_row + cb + 16, th_p + 8);
+                    stg256(ts_row + 128 + cb, sg_p);
+                    stg256(ts_row + 128 + cb + 16, sg_p + 8);
                     if (skip_row) {
-                        uint4 *pz = reinterpret_cast<uint4 *>(zs_row + cb);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) pz[i] = make_uint4(z_p[4 * i], z_p[4 * i + 1], z_p[4 * i + 2], z_p[4 * i + 3]);
+                        stg256(zs_row + cb, z_p);
+                        stg256(zs_row + cb + 16, z_p + 8);
                     }
                 }
                 if (a.do_dense) {
@@ -540,8 +549,6 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                 float v[32];
                 tc_ld32(tlane + cb, v);
                 tc_ld_wait();
-                const uint32_t xs[16] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w,
-                                         xr[2].x, xr[2].y, xr[2].z, xr[2].w, xr[3].x, xr[3].y, xr[3].z, xr[3].w};
                 uint32_t o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -549,9 +556,8 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
                     o[i] = pack2(v[2 * i] + __low2float(xb) + s_bd[cb + 2 * i], v[2 * i + 1] + __high2float(xb) + s_bd[cb + 2 * i + 1]);
                 }
                 if (valid) {
-                    uint4 *po = reinterpret_cast<uint4 *>(xn_row + cb);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    stg256(xn_row + cb, o);
+                    stg256(xn_row + cb + 16, o + 8);
                 }
                 tc_fence_before();
             }
@@ -757,7 +763,15 @@ layer_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // Per 128-row tile the TMA traffic drops from 64 + 64 KB (MODE_GATE) / 256 + 128 KB... to the A operand alone.
 constexpr int PB_STAGES = 4;
 constexpr int PB_OFF_B = PB_STAGES * BW_A_BYTES;                       // 64 KB of A stages, then the resident B (up to 8 K blocks x 16 KB)
-constexpr int PB_SMEM_BYTES = PB_OFF_B + 8 * BW_B_BYTES + 1024;        // 193 KB
+constexpr int PB_WB_ROW = 80, PB_WB_BYTES = 32 * PB_WB_ROW;            // per-warp staging buffer: 32 rows x (64 B + 16 B pad)
+template <int MODE> struct PbLayout {
+    static constexpr int NB = MODE == MODE_GATE ? 2 : 8;                // resident K blocks of B
+    static constexpr int OFF_W = PB_OFF_B + NB * BW_B_BYTES;            // MODE_GATE: 3 staging buffers (th, sg, dz) per epilogue warp
+    static constexpr int SMEM = OFF_W + (MODE == MODE_GATE ? PF_EPI_WARPS * 3 * PB_WB_BYTES : 0) + 1024;   // 217 KB / 193 KB
+};
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 constexpr int PB_TMEM_COLS = 256;
 
 template <int MODE>
@@ -796,7 +810,7 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     if (warp == 0) {
         if (lane == 0 && nkb > 0) {
             mbar_expect_tx(&b_full, nkb * BW_B_BYTES);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + PB_OFF_B + kb * BW_B_BYTES, &map_b, &b_full, kb * KB, a.l * ND);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + PB_OFF_B + kb * BW_B_BYTES, &map_b, &b_full, kb * KB, a.l * ND);   // nkb <= PbLayout<MODE>::NB
             int g = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const long row0 = (long)a.s + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
@@ -843,12 +857,31 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
             const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ND);
             if (MODE == MODE_GATE) {
+                // Thread = row is what TMEM gives, but 32 lanes x 16 B at a 512 B stride costs 32 half-used sectors per request.
+                // So the warp's 32 rows x 32 channels of tanh / sigmoid / skip gradient come in through coalesced cp.async
+                // (4 lanes per row, 64 B contiguous) into a per-warp staging buffer, and dFG / z leave the same way.
                 const bool live = valid && tau >= a.off;
-                const bool skip_row = live && tau >= a.SL;
-                const bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
-                const bf16 *dzs_row = skip_row ? a.dZs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
-                bf16 *dfg_row = a.dFG + (size_t)(valid ? row : 0) * NFG;
-                bf16 *z_row = a.Z ? a.Z + (size_t)(valid ? row : 0) * ND : nullptr;
+                uint8_t *wb = smem + PbLayout<MODE>::OFF_W + (warp - 2) * 3 * PB_WB_BYTES;
+                const long wrow0 = row0 + q * 32;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int id = k * 32 + lane, rw = id >> 2, part = id & 3;
+                    const long rg = wrow0 + rw;
+                    const int nr = (int)(rg / a.T0), tr = (int)(rg - (long)nr * a.T0);
+                    const bool lv = rg < a.M && tr >= a.off;
+                    uint8_t *d0 = wb + rw * PB_WB_ROW + part * 16;
+                    if (lv) {
+                        const bf16 *src = a.TS + (size_t)rg * NFG + cb + part * 8;
+                        cp_async16(d0, src);
+                        cp_async16(d0 + PB_WB_BYTES, src + 128);
+                    } else {
+                        *reinterpret_cast<uint4 *>(d0) = make_uint4(0, 0, 0, 0);
+                        *reinterpret_cast<uint4 *>(d0 + PB_WB_BYTES) = make_uint4(0, 0, 0, 0);
+                    }
+                    if (lv && tr >= a.SL) cp_async16(d0 + 2 * PB_WB_BYTES, a.dZs + ((size_t)nr * a.OW + (tr - a.SL)) * a.LD + a.zs_col0 + cb + part * 8);
+                    else *reinterpret_cast<uint4 *>(d0 + 2 * PB_WB_BYTES) = make_uint4(0, 0, 0, 0);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
                 float v[32];
                 if (nkb > 0) {
                     mbar_wait(&acc_full[buf], (it >> 1) & 1, a.err);
@@ -861,15 +894,17 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0.f;
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                uint8_t *mine = wb + lane * PB_WB_ROW;
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {                 // 16 channels at a time keeps the live set under 96 registers
-                    const int c0 = cb + hh * 16;
                     uint4 th_r[2], sg_r[2], dz_r[2];
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        th_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
-                        sg_r[i] = live ? *reinterpret_cast<const uint4 *>(ts_row + 128 + c0 + i * 8) : make_uint4(0, 0, 0, 0);
-                        dz_r[i] = skip_row ? *reinterpret_cast<const uint4 *>(dzs_row + c0 + i * 8) : make_uint4(0, 0, 0, 0);
+                        th_r[i] = *reinterpret_cast<const uint4 *>(mine + (hh * 2 + i) * 16);
+                        sg_r[i] = *reinterpret_cast<const uint4 *>(mine + PB_WB_BYTES + (hh * 2 + i) * 16);
+                        dz_r[i] = *reinterpret_cast<const uint4 *>(mine + 2 * PB_WB_BYTES + (hh * 2 + i) * 16);
                     }
                     const uint32_t *thw = reinterpret_cast<const uint32_t *>(th_r), *sgw = reinterpret_cast<const uint32_t *>(sg_r),
                                    *dzw = reinterpret_cast<const uint32_t *>(dz_r);
@@ -884,25 +919,38 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
                         dg_p[i] = pack2(d0 * t0 * s0 * (1.f - s0), d1 * t1 * s1 * (1.f - s1));
                         z_p[i] = pack2(t0 * s0, t1 * s1);
                     }
-                    if (valid) {
-                        uint4 *pf = reinterpret_cast<uint4 *>(dfg_row + c0), *pg = reinterpret_cast<uint4 *>(dfg_row + 128 + c0);
-                        pf[0] = make_uint4(df_p[0], df_p[1], df_p[2], df_p[3]);
-                        pf[1] = make_uint4(df_p[4], df_p[5], df_p[6], df_p[7]);
-                        pg[0] = make_uint4(dg_p[0], dg_p[1], dg_p[2], dg_p[3]);
-                        pg[1] = make_uint4(dg_p[4], dg_p[5], dg_p[6], dg_p[7]);
-                        if (z_row) {
-                            uint4 *pz = reinterpret_cast<uint4 *>(z_row + c0);
-                            pz[0] = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
-                            pz[1] = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
-                        }
+                    // results overwrite this lane's own row of the three buffers
+                    *reinterpret_cast<uint4 *>(mine + (hh * 2) * 16) = make_uint4(df_p[0], df_p[1], df_p[2], df_p[3]);
+                    *reinterpret_cast<uint4 *>(mine + (hh * 2 + 1) * 16) = make_uint4(df_p[4], df_p[5], df_p[6], df_p[7]);
+                    *reinterpret_cast<uint4 *>(mine + PB_WB_BYTES + (hh * 2) * 16) = make_uint4(dg_p[0], dg_p[1], dg_p[2], dg_p[3]);
+                    *reinterpret_cast<uint4 *>(mine + PB_WB_BYTES + (hh * 2 + 1) * 16) = make_uint4(dg_p[4], dg_p[5], dg_p[6], dg_p[7]);
+                    *reinterpret_cast<uint4 *>(mine + 2 * PB_WB_BYTES + (hh * 2) * 16) = make_uint4(z_p[0], z_p[1], z_p[2], z_p[3]);
+                    *reinterpret_cast<uint4 *>(mine + 2 * PB_WB_BYTES + (hh * 2 + 1) * 16) = make_uint4(z_p[4], z_p[5], z_p[6], z_p[7]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int id = k * 32 + lane, rw = id >> 2, part = id & 3;
+                    const long rg = wrow0 + rw;
+                    if (rg < a.M) {
+                        const uint8_t *s0 = wb + rw * PB_WB_ROW + part * 16;
+                        bf16 *dst = a.dFG + (size_t)rg * NFG + cb + part * 8;
+                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(s0);
+                        *reinterpret_cast<uint4 *>(dst + 128) = *reinterpret_cast<const uint4 *>(s0 + PB_WB_BYTES);
+                        if (a.Z) *reinterpret_cast<uint4 *>(a.Z + (size_t)rg * ND + cb + part * 8) = *reinterpret_cast<const uint4 *>(s0 + 2 * PB_WB_BYTES);
                     }
                 }
+                __syncwarp();
             } else {
                 const bf16 *x_row = a.dXin + (size_t)(valid ? row : 0) * ND;
                 bf16 *o_row = a.dXout + (size_t)(valid ? row : 0) * ND;
-                uint4 xr[4];
+                uint32_t xs[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) xr[i] = valid ? *reinterpret_cast<const uint4 *>(x_row + cb + i * 8) : make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < 16; ++i) xs[i] = 0u;
+                if (valid) {
+                    ldg256(x_row + cb, xs);
+                    ldg256(x_row + cb + 16, xs + 8);
+                }
                 mbar_wait(&acc_full[buf], (it >> 1) & 1, a.err);
                 tc_fence_after();
                 float v[32];
@@ -910,7 +958,6 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
                 tc_ld_wait();
                 tc_fence_before();
                 mbar_arrive(&tmem_empty[buf]);
-                const uint32_t *xs = reinterpret_cast<const uint32_t *>(xr);
                 uint32_t o[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -918,9 +965,8 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
                     o[i] = pack2(v[2 * i] + __low2float(xb), v[2 * i + 1] + __high2float(xb));
                 }
                 if (valid) {
-                    uint4 *po = reinterpret_cast<uint4 *>(o_row + cb);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    stg256(o_row + cb, o);
+                    stg256(o_row + cb + 16, o + 8);
                 }
             }
         }
