@@ -94,6 +94,8 @@ struct wnt_handle {
     bf16 *dXp[2] = {nullptr, nullptr};   // ping-pong gradient w.r.t. the layer outputs / inputs (fused backward, bf16)
     bool fused_bwd = false, fused_persistent = true;
     CUtensorMap map_x, map_lc, map_wfg, map_wd, map_dx[2], map_dfg, map_wdp, map_wdxp;
+    CUtensorMap map_x64, map_lc64, map_z64, map_dfg64, map_dx64[2];   // 64-row x 64-channel boxes: MN-major operands of the weight-gradient kernel
+    bool fused_wgrad = false;
     unsigned *fused_err = nullptr;
     int64_t fused_launches = 0;
 };
@@ -354,6 +356,15 @@ int setup_fused(wnt_handle *h) {
     CKR(make_map(h, enc, &h->map_wdxp, h->WdxP, (uint64_t)h->L * wntf::ND, 512, wntf::ND));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::BW_SMEM_BYTES));
+    CKR(make_map(h, enc, &h->map_x64, h->Xall, (uint64_t)h->L * h->M, 128, wntf::WG_KROWS));
+    if (h->C) CKR(make_map(h, enc, &h->map_lc64, h->LC, (uint64_t)h->M, (uint64_t)h->C, wntf::WG_KROWS));
+    else h->map_lc64 = h->map_x64;
+    CKR(make_map(h, enc, &h->map_z64, h->Z, (uint64_t)h->M, 128, wntf::WG_KROWS));
+    CKR(make_map(h, enc, &h->map_dfg64, h->dFG, (uint64_t)h->M, 256, wntf::WG_KROWS));
+    for (int i = 0; i < 2; ++i) CKR(make_map(h, enc, &h->map_dx64[i], h->dXp[i], (uint64_t)h->M, 128, wntf::WG_KROWS));
+    CK(cudaFuncSetAttribute(wntf::layer_wgrad_kernel<wntf::MODE_WFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::WgLayout<wntf::MODE_WFG>::SMEM));
+    CK(cudaFuncSetAttribute(wntf::layer_wgrad_kernel<wntf::MODE_WLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::WgLayout<wntf::MODE_WLD>::SMEM));
+    h->fused_wgrad = getenv("WNT_NO_FUSED_WGRAD") == nullptr;
     CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PbLayout<wntf::MODE_GATE>::SMEM));
     CK(cudaFuncSetAttribute(wntf::layer_bwd_persistent_kernel<wntf::MODE_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, wntf::PbLayout<wntf::MODE_DX>::SMEM));
     return WNT_OK;
@@ -488,6 +499,8 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     CK(cudaMemsetAsync(h->dX32, 0, (size_t)M * R * sizeof(float), st));
     if (h->fused && h->fused_bwd)
         for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->dXp[i], 0, (size_t)M * R * 2, st));
+    if (h->fused && h->fused_bwd && h->fused_wgrad)   // the split-K weight-gradient kernels accumulate with atomics
+        CK(cudaMemsetAsync(Gr + h->o_layer_w, 0, (size_t)h->layer_w_stride * L * sizeof(float), st));
     if (C) CK(cudaMemsetAsync(h->dLC32, 0, (size_t)M * C * sizeof(float), st));
     CK(cudaMemsetAsync(h->SB, 0, (size_t)L * N * D2 * sizeof(float), st));
     for (int l = L - 1; l >= 0; --l) {
@@ -524,6 +537,24 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             wntf::colsum_bf16_kernel<<<dim3((T0 + 511) / 512, N), EW_THREADS, 0, st>>>((const bf16 *)h->dFG, h->SB + (size_t)l * N * D2, T0, D2, (int)off, 1, 512);
             KCHECK();
             const bf16 *Xb = (const bf16 *)h->X[l], *dF = (const bf16 *)h->dFG, *Zq = (const bf16 *)h->Z;
+            if (h->fused_wgrad) {
+                // split-K tcgen05 weight gradients straight from the row-major activations (MN-major operands); dFG is read once per kernel
+                wntf::WgArgs wa;
+                wa.l = l; wa.d = d; wa.off = (int)off; wa.n_kblocks = (int)((m + wntf::WG_KROWS - 1) / wntf::WG_KROWS);
+                wa.M = M; wa.x_row0 = (long)l * M; wa.err = h->fused_err;
+                const unsigned wgrid = std::min<unsigned>((unsigned)wa.n_kblocks, (unsigned)h->sm_count);
+                wa.dW0 = GW + h->o_wfg; wa.dW1 = GW + h->o_wfg + (int64_t)R * D2; wa.rows0 = 128;
+                wntf::layer_wgrad_kernel<wntf::MODE_WFG><<<wgrid, wntf::PF_THREADS, wntf::WgLayout<wntf::MODE_WFG>::SMEM, st>>>(
+                    h->map_x64, h->map_x64, h->map_dfg64, h->map_dfg64, wa);
+                KCHECK();
+                wa.dW0 = GW + h->o_wlc; wa.dW1 = GW + h->o_wd; wa.rows0 = C;
+                wntf::layer_wgrad_kernel<wntf::MODE_WLD><<<wgrid, wntf::PF_THREADS, wntf::WgLayout<wntf::MODE_WLD>::SMEM, st>>>(
+                    h->map_lc64, h->map_z64, h->map_dfg64, h->map_dx64[cur], wa);
+                KCHECK();
+                h->fused_launches += 2;
+                if (h->count_flops) h->flops += 2.0 * (double)m * ((2.0 * R + C) * D2 + (dense ? (double)D * R : 0.0));
+                if (C) CKR(gemm(h, st, false, true, m, C, D2, dF + off * D2, D2, W + h->o_wlc, D2, ts, 1.f, h->dLC32, C, h->dLC32, C, f32));
+            } else {
             if (dense) CKR(gemm(h, st, true, false, D, R, m, Zq + off * D, D, dXn + off * R, R, ts, 0.f, GW + h->o_wd, R, GW + h->o_wd, R, f32));
             CKR(gemm(h, st, true, false, R, D2, m, Xb + (off - d) * R, R, dF + off * D2, D2, ts, 0.f, GW + h->o_wfg, D2, GW + h->o_wfg, D2, f32));
             CKR(gemm(h, st, true, false, R, D2, m, Xb + off * R, R, dF + off * D2, D2, ts, 0.f, GW + h->o_wfg + (int64_t)R * D2, D2,
@@ -531,6 +562,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
             if (C) {
                 CKR(gemm(h, st, true, false, C, D2, m, h->LC, C, dF + off * D2, D2, ts, 0.f, GW + h->o_wlc, D2, GW + h->o_wlc, D2, f32));
                 CKR(gemm(h, st, false, true, m, C, D2, dF + off * D2, D2, W + h->o_wlc, D2, ts, 1.f, h->dLC32, C, h->dLC32, C, f32));
+            }
             }
             if (h->fused_persistent)
                 wntf::layer_bwd_persistent_kernel<wntf::MODE_DX><<<pgrid, wntf::PF_THREADS, wntf::PbLayout<wntf::MODE_DX>::SMEM, st>>>(h->map_dfg, h->map_wdxp, ba, (int)tiles);

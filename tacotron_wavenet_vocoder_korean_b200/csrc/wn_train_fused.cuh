@@ -978,6 +978,147 @@ layer_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradients of one dilation layer as split-K tcgen05 GEMMs over the ROW dimension (K = all 478 k rows):
+//     dW[m][n] = sum_rows A[row][m] * B[row][n]
+// Both operands are consumed exactly as they lie in HBM (row-major activations), i.e. MN-major for the tensor core: a TMA box
+// of 64 rows x 64 channels (128 B per row, 128B swizzle) is one swizzle atom column of an MN-major operand -- 8-row groups
+// 1024 B apart along K (stride byte offset), 64-channel groups one box (8 KB) apart along M/N (leading byte offset).
+//   MODE_WFG  acc0 (128 x 256) = X[row-d]^T . dFG[row]   (tap 0),   acc1 (128 x 256) = X[row]^T . dFG[row]   (tap 1)
+//   MODE_WLD  acc0 (128 x 256) = LC[row-off]^T . dFG[row] (rows >= C are zero: TMA out-of-bounds fill),  acc1 (128 x 128) = Z[row]^T . dXn[row]
+// dFG is read ONCE for both accumulators (cuBLASLt reads it once per GEMM).  Each CTA owns every gridDim-th 64-row block, keeps
+// its partial sums in TMEM (512 columns) and adds them to the fp32 gradient buffer with 16-byte vector atomics at the end.
+constexpr int WG_KROWS = 64;                                           // rows per K block
+constexpr int WG_BOX = WG_KROWS * 128;                                  // one 64 x 64 bf16 box = 8 KB
+constexpr int MODE_WFG = 0, MODE_WLD = 1;
+template <int MODE> struct WgLayout {
+    static constexpr int A0 = 0, A1 = 2 * WG_BOX, B0 = 4 * WG_BOX;      // A0, A1: 128 channels = 2 boxes; B0 (dFG): 256 = 4 boxes
+    static constexpr int B1 = 8 * WG_BOX;                               // MODE_WLD: dXn, 2 boxes
+    static constexpr int STAGE = MODE == MODE_WFG ? 8 * WG_BOX : 10 * WG_BOX;   // 64 KB / 80 KB
+    static constexpr int STAGES = MODE == MODE_WFG ? 3 : 2;
+    static constexpr int SMEM = STAGES * STAGE + 1024;
+};
+
+struct WgArgs {
+    int l, d, off, n_kblocks;
+    long M, x_row0;            // rows per layer buffer; first row of layer l in the stacked X tensor
+    float *dW0, *dW1;          // MODE_WFG: tap 0 / tap 1 (128 x 256 each);  MODE_WLD: dWlc (C x 256) / dWd (128 x 128)
+    int rows0;                 // valid rows of dW0 (MODE_WLD: C), 128 otherwise
+    unsigned *err;
+};
+
+// MN-major operand descriptor (see the comment above): LBO = 8 KB between 64-channel groups, SBO = 1 KB between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((uint32_t)WG_BOX >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) { return instr_desc(M, N) | (1u << 15) | (1u << 16); }
+
+template <int MODE>
+__global__ void __launch_bounds__(PF_THREADS, 1)
+layer_wgrad_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b0,
+                   const __grid_constant__ CUtensorMap map_b1, const WgArgs a) {
+    typedef WgLayout<MODE> LY;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[LY::STAGES], empty_bar[LY::STAGES], acc_full;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_blocks = ((int)blockIdx.x < a.n_kblocks) ? (a.n_kblocks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < LY::STAGES; ++st) {
+            mbar_init(&full_bar[st], 1);
+            mbar_init(&empty_bar[st], 1);
+        }
+        mbar_init(&acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < my_blocks; ++i) {
+                const int st = i % LY::STAGES, ph = (i / LY::STAGES) & 1;
+                const long row = (long)a.off + ((long)blockIdx.x + (long)i * gridDim.x) * WG_KROWS;      // rows past M read as zero
+                mbar_wait(&empty_bar[st], ph ^ 1, a.err);
+                uint8_t *sp = smem + st * LY::STAGE;
+                mbar_expect_tx(&full_bar[st], LY::STAGE);
+                if (MODE == MODE_WFG) {
+                    for (int h = 0; h < 2; ++h) {
+                        tma_load_2d(sp + LY::A0 + h * WG_BOX, &map_a0, &full_bar[st], h * 64, (int)(a.x_row0 + row - a.d));
+                        tma_load_2d(sp + LY::A1 + h * WG_BOX, &map_a0, &full_bar[st], h * 64, (int)(a.x_row0 + row));
+                    }
+                } else {
+                    for (int h = 0; h < 2; ++h) {
+                        tma_load_2d(sp + LY::A0 + h * WG_BOX, &map_a0, &full_bar[st], h * 64, (int)(row - a.off));   // LC
+                        tma_load_2d(sp + LY::A1 + h * WG_BOX, &map_a1, &full_bar[st], h * 64, (int)row);             // Z
+                        tma_load_2d(sp + LY::B1 + h * WG_BOX, &map_b1, &full_bar[st], h * 64, (int)row);             // dXn
+                    }
+                }
+                for (int h = 0; h < 4; ++h) tma_load_2d(sp + LY::B0 + h * WG_BOX, &map_b0, &full_bar[st], h * 64, (int)row);   // dFG
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id256 = instr_desc_mn(128, 256), id128 = instr_desc_mn(128, 128);
+            for (int i = 0; i < my_blocks; ++i) {
+                const int st = i % LY::STAGES, ph = (i / LY::STAGES) & 1;
+                mbar_wait(&full_bar[st], ph, a.err);
+                tc_fence_after();
+                const uint32_t sp = smem_u32(smem + st * LY::STAGE);
+#pragma unroll
+                for (int k = 0; k < WG_KROWS / 16; ++k) {          // 16 rows = 2048 B further down the box
+                    const uint64_t koff = (uint64_t)((k * 16 * 128) >> 4);
+                    const uint64_t da0 = smem_desc_mn(sp + LY::A0) + koff, da1 = smem_desc_mn(sp + LY::A1) + koff, db0 = smem_desc_mn(sp + LY::B0) + koff;
+                    const uint32_t accum = (i | k) != 0 ? 1u : 0u;
+                    tc_mma(tmem_base, da0, db0, id256, accum);
+                    if (MODE == MODE_WFG) tc_mma(tmem_base + 256, da1, db0, id256, accum);
+                    else tc_mma(tmem_base + 256, da1, smem_desc_mn(sp + LY::B1) + koff, id128, accum);
+                }
+                tc_commit(&empty_bar[st]);
+            }
+            tc_commit(&acc_full);
+        }
+    } else if (my_blocks > 0) {
+        // epilogue: thread = (output row m = TMEM lane, 64-column quarter); partial sums -> fp32 gradients with 16-byte atomics
+        const int q = warp & 3, qd = (warp - 2) >> 2;
+        const int m = q * 32 + lane;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        mbar_wait(&acc_full, 0, a.err);
+        tc_fence_after();
+#pragma unroll 1
+        for (int acc = 0; acc < 2; ++acc) {
+            const int ncols = (MODE == MODE_WLD && acc == 1) ? 128 : 256;
+            float *dst = (acc == 0 ? a.dW0 : a.dW1) + (size_t)m * ncols;
+            const bool row_ok = acc == 0 ? m < a.rows0 : true;
+            const int per = ncols / 4;                            // columns per quarter
+#pragma unroll 1
+            for (int c0 = qd * per; c0 < (qd + 1) * per; c0 += 32) {
+                float v[32];
+                tc_ld32(tlane + acc * 256 + c0, v);
+                tc_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4 *>(dst + c0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // Per-sentence column sums of a bf16 (M, cols) matrix over the rows tau >= tau_min of each sentence, atomically added into
 // out (n, cols) (or out (cols) when per_sentence == 0): bias and global-condition gradients of the fused backward path.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ in, float *__restrict__ out, int T0, int cols, int tau_min, int per_sentence, int CH) {

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from tacotron_wavenet_vocoder_korean_b200 import synth
-from tests.train_helpers import train_case, rel_err, cosine
+from tests.train_helpers import train_case, rel_err, cosine, well_conditioned
 
 pytestmark = pytest.mark.gpu
 
@@ -174,6 +174,35 @@ def test_bf16_overfits_one_batch_at_reference_layer_sizes():
     assert losses[-1] < losses[0] - 0.3, losses
     i = tr.info()
     assert i['gemm_launches'] > 0 and i['kernel_launches'] > 0 and i['flops_per_step'] > 0
+
+
+def test_fused_tcgen05_path_matches_fp32_oracle_and_cublaslt_path(monkeypatch):
+    """R = D = 128 (BASELINE configs[3] layer sizes): the tcgen05/TMEM/TMA kernels (persistent fused forward, gate backward,
+    dx, MN-major split-K weight gradients) against the fp32 torch oracle and against the cuBLASLt path on the same inputs."""
+    kw = synth.cfg2(2)
+    T = 3600
+    w, wav, mel, gc = train_case(kw, T)
+    w = well_conditioned(w)
+    Lo, go = _oracle(kw, w).loss_and_grads(wav, mel, gc)
+    res = {}
+    for mode in ('cublaslt', 'tcgen05'):
+        if mode == 'cublaslt':
+            monkeypatch.setenv('WNT_NO_FUSED', '1')
+        else:
+            monkeypatch.delenv('WNT_NO_FUSED', raising=False)
+        tr = _trainer(kw, T, 'bf16', w)
+        L = float(tr.loss_and_grads(wav, mel, gc).item())
+        res[mode] = (L, tr.state_dict('grads'), tr.info())
+        assert abs(L - Lo) <= 5e-3 * abs(Lo), (mode, L, Lo)
+    assert res['cublaslt'][2]['fused_launches'] == 0
+    assert res['tcgen05'][2]['fused_launches'] == 30 + 2 * 30 + 2 * 30          # forward, (gate, dx), (wfg, wlc+wd) per layer
+    g_c, g_t = res['cublaslt'][1], res['tcgen05'][1]
+    big = [k for k in go if np.linalg.norm(go[k]) > 1e-4]
+    bad = {k: (cosine(g_t[k], go[k]), rel_err(g_t[k], go[k])) for k in big if cosine(g_t[k], go[k]) < 0.995 or rel_err(g_t[k], go[k]) > 0.1}
+    assert not bad, bad
+    assert min(cosine(g_t[k], g_c[k]) for k in big) >= 0.995
+    # the fused path must not be noticeably noisier than the cuBLASLt path
+    assert max(rel_err(g_t[k], go[k]) for k in big) <= 1.5 * max(rel_err(g_c[k], go[k]) for k in big) + 0.01
 
 
 def test_wavenet_model_add_loss_add_optimizer_surface():
