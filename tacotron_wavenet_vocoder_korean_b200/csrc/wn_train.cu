@@ -96,6 +96,9 @@ struct wnt_handle {
     CUtensorMap map_x, map_lc, map_wfg, map_wd, map_dx[2], map_dfg, map_wdp, map_wdxp;
     CUtensorMap map_x64, map_lc64, map_z64, map_dfg64, map_dx64[2];   // 64-row x 64-channel boxes: MN-major operands of the weight-gradient kernel
     bool fused_wgrad = false;
+    bf16 *Wcol = nullptr, *WcDup = nullptr;   // causal layer as a GEMM: hi|lo im2col of the waveform, duplicated kernel
+    float *dWcTmp = nullptr;
+    bool causal_gemm = false;
     unsigned *fused_err = nullptr;
     int64_t fused_launches = 0;
 };
@@ -319,6 +322,10 @@ int refresh_copy(wnt_handle *h, cudaStream_t st) {
         wntf::transpose_weights_kernel<<<grid_for(tot, EW_THREADS, 8 * h->sm_count), EW_THREADS, 0, st>>>(
             h->P, h->o_layer_w, h->layer_w_stride, h->o_wfg, h->o_wlc, h->o_wd, h->L, h->C, h->WfgT, h->WdT, h->WdP, h->WdxP);
         KCHECK();
+        if (h->causal_gemm) {
+            wntf::causal_dup_kernel<<<(h->ifw * h->R + 255) / 256, 256, 0, st>>>(h->P + h->o_wc, h->WcDup, h->ifw, h->R);
+            KCHECK();
+        }
     }
     return WNT_OK;
 }
@@ -411,9 +418,15 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     }
     // ---- causal layer ----
     {
-        const size_t sm = ((size_t)h->ifw * R + CH + h->ifw) * sizeof(float);
-        causal_fwd_kernel<T><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, P + h->o_wc, (T *)h->X[0], h->T, T0, h->ifw, R, CH);
-        KCHECK();
+        if (h->fused && h->causal_gemm) {
+            wntf::wav_im2col_kernel<<<grid_for((long)M * h->ifw, EW_THREADS, cap), EW_THREADS, 0, st>>>(wav, h->Wcol, N, h->T, T0, h->ifw);
+            KCHECK();
+            CKR(gemm(h, st, false, false, M, R, 2 * h->ifw, h->Wcol, 2 * h->ifw, h->WcDup, R, ts, 0.f, h->X[0], R, h->X[0], R, ts));
+        } else {
+            const size_t sm = ((size_t)h->ifw * R + CH + h->ifw) * sizeof(float);
+            causal_fwd_kernel<T><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, P + h->o_wc, (T *)h->X[0], h->T, T0, h->ifw, R, CH);
+            KCHECK();
+        }
     }
     // ---- dilation stack ----
     for (int l = 0; l < L; ++l) {
@@ -603,7 +616,10 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     {
         CK(cudaMemsetAsync(Gr + h->o_wc, 0, (size_t)h->ifw * R * sizeof(float), st));
         const size_t sm = (size_t)(CH + h->ifw) * sizeof(float);
-        if (h->fused && h->fused_bwd)
+        if (h->fused && h->fused_bwd && h->causal_gemm) {
+            CKR(gemm(h, st, true, false, 2 * h->ifw, R, M, h->Wcol, 2 * h->ifw, h->dXp[L & 1], R, ts, 0.f, h->dWcTmp, R, h->dWcTmp, R, f32));
+            wntf::causal_fold_kernel<<<(h->ifw * R + 255) / 256, 256, 0, st>>>(h->dWcTmp, Gr + h->o_wc, h->ifw, R);
+        } else if (h->fused && h->fused_bwd)
             causal_bwd_kernel<bf16><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, h->dXp[L & 1], Gr + h->o_wc, h->T, T0, h->ifw, R, CH);
         else
             causal_bwd_kernel<float><<<dim3((T0 + CH - 1) / CH, N), EW_THREADS, sm, st>>>(wav, h->dX32, Gr + h->o_wc, h->T, T0, h->ifw, R, CH);
@@ -767,6 +783,12 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
         A_(h->dXp[0], (size_t)M * h->R * 2);
         A_(h->dXp[1], (size_t)M * h->R * 2);
         h->fused_bwd = getenv("WNT_NO_FUSED_BWD") == nullptr;
+        h->causal_gemm = h->ifw % 4 == 0 && getenv("WNT_NO_CAUSAL_GEMM") == nullptr;
+        if (h->causal_gemm) {
+            A_(h->Wcol, (size_t)M * 2 * h->ifw * 2);
+            A_(h->WcDup, (size_t)2 * h->ifw * h->R * 2);
+            A_(h->dWcTmp, (size_t)2 * h->ifw * h->R * 4);
+        }
         A_(h->fused_err, 16);
     }
     A_(h->Zs, (size_t)Mo * LD * e);
@@ -820,6 +842,7 @@ void wnt_destroy(wnt_handle *h) {
     if (h->bf) fr(h->Pc);   // fp32: Pc aliases the caller's parameter buffer
     for (auto p : h->U) fr(p);
     for (auto p : h->dU) fr(p);
+    fr(h->Wcol); fr(h->WcDup); fr(h->dWcTmp);
     fr(h->Xall); fr(h->WfgT); fr(h->WdT); fr(h->WdP); fr(h->WdxP); fr(h->dXp[0]); fr(h->dXp[1]); fr(h->fused_err);
     for (auto p : h->TS) fr(p);
     void *all[] = {h->LC, h->dLC32, h->Zs, h->dZs, h->Z, h->T1, h->T2, h->dC1, h->dTot, h->dY, h->dXb, h->dFG, h->FG32, h->TOT, h->dT32, h->Y,

@@ -1166,6 +1166,36 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Causal layer (scalar input) as tensor-core GEMMs.  The 32-tap FIR x0[row][r] = sum_k wav[n, tau+k] * Wc[k][r] is a GEMM over
+// the im2col matrix of the waveform; to keep 16-bit audio exact in bf16 operands every sample is split into hi + lo bf16 parts:
+//   Wcol (M, 2*ifw) = [ hi(wav[tau+0..ifw)) | lo(wav[tau+0..ifw)) ],   WcDup (2*ifw, R) = [Wc ; Wc]   ->   x0 = Wcol . WcDup
+// and the weight gradient is dWc[k] = (Wcol^T . dx0)[k] + (Wcol^T . dx0)[ifw + k].
+__global__ void wav_im2col_kernel(const float *__restrict__ wav, bf16 *__restrict__ Wcol, int N, int Tlen, int T0, int ifw) {
+    const long total = (long)N * T0 * ifw;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % ifw);
+        const long row = e / ifw;
+        const int n = (int)(row / T0), tau = (int)(row - (long)n * T0);
+        const float x = wav[(size_t)n * Tlen + tau + k];
+        const bf16 hi = __float2bfloat16_rn(x);
+        Wcol[row * (2 * ifw) + k] = hi;
+        Wcol[row * (2 * ifw) + ifw + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+    }
+}
+__global__ void causal_dup_kernel(const float *__restrict__ Wc, bf16 *__restrict__ WcDup, int ifw, int R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ifw * R) {
+        const bf16 v = __float2bfloat16_rn(Wc[i]);
+        WcDup[i] = v;
+        WcDup[ifw * R + i] = v;
+    }
+}
+__global__ void causal_fold_kernel(const float *__restrict__ tmp, float *__restrict__ dWc, int ifw, int R) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ifw * R) dWc[i] = tmp[i] + tmp[ifw * R + i];
+}
+
 // K-major (transposed) bf16 copies of the per-layer kernels, rebuilt whenever the parameters change:
 //   WfgT (L*256, 384): row = l*256 + n (n: filter 0..127 | gate 128..255), column k: [0,128) tap x[tau-d], [128,256) tap x[tau],
 //                      [256, 256+C) local condition, zero beyond;   WdT (L*128, 128): row = l*128 + r, column = d.
