@@ -509,7 +509,7 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     CKR(gemm(h, st, true, false, LD, S, Mo, h->Zs, LD, h->dTot, S, ts, 0.f, Gr + h->o_ws, S, Gr + h->o_ws, S, f32));
     CKR(gemm(h, st, false, true, Mo, LD, S, h->dTot, S, Pc + h->o_ws, S, ts, 0.f, h->dZs, LD, h->dZs, LD, ts));
     // ---- backward: dilation stack ----
-    CK(cudaMemsetAsync(h->dX32, 0, (size_t)M * R * sizeof(float), st));
+    if (h->dX32) CK(cudaMemsetAsync(h->dX32, 0, (size_t)M * R * sizeof(float), st));
     if (h->fused && h->fused_bwd)
         for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->dXp[i], 0, (size_t)M * R * 2, st));
     if (h->fused && h->fused_bwd && h->fused_wgrad)   // the split-K weight-gradient kernels accumulate with atomics
@@ -799,14 +799,18 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     A_(h->dC1, (size_t)Mo * h->S * e);
     A_(h->dTot, (size_t)Mo * h->S * e);
     A_(h->dY, (size_t)Mo * h->OP * e);
-    A_(h->dXb, (size_t)M * h->R * e);
+    // the cuBLASLt path keeps fp32 pre-activations and an fp32 dx master; the tcgen05 path needs neither
+    const bool lt_fwd = !h->fused, lt_bwd = !(h->fused && getenv("WNT_NO_FUSED_BWD") == nullptr);
+    if (lt_bwd) A_(h->dXb, (size_t)M * h->R * e);
     A_(h->dFG, (size_t)M * D2 * e);
-    A_(h->FG32, (size_t)M * D2 * 4);
+    if (lt_fwd) A_(h->FG32, (size_t)M * D2 * 4);
     A_(h->TOT, (size_t)Mo * h->S * 4);
     A_(h->dT32, (size_t)Mo * h->S * 4);
     A_(h->Y, (size_t)Mo * h->OP * 4);
-    A_(h->dX32, (size_t)M * h->R * 4);
-    A_(h->dZ32, (size_t)M * h->D * 4);
+    if (lt_bwd) {
+        A_(h->dX32, (size_t)M * h->R * 4);
+        A_(h->dZ32, (size_t)M * h->D * 4);
+    }
     A_(h->GCB, (size_t)h->L * h->N * D2 * 4);
     A_(h->SB, (size_t)h->L * h->N * D2 * 4);
     A_(h->bsum, (size_t)h->S * 4);
