@@ -29,7 +29,8 @@ hparams = HParams(
     skip_channels=512, use_biases=True, initial_filter_width=32, upsample_factor=[5, 5, 12],
     # wavenet training (hparams.py:54-55,84-94)
     l2_regularization_strength=0, sample_size=15000, wavenet_batch_size=8, wavenet_learning_rate=1e-3, wavenet_decay_rate=0.5,
-    wavenet_decay_steps=300000, wavenet_clip_gradients=False, optimizer='adam',
+    wavenet_decay_steps=300000, wavenet_clip_gradients=False, optimizer='adam', num_steps=200000, skip_path_filter=False,
+    max_checkpoints=3,
     # tacotron (hparams.py:124-166)
     cleaners='korean_cleaners', model_type='deepvoice', speaker_embedding_size=16, embedding_size=256, dropout_prob=0.5,
     enc_prenet_sizes=[256, 128], enc_bank_size=16, enc_bank_channel_size=128, enc_maxpool_width=2, enc_highway_depth=4,
