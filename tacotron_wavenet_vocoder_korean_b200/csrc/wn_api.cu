@@ -1062,7 +1062,7 @@ int wn_melspectrogram(const float *wav_dev, int rows, int64_t n, const wn_mel_co
     p.min_level = (float)std::exp(mc->min_level_db / 20.0 * std::log(10.0));
     p.ref_level_db = mc->ref_level_db; p.min_level_db = mc->min_level_db; p.max_abs = mc->max_abs_value;
     p.out = out_dev;
-    const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 4 + 16;
+    const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 8 + 16;    // FFT buffer + two magnitude spectra
     if (cudaFuncSetAttribute(wn_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");

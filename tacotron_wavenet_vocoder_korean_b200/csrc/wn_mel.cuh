@@ -26,30 +26,39 @@ struct WnMelParams {
     float *out;                // [rows][frames][n_mels]
 };
 
+// Two frames per FFT: frames f and f+1 of a row are the real and imaginary parts of one complex 2048-point transform,
+// z = x1 + i*x2  ->  X1[k] = (Z[k] + conj(Z[N-k])) / 2,  X2[k] = (Z[k] - conj(Z[N-k])) / (2i)  (exact up to fp64 rounding),
+// which halves the butterfly work and the number of block barriers per frame.
 extern "C" __global__ void __launch_bounds__(256) wn_mel_kernel(const WnMelParams p)
 {
     extern __shared__ __align__(16) unsigned char mel_smem[];
     double2 *buf = reinterpret_cast<double2 *>(mel_smem);                  // [n_fft]
-    float *mag = reinterpret_cast<float *>(buf + p.n_fft);                 // [n_bins]
+    float *mag = reinterpret_cast<float *>(buf + p.n_fft);                 // [2][n_bins]
     const int tid = threadIdx.x;
     const int nth = blockDim.x;
-    for (long long item = blockIdx.x; item < (long long)p.rows * p.frames; item += gridDim.x) {
-        const int row = (int)(item / p.frames), f = (int)(item % p.frames);
+    const int pairs = (p.frames + 1) / 2;
+    for (long long item = blockIdx.x; item < (long long)p.rows * pairs; item += gridDim.x) {
+        const int row = (int)(item / pairs), f0 = 2 * (int)(item % pairs);
+        const bool two = f0 + 1 < p.frames;
         const float *x = p.wav + (size_t)row * p.n;
-        // 1. windowed, pre-emphasised, reflect-padded frame, stored in bit-reversed order
+        // 1. windowed, pre-emphasised, reflect-padded frames, stored in bit-reversed order
         for (int i = tid; i < p.n_fft; i += nth) {
-            double v = 0.0;
+            double v[2] = {0.0, 0.0};
             const int wi = i - p.win_off;
             if (wi >= 0 && wi < p.win) {
-                long long q = (long long)f * p.hop + i - p.n_fft / 2;
-                if (q < 0) q = -q;
-                if (q >= p.n) q = 2 * (p.n - 1) - q;
-                double y = (double)x[q];
-                if (p.preemph != 0.0 && q > 0) y = __dadd_rn(y, __dmul_rn(-p.preemph, (double)x[q - 1]));
-                v = __dmul_rn(p.window[wi], y);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !two) break;
+                    long long q = (long long)(f0 + u) * p.hop + i - p.n_fft / 2;
+                    if (q < 0) q = -q;
+                    if (q >= p.n) q = 2 * (p.n - 1) - q;
+                    double y = (double)x[q];
+                    if (p.preemph != 0.0 && q > 0) y = __dadd_rn(y, __dmul_rn(-p.preemph, (double)x[q - 1]));
+                    v[u] = __dmul_rn(p.window[wi], y);
+                }
             }
             const unsigned r = __brev((unsigned)i) >> (32 - p.log2n);
-            buf[r] = make_double2(v, 0.0);
+            buf[r] = make_double2(v[0], v[1]);
         }
         __syncthreads();
         // 2. radix-2 decimation-in-time FFT, fp64
@@ -67,22 +76,27 @@ extern "C" __global__ void __launch_bounds__(256) wn_mel_kernel(const WnMelParam
             }
             __syncthreads();
         }
-        // 3. |D| with the components rounded to fp32 first (complex64), np.abs -> hypot
+        // 3. split the two spectra; |D| with the components rounded to fp32 first (complex64), np.abs -> hypot
         for (int k = tid; k < p.n_bins; k += nth) {
-            const double re = (double)(float)buf[k].x, im = (double)(float)buf[k].y;
-            mag[k] = (float)sqrt(re * re + im * im);
+            const double2 zk = buf[k], zn = buf[(p.n_fft - k) & (p.n_fft - 1)];
+            const double re1 = (double)(float)(0.5 * (zk.x + zn.x)), im1 = (double)(float)(0.5 * (zk.y - zn.y));
+            const double re2 = (double)(float)(0.5 * (zk.y + zn.y)), im2 = (double)(float)(0.5 * (zn.x - zk.x));
+            mag[k] = (float)sqrt(re1 * re1 + im1 * im1);
+            mag[p.n_bins + k] = (float)sqrt(re2 * re2 + im2 * im2);
         }
         __syncthreads();
         // 4. mel filterbank (sparse triangles), dB, reference level, symmetric normalisation + clip; all fp32
-        if (tid < p.n_mels) {
-            const float *w = p.mel_w + p.mel_off[tid];
-            const float *m = mag + p.mel_start[tid];
+        for (int o = tid; o < 2 * p.n_mels; o += nth) {
+            const int u = o / p.n_mels, c = o - u * p.n_mels;
+            if (u == 1 && !two) continue;
+            const float *w = p.mel_w + p.mel_off[c];
+            const float *m = mag + u * p.n_bins + p.mel_start[c];
             float acc = 0.0f;
-            for (int j = 0; j < p.mel_len[tid]; ++j) acc = __fmaf_rn(w[j], m[j], acc);
+            for (int j = 0; j < p.mel_len[c]; ++j) acc = __fmaf_rn(w[j], m[j], acc);
             float S = __fsub_rn(__fmul_rn(20.0f, log10f(fmaxf(p.min_level, acc))), p.ref_level_db);
             float v = __fsub_rn(__fmul_rn(2.0f * p.max_abs, __fdiv_rn(__fsub_rn(S, p.min_level_db), -p.min_level_db)), p.max_abs);
             v = fminf(fmaxf(v, -p.max_abs), p.max_abs);
-            p.out[((size_t)row * p.frames + f) * p.n_mels + tid] = v;
+            p.out[((size_t)row * p.frames + f0 + u) * p.n_mels + c] = v;
         }
         __syncthreads();
     }
