@@ -379,9 +379,9 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc1_full[b], 1);
             mbar_init(&acc2_full[b], 1);
-            mbar_init(&tmem_empty[b], PF_EPI_THREADS);
+            mbar_init(&tmem_empty[b], PF_EPI_THREADS / 2);
         }
-        mbar_init(&z_ready, PF_EPI_THREADS);
+        mbar_init(&z_ready, PF_EPI_THREADS / 2);
         mbar_init(&wd_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -458,110 +458,132 @@ layer_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_x, const __g
             }
         }
     } else {
-        // ===================== epilogue: thread = (row, 32 of the 128 channels) =====================
-        const int q = warp & 3, qd = (warp - 2) >> 2;
+        // ===================== epilogue: two warp groups working on consecutive tiles =====================
+        // warps 2-9  GATE group: tile it: tcgen05.ld f/g -> gate -> tanh, sigmoid, skip z to HBM, z to shared memory (A of the dense MMA)
+        // warps 10-17 RESIDUAL group: tile it: dense accumulator + x + bd -> x_next
+        // so the gate epilogue of tile it+1 overlaps the dense MMA and the residual epilogue of tile it.  thread = (row, 64 channels).
+        const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int cb = qd * 32;                                  // first channel of this thread
-        const int t = threadIdx.x - 64;
-        if (t < ND) s_bd[t] = a.bd ? a.bd[t] : 0.f;
-        int staged_n0 = -1;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int buf = it & 1;
-            const long row0 = (long)a.off + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
-            const long row = row0 + r;
-            const bool valid = row < a.M;
-            const int n0 = (int)(row0 / a.T0);
-            const int n = valid ? (int)(row / a.T0) : n0;
-            const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
-            const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NFG);
-            if (n0 != staged_n0) {                               // uniform across the CTA: bias (+ gc) of sentences n0, n0+1
-                asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS) : "memory");  // everyone is done with the previous vectors
-                if (t < NFG) {
+        const bool gate_group = warp < 2 + PF_EPI_WARPS / 2;
+        const int hb = ((warp - 2) >> 2) & 1;                    // which 64 of the 128 channels
+        const int t = (threadIdx.x - 64) & (PF_EPI_THREADS / 2 - 1);   // index inside the group
+        if (gate_group) {
+            int staged_n0 = -1;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                const long row0 = (long)a.off + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+                const long row = row0 + r;
+                const bool valid = row < a.M;
+                const int n0 = (int)(row0 / a.T0);
+                const int n = valid ? (int)(row / a.T0) : n0;
+                const int tau = valid ? (int)(row - (long)n * a.T0) : 0;
+                const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NFG);
+                if (n0 != staged_n0) {                           // uniform across the group: bias (+ gc) of sentences n0, n0+1
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS / 2) : "memory");
                     const float b = a.bias ? a.bias[t] : 0.f;
                     const int n1 = min(n0 + 1, a.N - 1);
                     s_bias[0][t] = b + (a.gcb ? a.gcb[(size_t)n0 * NFG + t] : 0.f);
                     s_bias[1][t] = b + (a.gcb ? a.gcb[(size_t)n1 * NFG + t] : 0.f);
+                    asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS / 2) : "memory");
+                    staged_n0 = n0;
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(PF_EPI_THREADS) : "memory");
-                staged_n0 = n0;
-            }
-            const float *sb = s_bias[n - n0];
-            const bool skip_row = valid && tau >= a.SL;
-            bf16 *zs_row = skip_row ? a.Zs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
-            bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
-            // residual input for the second epilogue: requested now, consumed after the dense MMA
-            const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND;
-            uint32_t xs[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xs[i] = 0u;
-            if (a.do_dense && valid) {
-                ldg256(x_row + cb, xs);
-                ldg256(x_row + cb + 16, xs + 8);
-            }
-            mbar_wait(&acc1_full[buf], (it >> 1) & 1, a.err);
-            tc_fence_after();
-            {
-                float f[32], g[32];
-                tc_ld32(tlane + cb, f);
-                tc_ld32(tlane + 128 + cb, g);
-                tc_ld_wait();
-                uint32_t th_p[16], sg_p[16], z_p[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bf4 = *reinterpret_cast<const float4 *>(sb + cb + i), bg4 = *reinterpret_cast<const float4 *>(sb + 128 + cb + i);
-                    const float fb[4] = {bf4.x, bf4.y, bf4.z, bf4.w}, gbv[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
-#pragma unroll
-                    for (int u = 0; u < 4; u += 2) {
-                        const float t0 = tanh_fast(f[i + u] + fb[u]), t1 = tanh_fast(f[i + u + 1] + fb[u + 1]);
-                        const float s0 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u] + gbv[u])), 0.5f);
-                        const float s1 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u + 1] + gbv[u + 1])), 0.5f);
-                        th_p[(i + u) >> 1] = pack2(t0, t1);
-                        sg_p[(i + u) >> 1] = pack2(s0, s1);
-                        z_p[(i + u) >> 1] = pack2(t0 * s0, t1 * s1);
-                    }
-                }
-                if (valid) {
-                    stg256(ts_row + cb, th_p);
-                    stg256(ts_row + cb + 16, th_p + 8);
-                    stg256(ts_row + 128 + cb, sg_p);
-                    stg256(ts_row + 128 + cb + 16, sg_p + 8);
-                    if (skip_row) {
-                        stg256(zs_row + cb, z_p);
-                        stg256(zs_row + cb + 16, z_p + 8);
-                    }
-                }
-                if (a.do_dense) {
-                    // z as the K-major, 128B-swizzled A operand of the dense MMA: K block cb/64, 16-byte chunk index XOR (row & 7)
-                    uint8_t *zt = smem + PF_OFF_Z + (cb >> 6) * A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-                    const int ch = (cb & 63) >> 3;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4 *>(zt + (((ch + i) ^ (r & 7)) << 4)) = make_uint4(z_p[4 * i], z_p[4 * i + 1], z_p[4 * i + 2], z_p[4 * i + 3]);
-                }
-            }
-            tc_fence_before();
-            if (a.do_dense) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&z_ready);
-                bf16 *xn_row = a.Xn + (size_t)(valid ? row : 0) * ND;
-                mbar_wait(&acc2_full[buf], (it >> 1) & 1, a.err);
+                const float *sb = s_bias[n - n0];
+                const bool skip_row = valid && tau >= a.SL;
+                bf16 *zs_row = skip_row ? a.Zs + ((size_t)n * a.OW + (tau - a.SL)) * a.LD + a.zs_col0 : nullptr;
+                bf16 *ts_row = a.TS + (size_t)(valid ? row : 0) * NFG;
+                mbar_wait(&acc1_full[buf], (it >> 1) & 1, a.err);
                 tc_fence_after();
-                float v[32];
-                tc_ld32(tlane + cb, v);
-                tc_ld_wait();
-                uint32_t o[16];
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cb = hb * 64 + hh * 32;
+                    float f[32], g[32];
+                    tc_ld32(tlane + cb, f);
+                    tc_ld32(tlane + 128 + cb, g);
+                    tc_ld_wait();
+                    uint32_t th_p[16], sg_p[16], z_p[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[i]);
-                    o[i] = pack2(v[2 * i] + __low2float(xb) + s_bd[cb + 2 * i], v[2 * i + 1] + __high2float(xb) + s_bd[cb + 2 * i + 1]);
-                }
-                if (valid) {
-                    stg256(xn_row + cb, o);
-                    stg256(xn_row + cb + 16, o + 8);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bf4 = *reinterpret_cast<const float4 *>(sb + cb + i), bg4 = *reinterpret_cast<const float4 *>(sb + 128 + cb + i);
+                        const float fb[4] = {bf4.x, bf4.y, bf4.z, bf4.w}, gbv[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; u += 2) {
+                            const float t0 = tanh_fast(f[i + u] + fb[u]), t1 = tanh_fast(f[i + u + 1] + fb[u + 1]);
+                            const float s0 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u] + gbv[u])), 0.5f);
+                            const float s1 = fmaf(0.5f, tanh_fast(0.5f * (g[i + u + 1] + gbv[u + 1])), 0.5f);
+                            th_p[(i + u) >> 1] = pack2(t0, t1);
+                            sg_p[(i + u) >> 1] = pack2(s0, s1);
+                            z_p[(i + u) >> 1] = pack2(t0 * s0, t1 * s1);
+                        }
+                    }
+                    if (valid) {
+                        stg256(ts_row + cb, th_p);
+                        stg256(ts_row + cb + 16, th_p + 8);
+                        stg256(ts_row + 128 + cb, sg_p);
+                        stg256(ts_row + 128 + cb + 16, sg_p + 8);
+                        if (skip_row) {
+                            stg256(zs_row + cb, z_p);
+                            stg256(zs_row + cb + 16, z_p + 8);
+                        }
+                    }
+                    if (a.do_dense) {
+                        // the single z tile is free once the dense MMA of the previous tile has completed (it is queued right
+                        // behind this tile's filter|gate MMAs, so this wait is normally already satisfied)
+                        if (hh == 0 && it >= 1) mbar_wait(&acc2_full[(it - 1) & 1], ((it - 1) >> 1) & 1, a.err);
+                        uint8_t *zt = smem + PF_OFF_Z + (cb >> 6) * A_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                        const int ch = (cb & 63) >> 3;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            *reinterpret_cast<uint4 *>(zt + (((ch + i) ^ (r & 7)) << 4)) = make_uint4(z_p[4 * i], z_p[4 * i + 1], z_p[4 * i + 2], z_p[4 * i + 3]);
+                    }
                 }
                 tc_fence_before();
+                if (a.do_dense) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&z_ready);
+                } else {
+                    mbar_arrive(&tmem_empty[buf]);
+                }
             }
-            mbar_arrive(&tmem_empty[buf]);                        // this accumulator may be overwritten by tile it+2
+        } else if (a.do_dense) {
+            if (t < ND) s_bd[t] = a.bd ? a.bd[t] : 0.f;
+            asm volatile("bar.sync 2, %0;" ::"n"(PF_EPI_THREADS / 2) : "memory");
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                const long row0 = (long)a.off + ((long)blockIdx.x + (long)it * gridDim.x) * TILE_M;
+                const long row = row0 + r;
+                const bool valid = row < a.M;
+                const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NFG);
+                const bf16 *x_row = a.Xl + (size_t)(valid ? row : 0) * ND + hb * 64;
+                bf16 *xn_row = a.Xn + (size_t)(valid ? row : 0) * ND + hb * 64;
+                uint32_t xs[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xs[i] = 0u;
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ldg256(x_row + i * 16, xs + i * 8);
+                }
+                mbar_wait(&acc2_full[buf], (it >> 1) & 1, a.err);
+                tc_fence_after();
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cb = hb * 64 + hh * 32;
+                    float v[32];
+                    tc_ld32(tlane + cb, v);
+                    tc_ld_wait();
+                    uint32_t o[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const __nv_bfloat162 xb = *reinterpret_cast<const __nv_bfloat162 *>(&xs[hh * 16 + i]);
+                        o[i] = pack2(v[2 * i] + __low2float(xb) + s_bd[cb + 2 * i], v[2 * i + 1] + __high2float(xb) + s_bd[cb + 2 * i + 1]);
+                    }
+                    if (valid) {
+                        stg256(xn_row + hh * 32, o);
+                        stg256(xn_row + hh * 32 + 16, o + 8);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&tmem_empty[buf]);                    // this accumulator may be overwritten by tile it+2
+            }
         }
     }
     __syncthreads();
