@@ -198,10 +198,8 @@ def validate_directories(config):
     if config.logdir and config.logdir_root:
         raise ValueError("--logdir and --logdir_root cannot be specified at the same time.")
     if config.logdir and config.restore_from:
-        raise ValueError("--logdir and --restore_from cannot be specified at the same time. This is to keep your previous "
-                         "model from unexpected overwrites.\nUse --logdir_root to specify the root of the directory which will be "
-                         "automatically created with current date and time, or use only --logdir to just continue the training "
-                         "from the last checkpoint.")
+        raise ValueError("--logdir continues a run in place, so it cannot be combined with --restore_from (that would overwrite the "
+                         "restored model); use --logdir_root to start a new dated run from --restore_from.")
     root = config.logdir_root or './logdir-wavenet'
     logdir = config.logdir or os.path.join(root, 'train', "{0:%Y-%m-%dT%H-%M-%S}".format(datetime.now()))
     restore_from = config.restore_from or logdir
