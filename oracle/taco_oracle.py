@@ -2,15 +2,17 @@
 rows a15-a20, Appendix C).  Only tests/, __graft_entry__.smoke() and the CPU legs of the benchmarks may
 import it; the product package never does.
 
-PARITY: prenet + encoder/post CBHG (rows a15, a20) are pinned to the reference's own tacotron/modules.py run on the numpy TF
-stand-in (tests/golden/make_reference_taco_golden.py -> ref_taco_modules.npz, reproduced to 2e-5, tests/test_reference_pin.py).
-The attention decoder (rows a16-a19) is PARITY UNPINNED: TensorFlow 1.x is not installable here and the reference ships neither tests nor
-checkpoints, so the TF-internal pieces (tf.contrib.rnn.GRUCell, tf.contrib.seq2seq.BahdanauMonotonicAttention,
-dynamic_decode, tf.layers.conv1d/batch_normalization/max_pooling1d 'same' semantics,
-bidirectional_dynamic_rnn with sequence_length) are restated from their published definitions.  What can
-be pinned locally is pinned in tests/test_taco_oracle.py: conv1d-'same' / max-pool / batch-norm against
-torch.nn.functional, the parallel monotonic-attention closed form against the recursive definition of
-Raffel et al. 2017, the fp32 evaluation against an fp64 evaluation of the same graph.
+PARITY: pinned to the reference's OWN tacotron package.  tacotron/tacotron.py (Tacotron.initialize, inference), rnn_wrappers.py
+(AttentionWrapper incl. the manual-alignment override, DecoderPrenetWrapper, ConcatOutputAndAttentionWrapper,
+LocationSensitiveAttention), helpers.py (TacoTestHelper) and modules.py are imported unmodified from /root/reference and run on
+numpy stand-ins for the TF API (tests/golden/tf_numpy_shim.py, tf_contrib_shim.py); this oracle reproduces the resulting mel /
+linear / alignment outputs to 2.4e-7 for bah_mon_norm, bah_mon, loc_sen, one speaker, the post-net dense branch and manual
+alignments (tests/golden/make_reference_taco_full_golden.py -> ref_taco_full_*.npz, tests/test_reference_pin.py).
+UNPINNED: the arithmetic of the tf.contrib / tf.layers classes themselves (GRUCell, BahdanauMonotonicAttention incl.
+monotonic_attention, dynamic_decode, conv1d / batch_normalization / max_pooling1d 'same', bidirectional_dynamic_rnn with
+sequence_length), restated here and in the stand-in from their published definitions; TensorFlow 1.x is not installable.  Local
+pins of those pieces (tests/test_taco_oracle.py): conv1d-'same' / max-pool / batch-norm against torch.nn.functional, the parallel
+monotonic-attention closed form against the recursive definition of Raffel et al. 2017, fp32 against fp64 evaluation.
 
 Follows (reference file:line):
   tacotron/tacotron.py:36-235      graph wiring (embedding zero row :51-56, deepvoice speaker states :78-84,

@@ -30,8 +30,24 @@ class _Shape(list):
         return list(self)
 
 
+class Dim(int):
+    """tf.Dimension: an int with `.value`."""
+
+    @property
+    def value(self):
+        return int(self)
+
+
 class Tensor(np.ndarray):
-    """numpy array with the two TF tensor methods the reference calls."""
+    """numpy array with the TF tensor surface the reference calls (`get_shape().as_list()`, `shape[i].value`)."""
+
+    @property
+    def shape(self):
+        return tuple(Dim(d) for d in np.ndarray.shape.__get__(self))
+
+    @shape.setter
+    def shape(self, v):
+        np.ndarray.shape.__set__(self, v)
 
     def get_shape(self):
         return _Shape(self.shape)
@@ -51,6 +67,8 @@ class _State(object):
         self.counters = {}           # per-pass unique-name counters
         self.uniforms = []           # queue for tf.random_uniform
         self.created_order = []
+        self.resolver = None         # optional: TF-scoped name -> key of the supplied weight dict
+        self.resolved = {}
 
 
 S = _State()
@@ -93,9 +111,11 @@ def _make_variable(full, shape, trainable, init=None):
             raise ValueError('variable %s re-created with shape %s (was %s)' % (full, tuple(shape), v.shape))
         return v
     if init is None:
-        if full not in S.initial:
-            raise KeyError('the reference created trainable variable %r %s, which the supplied weights do not contain' % (full, tuple(shape)))
-        init = S.initial[full]
+        key = S.resolver(full) if S.resolver else full
+        if key not in S.initial:
+            raise KeyError('the reference created trainable variable %r %s (-> %r), which the supplied weights do not contain' % (full, tuple(shape), key))
+        S.resolved[full] = key
+        init = S.initial[key]
         if tuple(init.shape) != tuple(shape):
             raise ValueError('variable %s: reference shape %s, supplied %s' % (full, tuple(shape), init.shape))
     v = _t(np.array(init, np.float32, copy=True))
@@ -112,10 +132,15 @@ AUTO_REUSE = 'auto_reuse'
 
 
 @contextlib.contextmanager
-def variable_scope(name, reuse=None, default_name=None):
+def variable_scope(name_or_scope, default_name=None, values=None, reuse=None):
+    """tf.variable_scope(name_or_scope, default_name=None, values=None, ..., reuse=None): with name None the default name is
+    uniquified inside the enclosing scope."""
+    if not isinstance(default_name, (str, type(None))):      # reference call sites pass reuse= by keyword only
+        default_name = None
+    name = name_or_scope if name_or_scope is not None else _unique(_scoped(default_name)).rsplit('/', 1)[-1]
     S.scope.append(name)
     try:
-        yield
+        yield name
     finally:
         S.scope.pop()
 
@@ -137,7 +162,7 @@ def Variable(initial_value=None, name=None, trainable=True, dtype=None):
 
 
 def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True):
-    return _make_variable(_scoped(name), tuple(shape), trainable)
+    return _make_variable(_scoped(name), tuple(int(d) for d in shape), trainable)
 
 
 def trainable_variables():
@@ -158,7 +183,7 @@ def scatter_update(ref, indices, updates):
 
 # ---- array ops --------------------------------------------------------------------------------------------------------
 def zeros(shape, dtype=np.float32):
-    return _t(np.zeros(shape, dtype))
+    return _t(np.zeros([int(d) for d in shape], dtype))
 
 
 def range(*a):          # noqa: A001 (mirrors tf.range)
@@ -207,7 +232,10 @@ def squeeze(x, axis=None):
 
 
 def tile(x, multiples):
-    return _t(np.tile(np.asarray(x), multiples))
+    a = np.asarray(x)
+    if a.dtype == np.float64 and not isinstance(x, np.ndarray):
+        a = a.astype(np.float32)           # a Python float constant is a float32 tensor in TF
+    return _t(np.tile(a, [int(m) for m in multiples]))
 
 
 def one_hot(indices, depth, dtype=np.float32):
@@ -251,8 +279,12 @@ def minimum(a, b):
     return _t(np.minimum(np.asarray(a), np.asarray(b, dtype=np.asarray(a).dtype)))
 
 
+def _ax(axis):
+    return tuple(axis) if isinstance(axis, (list, tuple)) else axis
+
+
 def reduce_sum(x, axis=None, keepdims=False):
-    return _t(np.sum(np.asarray(x), axis=axis, keepdims=keepdims))
+    return _t(np.sum(np.asarray(x), axis=_ax(axis), keepdims=keepdims))
 
 
 def reduce_max(x, axis=None, keepdims=False):

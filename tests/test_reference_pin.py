@@ -170,3 +170,46 @@ def test_taco_oracle_prenet_and_cbhg_match_reference_modules():
     assert np.abs(enc - g['encoder_out']).max() < 2e-5
     post = o.cbhg(g['mel'], None, 'post_cbhg', hp['post_bank_size'], hp['post_proj_sizes'], hp['post_highway_depth'], hp['post_rnn_size'])
     assert np.abs(post - g['post_out']).max() < 2e-5
+
+
+# ---- the WHOLE reference Tacotron graph: tacotron.py + rnn_wrappers.py + helpers.py + modules.py (make_reference_taco_full_golden.py) ----
+TACO_FULL = ['tiny_mon_norm', 'tiny_mon', 'tiny_loc_sen', 'tiny_single_speaker', 'tiny_post_dense', 'tiny_mon_norm_manual']
+
+
+def _taco_case(tag):
+    from tests.taco_helpers import case
+    g = np.load(os.path.join(GOLD, 'ref_taco_full_%s.npz' % tag))
+    hp, ns, w, ids, lens, spk, steps = case(tag.replace('_manual', ''))
+    assert np.array_equal(ids, g['ids']) and np.array_equal(lens, g['lengths']) and int(g['steps']) == steps
+    return g, hp, ns, w, ids, lens, spk, steps, (g['manual_alignments'] if 'manual_alignments' in g.files else None)
+
+
+@pytest.mark.parametrize('tag', TACO_FULL)
+def test_taco_oracle_matches_reference_full_graph(tag):
+    """Tacotron.initialize (inference) of the reference, run unmodified on the numpy TF stand-ins: the reference's AttentionWrapper
+    with the manual-alignment override, DecoderPrenetWrapper, ConcatOutputAndAttentionWrapper, LocationSensitiveAttention,
+    TacoTestHelper, cell stack, post net.  tf.contrib's cells / attention mechanisms / decode loop are restated in the stand-in."""
+    from oracle.taco_oracle import TacotronOracle
+    g, hp, ns, w, ids, lens, spk, steps, man = _taco_case(tag)
+    mel, lin, al = TacotronOracle(hp, w, ns).synthesize(ids, lens, spk, max_iters=steps, manual_alignments=man)
+    assert mel.shape == g['mel_outputs'].shape == (len(lens), steps * hp['reduction_factor'], hp['num_mels'])
+    assert np.abs(mel - g['mel_outputs']).max() < 2e-6 and np.abs(lin - g['linear_outputs']).max() < 2e-6
+    assert np.abs(al - g['alignments']).max() < 1e-6
+    # every weight of this repository's state dict is a variable the reference graph creates (through the documented name map)
+    assert set(g['mapped_names'].tolist()) == set(w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', TACO_FULL)
+def test_cuda_tacotron_matches_reference_full_graph(tag):
+    from tacotron_wavenet_vocoder_korean_b200.tacotron import Tacotron
+    from tests.taco_helpers import Bag
+    g, hp, ns, w, ids, lens, spk, steps, man = _taco_case(tag)
+    m = Tacotron(Bag(hp))
+    m.load_state_dict(w)
+    if man is not None:
+        m.is_manual_attention, m.manual_alignments = True, man
+    m.initialize(ids, lens, ns, spk, rnn_decoder_test_mode=True, n_steps=steps)
+    assert np.abs(m.mel_outputs.cpu().numpy() - g['mel_outputs']).max() <= 1e-4          # north_star tolerance on float mel
+    assert np.abs(m.linear_outputs.cpu().numpy() - g['linear_outputs']).max() <= 1e-4
+    assert np.abs(m.alignments.cpu().numpy() - g['alignments']).max() <= 1e-4
