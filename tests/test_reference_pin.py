@@ -213,3 +213,24 @@ def test_cuda_tacotron_matches_reference_full_graph(tag):
     assert np.abs(m.mel_outputs.cpu().numpy() - g['mel_outputs']).max() <= 1e-4          # north_star tolerance on float mel
     assert np.abs(m.linear_outputs.cpu().numpy() - g['linear_outputs']).max() <= 1e-4
     assert np.abs(m.alignments.cpu().numpy() - g['alignments']).max() <= 1e-4
+
+
+# ---- text/korean.py of the reference (tests/golden/make_reference_text_golden.py) ------------------------------------------------
+def test_korean_tokeniser_matches_reference_on_its_shipped_transcripts():
+    """normalize + tokenize of the reference's own text/korean.py on the 160 transcripts it ships and on number / unit / letter
+    cases (jamo package restated by Unicode arithmetic).  Without text/ko_dictionary.py's replacement tables installed, the
+    tokeniser here must equal the reference run with those tables emptied; sentences the reference itself rejects are skipped."""
+    import json
+    from tacotron_wavenet_vocoder_korean_b200.text import korean as mk, text_to_sequence
+    g = json.load(open(os.path.join(GOLD, 'ref_text.json'), encoding='utf-8'))
+    assert g['symbols']['all_symbols'] == mk.ALL_SYMBOLS and g['symbols']['pad'] == mk.PAD and g['symbols']['eos'] == mk.EOS
+    cases = [c for c in g['cases'] if 'error' not in c]
+    assert len(cases) >= 180
+    same_as_full = 0
+    for c in cases:
+        ids = list(mk.tokenize(c['text'], as_id=True))
+        assert ids == c['ids_without_dictionaries'], c['text']
+        if '~' not in c['normalized'] and '_' not in c['normalized']:     # text/__init__.py:_should_keep_symbol drops PAD / EOS characters
+            assert list(text_to_sequence(c['text'])) == ids
+        same_as_full += ids == c['ids']
+    assert same_as_full >= len(cases) - 4          # only the few sentences that hit a dictionary entry (e.g. 'TV') differ
