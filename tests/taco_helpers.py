@@ -35,7 +35,20 @@ CASES = {
 }
 
 
+# the reference's hparams.py:124-166 layer sizes (7.07 M parameters) on short inputs
+FULL_CASES = {
+    'full_mon_norm': (dict(), 2, 2, 14, 6, 21),
+    'full_loc_sen': (dict(attention_type='loc_sen'), 2, 2, 12, 5, 22),
+}
+
+
 def case(name):
+    if name in FULL_CASES:
+        over, ns, N, T_in, steps, seed = FULL_CASES[name]
+        hp = dict(synth.TACO_HP, **over)
+        w = synth.make_taco_weights(hp, ns)
+        ids, lens, spk = make_batch(N, T_in, hp['num_symbols'], seed=seed)
+        return hp, ns, w, ids, lens, spk, steps
     over, ns, N, T_in, steps = CASES[name]
     hp = synth.taco_tiny(**over)
     w = synth.make_taco_weights(hp, ns, seed=4321)
