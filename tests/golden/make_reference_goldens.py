@@ -10,6 +10,7 @@ Cases (seeded inputs = tests/helpers.make_inputs, weights = synth.make_weights, 
               sample_from_discretized_mix_logistic) and the drawn sample under teacher forcing, for 64 steps;
               create_upsample output; calculate_receptive_field.
   ref_mulaw   tiny mu-law model with mel + speaker conditioning: per-step softmax probabilities (predict_proba_incremental).
+  ref_cfg2    the benchmark configuration (BASELINE configs[1] layer sizes), 2 rows x 48 teacher-forced steps.
   ref_train   add_loss (train mode) of the tiny training model: the scalar loss the reference graph evaluates, with and
               without L2, and mu_law_encode / mu_law_decode of an amplitude grid (wavenet/ops.py).
 """
@@ -103,9 +104,14 @@ def main():
     kw = dict(synth.tiny_mulaw(), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8, global_condition_cardinality=3)
     np.savez_compressed(os.path.join(HERE, 'ref_mulaw.npz'), **incremental_case(kw, 48))
     np.savez_compressed(os.path.join(HERE, 'ref_train.npz'), **train_case_loss(synth.tiny_train(3), 96))
+    # BASELINE configs[1] layer sizes (30 layers, R=D=128, S=512, MoL-10, 80-channel mel, 2 speakers), 2 rows x 48 steps
+    g = incremental_case(synth.cfg2(2), 48)
+    g['lc_up'] = g['lc_up'][:, :48]
+    del g['variable_names']
+    np.savez_compressed(os.path.join(HERE, 'ref_cfg2.npz'), **g)
     rf = [ref_wavenet.WaveNetModel.calculate_receptive_field(2, [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 5, s, 32) for s in (False, True)]
     print('receptive fields (non-scalar, scalar, 50 layers):', rf)
-    for f in ('ref_mol', 'ref_mulaw', 'ref_train'):
+    for f in ('ref_mol', 'ref_mulaw', 'ref_train', 'ref_cfg2'):
         g = np.load(os.path.join(HERE, f + '.npz'))
         print(f, {k: g[k].shape for k in g.files})
 

@@ -236,3 +236,31 @@ def test_korean_tokeniser_matches_reference_on_its_shipped_transcripts():
             assert list(text_to_sequence(c['text'])) == ids
         same_as_full += ids == c['ids']
     assert same_as_full >= len(cases) - 4          # only the few sentences that hit a dictionary entry (e.g. 'TV') differ
+
+
+# ---- the benchmark configuration (BASELINE configs[1] layer sizes) through the reference's own wavenet/model.py -----------------
+def test_oracle_matches_reference_at_cfg2_sizes():
+    g = np.load(os.path.join(GOLD, 'ref_cfg2.npz'))
+    kw = synth.cfg2(2)
+    om = oracle_model(kw, synth.make_weights(**kw))
+    T = g['outputs'].shape[1]
+    inp = make_inputs(kw, T)
+    lc = om.upsample(inp['mel'])[:, :T]
+    np.testing.assert_allclose(lc, g['lc_up'], atol=3e-6)
+    s, lg = om.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.abs(lg - g['raw_output']).max() < 5e-5 and np.abs(s - g['outputs'][:, :, 0]).max() < 5e-5
+    assert int(g['receptive_field']) == 3101 and len(g['queue_names']) == 32          # causal + lc + 30 dilation queues
+
+
+@pytest.mark.gpu
+def test_cuda_generation_matches_reference_at_cfg2_sizes():
+    from tacotron_wavenet_vocoder_korean_b200.wavenet import WaveNetModel
+    g = np.load(os.path.join(GOLD, 'ref_cfg2.npz'))
+    kw = synth.cfg2(2)
+    net = WaveNetModel(train_mode=False, **kw)
+    net.load_state_dict(synth.make_weights(**kw))
+    T = g['outputs'].shape[1]
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    s, lg = net.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    assert np.abs(lg.cpu().numpy() - g['raw_output']).max() < 1e-4 and np.abs(s.cpu().numpy() - g['outputs'][:, :, 0]).max() < 1e-4
