@@ -84,7 +84,7 @@ def incremental_case(kw, T):
     return res
 
 
-def train_case_loss(kw, T):
+def train_case_loss(kw, T, codec=True):
     out = {}
     w, wav, mel, gc = train_case(kw, T)
     for tag, l2 in (('loss', None), ('loss_l2', 0.01)):
@@ -92,6 +92,8 @@ def train_case_loss(kw, T):
         with tf.graph_pass():
             net.add_loss(input_batch=wav[:, :, None], local_condition=mel, global_condition_batch=gc, l2_regularization_strength=l2)
         out[tag] = np.float64(net.loss)
+    if not codec:
+        return out
     grid = np.linspace(-1.2, 1.2, 4001).astype(np.float32)
     enc = np.array(ref_wavenet.mu_law_encode(grid, 256))
     out.update(mu_grid=grid, mu_encoded=enc.astype(np.int32), mu_decoded=np.array(ref_wavenet.mu_law_decode(np.arange(256, dtype=np.int32), 256)).astype(np.float32))
@@ -104,6 +106,7 @@ def main():
     kw = dict(synth.tiny_mulaw(), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8, global_condition_cardinality=3)
     np.savez_compressed(os.path.join(HERE, 'ref_mulaw.npz'), **incremental_case(kw, 48))
     np.savez_compressed(os.path.join(HERE, 'ref_train.npz'), **train_case_loss(synth.tiny_train(3), 96))
+    np.savez_compressed(os.path.join(HERE, 'ref_train_cfg2.npz'), **train_case_loss(synth.cfg2(2), 3600, codec=False))   # BASELINE configs[3] layers
     # BASELINE configs[1] layer sizes (30 layers, R=D=128, S=512, MoL-10, 80-channel mel, 2 speakers), 2 rows x 48 steps
     g = incremental_case(synth.cfg2(2), 48)
     g['lc_up'] = g['lc_up'][:, :48]

@@ -74,6 +74,17 @@ def test_training_loss_and_mu_law_match_reference_graph():
     np.testing.assert_allclose(oracle.mu_law_decode(np.arange(256, dtype=np.float32), 256), g['mu_decoded'], atol=1e-6)
 
 
+def test_training_loss_matches_reference_graph_at_reference_layer_sizes():
+    """add_loss of the reference at the BASELINE configs[3] layer sizes (30 layers, R = D = 128, S = 512), 2 crops x 3600 samples:
+    the input of tests/test_train_gpu.py::test_fp32_reference_layer_sizes_match_oracle, so the CUDA step is tied to it too."""
+    g = np.load(os.path.join(GOLD, 'ref_train_cfg2.npz'))
+    kw = synth.cfg2(2)
+    w, wav, mel, gc = train_case(kw, 3600)
+    m = to.TorchWaveNetTrain(w, **kw)
+    assert abs(float(m.loss(wav, mel, gc).detach()) - float(g['loss'])) < 2e-5 * abs(float(g['loss']))
+    assert abs(float(m.loss(wav, mel, gc, 0.01).detach()) - float(g['loss_l2'])) < 2e-5 * abs(float(g['loss_l2']))
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
