@@ -275,3 +275,16 @@ def test_cuda_generation_matches_reference_at_cfg2_sizes():
     lc = net.create_upsample(inp['mel'])
     s, lg = net.generate(T, inp['forced_full'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
     assert np.abs(lg.cpu().numpy() - g['raw_output']).max() < 1e-4 and np.abs(s.cpu().numpy() - g['outputs'][:, :, 0]).max() < 1e-4
+
+
+# ---- utils/__init__.py helpers on the drop-in boundary (tests/golden/make_reference_utils_golden.py) -----------------------------
+def test_load_json_and_load_hparams_match_reference(tmp_path, capsys):
+    import json
+    from tacotron_wavenet_vocoder_korean_b200.hparams import HParams, load_json, load_hparams
+    g = json.load(open(os.path.join(GOLD, 'ref_utils.json'), encoding='utf-8'))
+    p = tmp_path / 'params.json'
+    p.write_text(g['params_text'], encoding='euc-kr')
+    assert load_json(str(p)) == g['load_json']                       # trailing commas, euc-kr (utils/__init__.py:173-185)
+    hp = HParams(sample_rate=24000, num_mels=80, dilations=[1, 2], name='x', upsample_factor=[5, 5, 12], hop_size=300)
+    load_hparams(hp, str(tmp_path))
+    assert hp.values() == g['load_hparams']                          # known keys overridden, unknown skipped (:156-172)
