@@ -42,10 +42,16 @@ def mu_law_decode(output, quantization_channels, quantization=True):
     return out
 
 
-def _no_training(*_a, **_k):
-    raise NotImplementedError("optimizers belong to the training path (train_vocoder.py), which is outside "
-                              "the generation hot path this package implements (SURVEY.md section 8f, next-3)")
+def _adam(learning_rate=1e-3, **_k):
+    """wavenet/ops.py:3-5 create_adam_optimizer.  The reference's own trainer never goes through this table (add_optimizer builds
+    tf.train.AdamOptimizer directly, wavenet/model.py:325); here Adam is fused into libwn_train_b200's apply step, so the entry only
+    carries the hyper-parameters WaveNetTrainer.apply takes."""
+    return dict(optimizer='adam', learning_rate=learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8)
 
 
-# wavenet/ops.py:19 exports this mapping; the trainer is the only user.
-optimizer_factory = {'adam': _no_training, 'sgd': _no_training, 'rmsprop': _no_training}
+def _unsupported(*_a, **_k):
+    raise NotImplementedError("only Adam (the optimizer wavenet/model.py:325 hard-codes) is built into the B200 training step")
+
+
+# wavenet/ops.py:16-19 exports this mapping.
+optimizer_factory = {'adam': _adam, 'sgd': _unsupported, 'rmsprop': _unsupported}
