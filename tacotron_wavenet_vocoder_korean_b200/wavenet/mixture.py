@@ -22,5 +22,29 @@ def sample_from_discretized_mix_logistic(y, log_scale_min=None, uniforms=None):
     return torch.clamp(x, -1.0, 1.0)
 
 
-def discretized_mix_logistic_loss(*_a, **_k):
-    raise NotImplementedError("the MoL loss belongs to the training path (SURVEY.md section 8f, next-3)")
+def discretized_mix_logistic_loss(y_hat, y, num_class=256, log_scale_min=None, reduce=True):
+    """mixture.py:27-81 for callers that hold network outputs: y_hat (B, T, 3*nr_mix), y (B, T, 1) in [-1, 1] -> the summed loss
+    (`reduce=True`) or the per-step losses (B, T).  The training step does NOT go through this function: libwn_train_b200
+    evaluates the same formula fused with its gradient (csrc/wn_train_kernels.cuh, mol_loss_kernel); this is the tensor-level
+    entry point of the reference module, evaluated with torch ops on the tensors' device."""
+    import math
+    import torch.nn.functional as F
+    if log_scale_min is None:
+        log_scale_min = float(math.log(1e-14))
+    assert y_hat.dim() == 3 and y_hat.shape[2] % 3 == 0
+    nr = y_hat.shape[2] // 3
+    logit_probs, means = y_hat[..., :nr], y_hat[..., nr:2 * nr]
+    log_scales = torch.clamp(y_hat[..., 2 * nr:3 * nr], min=log_scale_min)
+    y = y.expand(-1, -1, nr)
+    centered = y - means
+    inv_stdv = torch.exp(-log_scales)
+    plus_in = inv_stdv * (centered + 1. / (num_class - 1))
+    min_in = inv_stdv * (centered - 1. / (num_class - 1))
+    cdf_delta = torch.sigmoid(plus_in) - torch.sigmoid(min_in)
+    mid_in = inv_stdv * centered
+    log_pdf_mid = mid_in - log_scales - 2. * F.softplus(mid_in)
+    inner = torch.where(cdf_delta > 1e-5, torch.log(torch.clamp(cdf_delta, min=1e-12)), log_pdf_mid - math.log((num_class - 1) / 2))
+    log_probs = torch.where(y < -0.999, plus_in - F.softplus(plus_in), torch.where(y > 0.999, -F.softplus(min_in), inner))
+    log_probs = log_probs + F.log_softmax(logit_probs, -1)
+    lse = torch.logsumexp(log_probs, -1)
+    return -lse.sum() if reduce else -lse
