@@ -104,6 +104,21 @@ def cpu_port_throughput(steps, threads):
     return ROWS * steps / dt
 
 
+def cpu_reference_structure_throughput(steps):
+    """SURVEY.md 8(d) "reference-structure" baseline: the numpy restatement driven by the same per-sample Python loop as
+    generate.py:202-233, every queue shifted by a full copy per step (model.py:122,125,145), numpy's BLAS threads as they
+    come.  Returns samples/s over ROWS rows."""
+    from oracle import np_oracle
+    kw, w, mel, uniforms, x0, gc = make_job(0)
+    net = np_oracle.NumpyWaveNet(**kw)
+    net.set_weights(w)
+    lc = net.create_upsample(mel[:, :(steps + 299) // 300])
+    np_oracle.generate(net, 10, np.asarray(x0).reshape(ROWS, -1)[:, :1], uniforms[:, :10], lc_up=lc, gc_ids=np.asarray(gc))
+    t0 = time.perf_counter()
+    np_oracle.generate(net, steps, np.asarray(x0).reshape(ROWS, -1)[:, :1], uniforms[:, :steps], lc_up=lc, gc_ids=np.asarray(gc))
+    return ROWS * steps / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU path cannot run (TensorFlow 1.x absent): time its CPU
     restatement (oracle port) with all host threads; each step is a bounded sample of the workload."""
@@ -300,7 +315,10 @@ def main():
         v = cpu_port_throughput(steps, threads)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": "%d rows x %d steps of the same workload, rows over %d host threads (oracle/wn_oracle.c, plain-C "
-                         "restatement; the TF 1.x reference cannot be installed)" % (ROWS, steps, threads)}
+                         "restatement; the TF 1.x reference cannot be installed)" % (ROWS, steps, threads),
+               "reference_structure": {"value": cpu_reference_structure_throughput(300), "unit": "samples/s",
+                                       "sample": "%d rows x 300 steps, numpy restatement in the per-sample Python loop of "
+                                                 "generate.py:202-233 with full queue copies per step (oracle/np_oracle.py)" % ROWS}}
 
     line = {"metric": "wavenet_generation_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,

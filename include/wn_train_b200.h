@@ -43,7 +43,7 @@ typedef struct wnt_config {
     int32_t n_layers, dilations[WNT_MAX_LAYERS];
     int32_t residual_channels, dilation_channels, skip_channels;   /* powers of two, 8..512 */
     int32_t out_channels, quantization_channels;
-    int32_t use_biases, scalar_input, initial_filter_width;        /* scalar_input must be 1 (MoL head) */
+    int32_t use_biases, scalar_input, initial_filter_width;        /* scalar_input 1: MoL head; 0: mu-law one-hot input + softmax head */
     int32_t gc_channels, gc_cardinality;                           /* 0 = no global conditioning */
     int32_t lc_channels;                                           /* 0 = no local conditioning; else multiple of 8 */
     int32_t n_upsample, upsample_factor[WNT_MAX_UPSAMPLE];

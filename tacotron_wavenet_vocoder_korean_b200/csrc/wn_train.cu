@@ -51,6 +51,9 @@ struct wnt_handle {
     std::string err;
     // geometry
     int N, L, R, D, S, O, OP, K, C, G, card, ifw, T, T0, SL, OW, rf, mel_frames;
+    bool scalar = true;               // scalar input + MoL head, or one-hot input + softmax head
+    int Q = 0, cw = 0, cin = 1;       // classes; causal filter width (ifw or filter_width = 2) and its input channels (1 or Q)
+    int32_t *ids = nullptr;           // (N, T) mu-law ids of the waveform (one-hot model)
     long M, Mo;
     std::vector<int> s, off;          // input start / output start of each layer
     bool bf;                          // bf16 storage
@@ -245,7 +248,7 @@ int build_layout(wnt_handle *h) {
     h->o_layer_w = o;
     o += h->layer_w_stride * L;
     h->o_ws = o; o = align_up(o + (int64_t)L * D * S, A);
-    h->o_wc = o; o = align_up(o + (int64_t)h->ifw * R, A);
+    h->o_wc = o; o = align_up(o + (int64_t)h->cw * h->cin * R, A);
     h->o_w1 = o; o = align_up(o + (int64_t)S * S, A);
     h->o_w2 = o; o = align_up(o + (int64_t)S * h->OP, A);
     h->o_e = o; o = align_up(o + (int64_t)h->card * G, A);
@@ -269,7 +272,7 @@ int build_layout(wnt_handle *h) {
     if (G) add_view(h, "wavenet/gc_embedding", h->o_e, 1, 0, h->card, G, G);
     for (int i = 0; i < h->cfg.n_upsample; ++i)
         add_view(h, "wavenet/upsample" + std::to_string(i) + "/kernel", h->o_up[i], 1, 0, h->cfg.upsample_factor[i], 2, 2);
-    add_view(h, "wavenet/conv1d/kernel", h->o_wc, 1, 0, h->ifw, R, R);
+    add_view(h, "wavenet/conv1d/kernel", h->o_wc, 1, 0, h->cw * h->cin, R, R);   // (cw, cin, R)
     for (int l = 0; l < L; ++l) {
         const std::string pre = "wavenet/dilated_stack/layer" + std::to_string(l) + "/dilation_layer/";
         const int64_t w = h->o_layer_w + h->layer_w_stride * l, bb = h->o_layer_b + h->layer_b_stride * l;
@@ -417,7 +420,13 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
         KCHECK();
     }
     // ---- causal layer ----
-    {
+    if (!h->scalar) {
+        mulaw_ids_kernel<<<grid_for((long)N * h->T, EW_THREADS, cap), EW_THREADS, 0, st>>>(wav, h->ids, (size_t)N * h->T, h->Q);
+        KCHECK();
+        onehot_causal_fwd_kernel<T><<<grid_for(M, EW_THREADS / (R / 2), cap), EW_THREADS, 0, st>>>(h->ids, P + h->o_wc, (T *)h->X[0], h->T, T0, M,
+                                                                                                h->Q, R);
+        KCHECK();
+    } else {
         if (h->fused && h->causal_gemm) {
             wntf::wav_im2col_kernel<<<grid_for((long)M * h->ifw, EW_THREADS, cap), EW_THREADS, 0, st>>>(wav, h->Wcol, N, h->T, T0, h->ifw);
             KCHECK();
@@ -486,9 +495,13 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
              ub ? (const void *)(P + h->o_b2) : nullptr));
     // ---- loss + d loss / d raw_output ----
     CK(cudaMemsetAsync(Gr + h->o_layer_b, 0, (size_t)(h->n_params - h->o_layer_b) * sizeof(float), st));   // all bias grads (atomics)
-    mol_loss_kernel<T><<<(unsigned)((Mo + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, st>>>(
-        h->Y, wav, (T *)h->dY, ub ? Gr + h->o_b2 : nullptr, h->acc, Mo, h->OW, h->T, h->rf, h->K, OP, (float)log(1e-14), 1.0f / 65535.0f,
-        (float)log(65535.0 / 2.0), (float)(1.0 / (double)Mo));
+    if (h->scalar)
+        mol_loss_kernel<T><<<(unsigned)((Mo + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, st>>>(
+            h->Y, wav, (T *)h->dY, ub ? Gr + h->o_b2 : nullptr, h->acc, Mo, h->OW, h->T, h->rf, h->K, OP, (float)log(1e-14), 1.0f / 65535.0f,
+            (float)log(65535.0 / 2.0), (float)(1.0 / (double)Mo));
+    else
+        softmax_ce_kernel<T><<<grid_for(Mo, EW_THREADS / 32, cap), EW_THREADS, 0, st>>>(h->Y, h->ids, (T *)h->dY, ub ? Gr + h->o_b2 : nullptr, h->acc,
+                                                                                     Mo, h->OW, h->T, h->rf, h->Q, OP, (float)(1.0 / (double)Mo));
     KCHECK();
     // ---- backward: post-processing ----
     CKR(gemm(h, st, true, false, S, OP, Mo, h->T2, S, h->dY, OP, ts, 0.f, Gr + h->o_w2, OP, Gr + h->o_w2, OP, f32));
@@ -614,9 +627,14 @@ int step_t(wnt_handle *h, const float *wav, const float *mel, const int32_t *gc_
     }
     // ---- backward: causal layer, conditioning ----
     {
-        CK(cudaMemsetAsync(Gr + h->o_wc, 0, (size_t)h->ifw * R * sizeof(float), st));
+        CK(cudaMemsetAsync(Gr + h->o_wc, 0, (size_t)h->cw * h->cin * R * sizeof(float), st));
         const size_t sm = (size_t)(CH + h->ifw) * sizeof(float);
-        if (h->fused && h->fused_bwd && h->causal_gemm) {
+        const int og = grid_for(M, EW_THREADS / (R / 2), cap);
+        if (!h->scalar && h->fused && h->fused_bwd)
+            onehot_causal_bwd_kernel<bf16><<<og, EW_THREADS, 0, st>>>(h->ids, h->dXp[L & 1], Gr + h->o_wc, h->T, T0, M, h->Q, R);
+        else if (!h->scalar)
+            onehot_causal_bwd_kernel<float><<<og, EW_THREADS, 0, st>>>(h->ids, h->dX32, Gr + h->o_wc, h->T, T0, M, h->Q, R);
+        else if (h->fused && h->fused_bwd && h->causal_gemm) {
             CKR(gemm(h, st, true, false, 2 * h->ifw, R, M, h->Wcol, 2 * h->ifw, h->dXp[L & 1], R, ts, 0.f, h->dWcTmp, R, h->dWcTmp, R, f32));
             wntf::causal_fold_kernel<<<(h->ifw * R + 255) / 256, 256, 0, st>>>(h->dWcTmp, Gr + h->o_wc, h->ifw, R);
         } else if (h->fused && h->fused_bwd)
@@ -692,7 +710,6 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     wnt_handle *h = nullptr;
     if (!cfg || !out) return fail(h, WNT_ERR_ARG, "null argument");
     *out = nullptr;
-    if (!cfg->scalar_input) return fail(h, WNT_ERR_UNSUPPORTED, "training with scalar_input=False (softmax cross-entropy head) is not built");
     if (cfg->n_layers < 1 || cfg->n_layers > WNT_MAX_LAYERS) return fail(h, WNT_ERR_ARG, "n_layers out of range");
     if (!pow2(cfg->residual_channels) || cfg->residual_channels < 8 || cfg->residual_channels > 256)
         return fail(h, WNT_ERR_UNSUPPORTED, "residual_channels must be a power of two in [8, 256]");
@@ -700,13 +717,15 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
         return fail(h, WNT_ERR_UNSUPPORTED, "dilation_channels must be a power of two in [8, 512]");
     if (!pow2(cfg->skip_channels) || cfg->skip_channels < 8 || cfg->skip_channels > 512)
         return fail(h, WNT_ERR_UNSUPPORTED, "skip_channels must be a power of two in [8, 512]");
-    if (cfg->out_channels % 3 || cfg->out_channels < 3 || cfg->out_channels / 3 > MOL_MAX_K)
+    if (cfg->scalar_input && (cfg->out_channels % 3 || cfg->out_channels < 3 || cfg->out_channels / 3 > MOL_MAX_K))
         return fail(h, WNT_ERR_ARG, "out_channels must be 3*nr_mix with nr_mix <= %d", MOL_MAX_K);
+    if (!cfg->scalar_input && (cfg->quantization_channels < 32 || cfg->quantization_channels % 32 || cfg->quantization_channels > 32 * CE_PER_LANE))
+        return fail(h, WNT_ERR_UNSUPPORTED, "quantization_channels must be a multiple of 32 in [32, %d]", 32 * CE_PER_LANE);
     if (cfg->lc_channels % 8) return fail(h, WNT_ERR_UNSUPPORTED, "lc_channels must be a multiple of 8");
     if (cfg->gc_channels < 0 || (cfg->gc_channels > 0 && cfg->gc_cardinality < 1)) return fail(h, WNT_ERR_ARG, "gc_cardinality missing");
     if (cfg->batch_size < 1 || cfg->initial_filter_width < 1 || cfg->initial_filter_width > 64) return fail(h, WNT_ERR_ARG, "bad batch_size / initial_filter_width");
     if (cfg->dtype != WNT_DTYPE_BF16 && cfg->dtype != WNT_DTYPE_FP32) return fail(h, WNT_ERR_ARG, "bad dtype");
-    {
+    if (cfg->scalar_input) {
         const int KG = EW_THREADS / cfg->residual_channels;
         if ((cfg->initial_filter_width + KG - 1) / KG > CAUSAL_TAPS) return fail(h, WNT_ERR_UNSUPPORTED, "initial_filter_width too large for residual_channels");
     }
@@ -727,10 +746,15 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     h->cfg = *cfg;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
     h->N = cfg->batch_size; h->L = cfg->n_layers; h->R = cfg->residual_channels; h->D = cfg->dilation_channels; h->S = cfg->skip_channels;
-    h->O = cfg->out_channels; h->OP = (int)align_up(cfg->out_channels, 8); h->K = cfg->out_channels / 3;
+    h->scalar = cfg->scalar_input != 0;
+    h->Q = cfg->quantization_channels;
+    h->O = h->scalar ? cfg->out_channels : h->Q;            // model.py:163-165
+    h->OP = (int)align_up(h->O, 8); h->K = h->scalar ? cfg->out_channels / 3 : 0;
     h->C = cfg->lc_channels; h->G = cfg->gc_channels; h->card = cfg->gc_channels ? cfg->gc_cardinality : 0;
     h->ifw = cfg->initial_filter_width; h->T = cfg->sample_size;
-    h->T0 = h->T - 1 - (h->ifw - 1);
+    h->cw = h->scalar ? h->ifw : 2;                         // model.py:41-46: initial_filter_width taps of 1 channel, or filter_width taps of Q
+    h->cin = h->scalar ? 1 : h->Q;
+    h->T0 = h->T - 1 - (h->cw - 1);
     h->bf = cfg->dtype == WNT_DTYPE_BF16;
     h->esz = h->bf ? 2 : 4;
     int sum = 0;
@@ -741,9 +765,9 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
         h->off.push_back(sum);
     }
     h->SL = sum;
-    h->rf = sum + 1 + (h->ifw - 1);                      // model.py:31-39
+    h->rf = sum + 1 + (h->cw - 1);                       // model.py:31-39
     h->OW = h->T0 - h->SL;
-    if (h->OW < 1) { delete h; return fail(nullptr, WNT_ERR_ARG, "sample_size %d does not exceed the receptive field %d", cfg->sample_size, sum + h->ifw); }
+    if (h->OW < 1) { delete h; return fail(nullptr, WNT_ERR_ARG, "sample_size %d does not exceed the receptive field %d", cfg->sample_size, h->rf); }
     h->M = (long)h->N * h->T0;
     h->Mo = (long)h->N * h->OW;
     h->mel_frames = h->C ? h->T / hop : 0;
@@ -755,6 +779,7 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
     const long M = h->M, Mo = h->Mo;
     const int D2 = 2 * h->D, LD = h->L * h->D;
     if (h->bf) { A_(h->Pc, (size_t)h->n_params * 2); }
+    if (!h->scalar) A_(h->ids, (size_t)h->N * h->T * sizeof(int32_t));
     if (h->C) {
         h->U.assign(h->cfg.n_upsample + 1, nullptr);
         h->dU.assign(h->cfg.n_upsample + 1, nullptr);
@@ -783,7 +808,7 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
         A_(h->dXp[0], (size_t)M * h->R * 2);
         A_(h->dXp[1], (size_t)M * h->R * 2);
         h->fused_bwd = getenv("WNT_NO_FUSED_BWD") == nullptr;
-        h->causal_gemm = h->ifw % 4 == 0 && getenv("WNT_NO_CAUSAL_GEMM") == nullptr;
+        h->causal_gemm = h->scalar && h->ifw % 4 == 0 && getenv("WNT_NO_CAUSAL_GEMM") == nullptr;
         if (h->causal_gemm) {
             A_(h->Wcol, (size_t)M * 2 * h->ifw * 2);
             A_(h->WcDup, (size_t)2 * h->ifw * h->R * 2);
@@ -820,7 +845,7 @@ int wnt_create(const wnt_config *cfg, wnt_handle **out) {
 #undef A_
     if (cublasLtCreate(&h->lt) != CUBLAS_STATUS_SUCCESS) { h->err = "cublasLtCreate failed"; return bail(WNT_ERR_CUBLAS); }
     if (h->fused) { int r_ = setup_fused(h); if (r_) return bail(r_); }
-    {
+    if (h->scalar) {
         const size_t sm = ((size_t)h->ifw * h->R + 128 + h->ifw) * sizeof(float);
         if (sm > 48 * 1024) {
             cudaFuncSetAttribute(causal_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -846,7 +871,7 @@ void wnt_destroy(wnt_handle *h) {
     if (h->bf) fr(h->Pc);   // fp32: Pc aliases the caller's parameter buffer
     for (auto p : h->U) fr(p);
     for (auto p : h->dU) fr(p);
-    fr(h->Wcol); fr(h->WcDup); fr(h->dWcTmp);
+    fr(h->Wcol); fr(h->WcDup); fr(h->dWcTmp); fr(h->ids);
     fr(h->Xall); fr(h->WfgT); fr(h->WdT); fr(h->WdP); fr(h->WdxP); fr(h->dXp[0]); fr(h->dXp[1]); fr(h->fused_err);
     for (auto p : h->TS) fr(p);
     void *all[] = {h->LC, h->dLC32, h->Zs, h->dZs, h->Z, h->T1, h->T2, h->dC1, h->dTot, h->dY, h->dXb, h->dFG, h->FG32, h->TOT, h->dT32, h->Y,

@@ -3,9 +3,10 @@
 // The contractions of the step (dilated 2-tap convs, 1x1 convs and their data / weight gradients) are plain GEMMs and
 // go to cuBLASLt (bf16 tensor cores, fp32 accumulation) from wn_train.cu; everything that is NOT a contraction is here:
 //   upsample fwd/bwd (conv2d_transpose stack, model.py:102-111), causal conv fwd/bwd (scalar input: a 32-tap FIR into R
-//   channels, model.py:41-46), gated activation fwd/bwd with the conditioning biases (model.py:71-86), ReLU / bias /
-//   column-sum epilogues of the post-processing stack (model.py:150-165), the discretized-mixture-of-logistics loss with
-//   its analytic gradient (mixture.py:27-81), global-condition gradients, L2, gradient norm, Adam + EMA (model.py:314-346).
+//   channels; one-hot input: two gathered kernel rows, model.py:41-46), gated activation fwd/bwd with the conditioning
+//   biases (model.py:71-86), ReLU / bias / column-sum epilogues of the post-processing stack (model.py:150-165), the
+//   discretized-mixture-of-logistics loss with its analytic gradient (mixture.py:27-81), the softmax cross-entropy head
+//   of the one-hot model (model.py:292-296), global-condition gradients, L2, gradient norm, Adam + EMA (model.py:314-346).
 //
 // All activations are indexed by ABSOLUTE time: row = n*T0 + tau, tau = index of the causal-conv output.  Layer l
 // (dilation d, input start s_l = sum of earlier dilations) produces valid outputs for tau >= off_l = s_l + d; rows
@@ -206,6 +207,50 @@ __global__ void causal_bwd_kernel(const float *__restrict__ wav, const TI *__res
 #pragma unroll
         for (int j = 0; j < CAUSAL_TAPS; ++j)
             if (j < per && k0 + j < ifw) atomicAdd(dW + (size_t)(k0 + j) * R + r, acc[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One-hot input (scalar_input=False): add_loss mu-law encodes the waveform (wavenet/ops.py:22-33, evaluated in fp32 as the
+// reference's graph does), one-hot encodes the ids (model.py:260) and the causal layer is a 'valid' conv of width
+// filter_width = 2 over Q channels (model.py:41-46) -- i.e. two gathered kernel rows per step:
+//   x0[n, tau, :] = W[0][id[n, tau]][:] + W[1][id[n, tau + 1]][:]
+__global__ void mulaw_ids_kernel(const float *__restrict__ wav, int32_t *__restrict__ ids, size_t n, int Q) {
+    const float mu = (float)(Q - 1), log_mu = log1pf(mu);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = wav[i];
+        const float mag = __fdiv_rn(log1pf(__fmul_rn(mu, fminf(fabsf(x), 1.0f))), log_mu);
+        const float sig = x > 0.f ? mag : (x < 0.f ? -mag : 0.f);
+        ids[i] = (int32_t)__fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(sig, 1.0f), 0.5f), mu), 0.5f);
+    }
+}
+
+template <typename T>
+__global__ void onehot_causal_fwd_kernel(const int32_t *__restrict__ ids, const float *__restrict__ W, T *__restrict__ X0, int Tlen,
+                                         int T0, long M, int Q, int R) {
+    const ColTile t(R);
+    for (long row = (long)blockIdx.x * t.rpp + t.lane_r; row < M; row += (long)gridDim.x * t.rpp) {
+        const int n = (int)(row / T0), tau = (int)(row - (long)n * T0);
+        const int a = ids[(size_t)n * Tlen + tau], b = ids[(size_t)n * Tlen + tau + 1];
+        const float2 u = ld2(W, (size_t)a * R + t.c), v = ld2(W, ((size_t)Q + b) * R + t.c);
+        st2(X0, (size_t)row * R + t.c, make_float2(u.x + v.x, u.y + v.y));
+    }
+}
+
+// dW[0][id[n, tau]][:] += dX[n, tau, :], dW[1][id[n, tau + 1]][:] += dX[n, tau, :]   (atomic scatter into pre-zeroed dW)
+template <typename TI>
+__global__ void onehot_causal_bwd_kernel(const int32_t *__restrict__ ids, const TI *__restrict__ dX, float *__restrict__ dW, int Tlen,
+                                         int T0, long M, int Q, int R) {
+    const ColTile t(R);
+    for (long row = (long)blockIdx.x * t.rpp + t.lane_r; row < M; row += (long)gridDim.x * t.rpp) {
+        const int n = (int)(row / T0), tau = (int)(row - (long)n * T0);
+        const int a = ids[(size_t)n * Tlen + tau], b = ids[(size_t)n * Tlen + tau + 1];
+        const float2 g = ld2(dX, (size_t)row * R + t.c);
+        float *pa = dW + (size_t)a * R + t.c, *pb = dW + ((size_t)Q + b) * R + t.c;
+        atomicAdd(pa, g.x);
+        atomicAdd(pa + 1, g.y);
+        atomicAdd(pb, g.x);
+        atomicAdd(pb + 1, g.y);
     }
 }
 
@@ -465,6 +510,73 @@ __global__ void mol_loss_kernel(const float *__restrict__ Y, const float *__rest
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < EW_THREADS / 32; ++w) s += (double)sloss[w];
+        atomicAdd(acc, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// softmax_cross_entropy_with_logits_v2 + reduce_mean (model.py:292-296) against the one-hot target id[n, rf + j], and its
+// gradient (softmax - one_hot) / count.  One warp per row of Y (Mo, OP) fp32, Q <= 32 * CE_PER_LANE classes; column sums of
+// dY (the conv1d_2/bias gradient) are kept per lane across the warp's rows, merged in shared memory, one atomic per column
+// and block; the loss sum in double into acc[0].
+constexpr int CE_PER_LANE = 16;
+template <typename T>
+__global__ void softmax_ce_kernel(const float *__restrict__ Y, const int32_t *__restrict__ ids, T *__restrict__ dY,
+                                  float *__restrict__ dbias, double *__restrict__ acc, long Mo, int OW, int Tlen, int rf, int Q, int OP,
+                                  float inv_count) {
+    __shared__ float scol[32 * CE_PER_LANE];
+    __shared__ float sloss[EW_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 32 * CE_PER_LANE; i += blockDim.x) scol[i] = 0.f;
+    __syncthreads();
+    float cs[CE_PER_LANE];
+#pragma unroll
+    for (int i = 0; i < CE_PER_LANE; ++i) cs[i] = 0.f;
+    float loss = 0.f;
+    for (long row = (long)blockIdx.x * nw + warp; row < Mo; row += (long)gridDim.x * nw) {
+        const int n = (int)(row / OW), j = (int)(row - (long)n * OW);
+        const int tgt = ids[(size_t)n * Tlen + rf + j];
+        const float *yr = Y + (size_t)row * OP;
+        float v[CE_PER_LANE];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < CE_PER_LANE; ++i) {
+            const int q = lane + 32 * i;
+            v[i] = q < Q ? yr[q] : -INFINITY;
+            mx = fmaxf(mx, v[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+#pragma unroll
+        for (int i = 0; i < CE_PER_LANE; ++i)
+            if (lane + 32 * i < Q) se += expf(v[i] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        const float lse = mx + logf(se);
+        if (lane == 0) loss += lse - yr[tgt];
+        T *dr = dY + (size_t)row * OP;
+#pragma unroll
+        for (int i = 0; i < CE_PER_LANE; ++i) {
+            const int q = lane + 32 * i;
+            if (q < Q) {
+                const float g = (expf(v[i] - lse) - (q == tgt ? 1.f : 0.f)) * inv_count;
+                st1(dr, q, g);
+                cs[i] += g;
+            }
+        }
+        for (int c = Q + lane; c < OP; c += 32) st1(dr, c, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < CE_PER_LANE; ++i)
+        if (lane + 32 * i < Q) atomicAdd(&scol[lane + 32 * i], cs[i]);
+    if (lane == 0) sloss[warp] = loss;
+    __syncthreads();
+    if (dbias)
+        for (int i = threadIdx.x; i < Q; i += blockDim.x) atomicAdd(dbias + i, scol[i]);
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += (double)sloss[w];
         atomicAdd(acc, s);
     }
 }

@@ -13,6 +13,8 @@ Cases (seeded inputs = tests/helpers.make_inputs, weights = synth.make_weights, 
   ref_cfg2    the benchmark configuration (BASELINE configs[1] layer sizes), 2 rows x 48 teacher-forced steps.
   ref_train   add_loss (train mode) of the tiny training model: the scalar loss the reference graph evaluates, with and
               without L2, and mu_law_encode / mu_law_decode of an amplitude grid (wavenet/ops.py).
+  ref_train_onehot  add_loss for scalar_input=False (mu-law one-hot input, softmax cross-entropy head), tiny models with
+              and without conditioning.
 """
 import os
 import sys
@@ -35,7 +37,7 @@ assert os.path.abspath(ref_wavenet.__file__).startswith(os.path.abspath(REF)), r
 sys.path.insert(1, ROOT)
 from tacotron_wavenet_vocoder_korean_b200 import synth    # noqa: E402
 from tests.helpers import make_inputs                       # noqa: E402
-from tests.train_helpers import train_case                  # noqa: E402
+from tests.train_helpers import train_case, at_cell_centres  # noqa: E402
 
 
 def build(kw, train_mode):
@@ -84,9 +86,11 @@ def incremental_case(kw, T):
     return res
 
 
-def train_case_loss(kw, T, codec=True):
+def train_case_loss(kw, T, codec=True, snap=False):
     out = {}
     w, wav, mel, gc = train_case(kw, T)
+    if snap:
+        wav = at_cell_centres(wav, kw['quantization_channels'])
     for tag, l2 in (('loss', None), ('loss_l2', 0.01)):
         net, _ = build(kw, True)
         with tf.graph_pass():
@@ -107,6 +111,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'ref_mulaw.npz'), **incremental_case(kw, 48))
     np.savez_compressed(os.path.join(HERE, 'ref_train.npz'), **train_case_loss(synth.tiny_train(3), 96))
     np.savez_compressed(os.path.join(HERE, 'ref_train_cfg2.npz'), **train_case_loss(synth.cfg2(2), 3600, codec=False))   # BASELINE configs[3] layers
+    # scalar_input=False: mu-law one-hot input + softmax cross-entropy (model.py:257-296), with and without conditioning
+    np.savez_compressed(os.path.join(HERE, 'ref_train_onehot.npz'),
+                        **{k + '_lc_gc': v for k, v in train_case_loss(dict(synth.tiny_train(3), scalar_input=False), 96, codec=False, snap=True).items()},
+                        **train_case_loss(synth.tiny_mulaw(2), 96, codec=False, snap=True))
     # BASELINE configs[1] layer sizes (30 layers, R=D=128, S=512, MoL-10, 80-channel mel, 2 speakers), 2 rows x 48 steps
     g = incremental_case(synth.cfg2(2), 48)
     g['lc_up'] = g['lc_up'][:, :48]

@@ -13,7 +13,7 @@ import oracle
 from oracle import train_oracle as to
 from tacotron_wavenet_vocoder_korean_b200 import synth
 from tests.helpers import make_inputs, oracle_model
-from tests.train_helpers import train_case
+from tests.train_helpers import train_case, at_cell_centres
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 MULAW_LC = dict(synth.tiny_mulaw(), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8,
@@ -85,6 +85,22 @@ def test_training_loss_matches_reference_graph_at_reference_layer_sizes():
     assert abs(float(m.loss(wav, mel, gc, 0.01).detach()) - float(g['loss_l2'])) < 2e-5 * abs(float(g['loss_l2']))
 
 
+ONE_HOT_CASES = {'': lambda: synth.tiny_mulaw(2), '_lc_gc': lambda: dict(synth.tiny_train(3), scalar_input=False)}
+
+
+@pytest.mark.parametrize('suffix', sorted(ONE_HOT_CASES))
+def test_one_hot_training_loss_matches_reference_graph(suffix):
+    """add_loss with scalar_input=False: mu_law_encode -> _one_hot -> 2-tap causal layer -> softmax cross-entropy (model.py:257-296)."""
+    g = np.load(os.path.join(GOLD, 'ref_train_onehot.npz'))
+    kw = ONE_HOT_CASES[suffix]()
+    w, wav, mel, gc = train_case(kw, 96)
+    wav = at_cell_centres(wav, kw['quantization_channels'])
+    m = to.TorchWaveNetTrain(w, **kw)
+    for tag, l2 in (('loss', None), ('loss_l2', 0.01)):
+        ref = float(g[tag + suffix])
+        assert abs(float(m.loss(wav, mel, gc, l2).detach()) - ref) < 2e-5 * abs(ref)
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
@@ -118,6 +134,21 @@ def test_cuda_training_loss_matches_reference_graph():
     tr.load_state_dict(w)
     assert abs(float(tr.loss_and_grads(wav, mel, gc).item()) - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
     assert abs(float(tr.loss_and_grads(wav, mel, gc, 0.01).item()) - float(g['loss_l2'])) < 1e-4 * abs(float(g['loss_l2']))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('suffix', sorted(ONE_HOT_CASES))
+def test_cuda_one_hot_training_loss_matches_reference_graph(suffix):
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.train import WaveNetTrainer
+    g = np.load(os.path.join(GOLD, 'ref_train_onehot.npz'))
+    kw = ONE_HOT_CASES[suffix]()
+    w, wav, mel, gc = train_case(kw, 96)
+    wav = at_cell_centres(wav, kw['quantization_channels'])
+    tr = WaveNetTrainer(96, dtype='fp32', **kw)
+    tr.load_state_dict(w)
+    for tag, l2 in (('loss', None), ('loss_l2', 0.01)):
+        ref = float(g[tag + suffix])
+        assert abs(float(tr.loss_and_grads(wav, mel, gc, l2).item()) - ref) < 1e-4 * abs(ref)
 
 
 # ---- utils/audio.py + hparams.py of the reference (tests/golden/make_reference_audio_golden.py) -----------------------------

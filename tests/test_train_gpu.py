@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from tacotron_wavenet_vocoder_korean_b200 import synth
-from tests.train_helpers import train_case, rel_err, cosine, well_conditioned
+from tests.train_helpers import train_case, rel_err, cosine, well_conditioned, at_cell_centres
 
 pytestmark = pytest.mark.gpu
 
@@ -67,6 +67,56 @@ def test_fp32_loss_logits_and_every_gradient_match_oracle(variant):
     assert set(g) == set(go)
     bad = _grad_outliers(g, kw, w, (wav, mel, gc), l2)
     assert not bad, bad
+
+
+ONE_HOT = {
+    'mulaw': lambda: synth.tiny_mulaw(2),                                        # BASELINE configs[0] family: no conditioning
+    'mulaw_lc_gc': lambda: dict(synth.tiny_train(3), scalar_input=False),
+    'mulaw_q64_no_bias': lambda: dict(synth.tiny_mulaw(2), quantization_channels=64, use_biases=False),
+}
+
+
+@pytest.mark.parametrize('variant', sorted(ONE_HOT))
+def test_fp32_one_hot_input_softmax_head_matches_oracle(variant):
+    """scalar_input=False: mu-law one-hot input, 2-tap causal layer over Q channels, softmax cross-entropy (model.py:257-296)."""
+    kw = ONE_HOT[variant]()
+    Q = kw['quantization_channels']
+    T = 96
+    w, wav, mel, gc = train_case(kw, T)
+    wav = at_cell_centres(wav, Q)
+    l2 = 0.01 if variant == 'mulaw' else None
+    Lo, go = _oracle(kw, w).loss_and_grads(wav, mel, gc, l2)
+    tr = _trainer(kw, T, 'fp32', w)
+    i = tr.info()
+    assert i['receptive_field'] == sum(kw['dilations']) + 2 and i['output_width'] == T - i['receptive_field']
+    L = float(tr.loss_and_grads(wav, mel, gc, l2).item())
+    raw_o = _oracle(kw, w).raw_output(wav, mel, gc)[0].detach().numpy().reshape(-1, Q)
+    raw = tr.debug_get('raw_output').reshape(-1, Q)
+    assert np.abs(raw - raw_o).max() <= 1e-4
+    assert abs(L - Lo) <= 1e-4 * max(1.0, abs(Lo))
+    g = tr.state_dict('grads')
+    assert set(g) == set(go) and g['wavenet/conv1d/kernel'].shape == (2, Q, kw['residual_channels'])
+    bad = _grad_outliers(g, kw, w, (wav, mel, gc), l2)
+    assert not bad, bad
+
+
+def test_bf16_one_hot_model_on_the_tcgen05_path():
+    """R = D = 128 with the softmax head: the fused layer kernels are the same, only the causal layer and the loss differ."""
+    kw = dict(synth.cfg2(2), scalar_input=False)
+    T = 3600
+    w, wav, mel, gc = train_case(kw, T)
+    wav = at_cell_centres(wav)
+    Lo, go = _oracle(kw, w).loss_and_grads(wav, mel, gc)
+    tr = _trainer(kw, T, 'bf16', w)
+    L = float(tr.loss_and_grads(wav, mel, gc).item())
+    assert tr.info()['fused_launches'] == 5 * 30
+    assert abs(L - Lo) <= 1e-2 * abs(Lo), (L, Lo)
+    g = tr.state_dict('grads')
+    big = [k for k in go if np.linalg.norm(go[k]) > 1e-4]
+    bad = {k: cosine(g[k], go[k]) for k in big if cosine(g[k], go[k]) < 0.99}
+    assert not bad, bad
+    losses = [float(tr.train_step(wav, mel, gc, dict(HP, wavenet_learning_rate=1e-4)).item()) for _ in range(8)]
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
 
 
 def test_state_dict_round_trip_and_layout():

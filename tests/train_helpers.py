@@ -24,6 +24,15 @@ def train_case(kw, T, seed=11, weight_seed=1234):
     return w, wav, mel, gc
 
 
+def at_cell_centres(wav, quantization_channels=256):
+    """Snap a waveform to the centres of its mu-law cells.  The one-hot model encodes the waveform inside the step
+    (wavenet/model.py:257, fp32); at a centre every libm / libdevice log1p yields the same id, so the oracle and the CUDA
+    path see the same one-hot input."""
+    from oracle import np_oracle
+    ids = np_oracle.mu_law_encode(wav, quantization_channels)
+    return np.asarray(np_oracle.mu_law_decode(ids, quantization_channels), np.float32)
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
