@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--one_hot', action='store_true', help='scalar_input=False: mu-law one-hot input + softmax cross-entropy head')
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -37,6 +38,8 @@ def main():
     if world > 1:
         dist.init_process_group('nccl')
     kw = synth.cfg2(a.batch)
+    if a.one_hot:
+        kw = dict(kw, scalar_input=False)
     tr = WaveNetTrainer(a.samples, dtype=a.dtype, **kw)
     tr.load_state_dict(synth.make_weights(**kw))
     tr.sync_params(0)
@@ -95,7 +98,7 @@ def main():
                 peak = float(peaks[k])
                 break
         print(json.dumps({
-            "metric": "WaveNet training throughput, audio samples/s (cfg-4: 30-layer R=D=128 S=512 MoL-10, batch %d x %d samples per GPU, %s, Adam+EMA)" % (a.batch, a.samples, a.dtype),
+            "metric": "WaveNet training throughput, audio samples/s (cfg-4: 30-layer R=D=128 S=512 %s, batch %d x %d samples per GPU, %s, Adam+EMA)" % ("mu-law one-hot input + softmax-256" if a.one_hot else "MoL-10", a.batch, a.samples, a.dtype),
             "value": world * a.batch * a.samples / (step_ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": step_ms, "split_ms": {"loss_and_grads": float(parts[0]), "grad_allreduce": float(parts[1]), "adam_ema": float(parts[2])},
             "gemm_tflops_achieved": tf, "gemm_tflops_peak": peak, "gemm_flops_per_step": info['flops_per_step'],
