@@ -309,7 +309,7 @@ def main():
                 "hbm_roofline_samples_per_sec": ROWS * peak * 1e9 / b_step}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only: the other ranks' hosts are idle at this point
         threads = min(os.cpu_count() or 1, ROWS)
         steps = 1500
         v = cpu_port_throughput(steps, threads)
