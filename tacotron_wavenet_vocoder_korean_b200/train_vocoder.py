@@ -60,7 +60,7 @@ class WavenetCropFeeder(object):
     """Host-side restatement of DataFeederWavenet (datasets/datafeeder_wavenet.py:50-176) as an iterator of
     (wav (N, sample_size) float32, mel (N, sample_size / hop, num_mels) float32, speaker ids (N,) int32 or None)."""
 
-    def __init__(self, data_dirs, batch_size, receptive_field, hparams, gc_enable=False, seed=123):
+    def __init__(self, data_dirs, batch_size, receptive_field, hparams, gc_enable=False, seed=123, crop_rng=None):
         self.data_dirs = list(data_dirs)
         self.batch_size = batch_size
         self.hop_size = hparams.hop_size
@@ -68,7 +68,8 @@ class WavenetCropFeeder(object):
         self.max_frames = self.sample_size // self.hop_size
         self.gc_enable = gc_enable
         self.skip_path_filter = getattr(hparams, 'skip_path_filter', False)
-        self.rng = np.random.RandomState(seed)                                                # :65 (the reference crops with the global RNG)
+        self.rng = np.random.RandomState(seed)                                                # :65
+        self.crop_rng = crop_rng if crop_rng is not None else self.rng                        # :153 crops with the GLOBAL numpy RNG
         self._offset = {d: 2 for d in self.data_dirs}                                         # :66 defaultdict(lambda: 2)
         self.data_dir_to_id = {d: i for i, d in enumerate(self.data_dirs)}
         self.path_dict = get_path_dict(self.data_dirs, max(self.sample_size, receptive_field), self.skip_path_filter)
@@ -98,7 +99,7 @@ class WavenetCropFeeder(object):
                 break
         wav = np.asarray(data['audio'], np.float32).reshape(-1)
         assert len(wav) % len(mel) == 0 and len(wav) // len(mel) == self.hop_size, "audio / mel not hop-aligned (datafeeder_wavenet.py:38)"
-        s = self.rng.randint(0, len(mel) - self.max_frames + 1)                               # :153
+        s = self.crop_rng.randint(0, len(mel) - self.max_frames + 1)                          # :153
         ts = s * self.hop_size
         ex = (wav[ts:ts + self.hop_size * self.max_frames], np.asarray(mel[s:s + self.max_frames], np.float32))
         return ex + ((self.data_dir_to_id[data_dir],) if self.gc_enable else ())

@@ -101,6 +101,33 @@ def test_one_hot_training_loss_matches_reference_graph(suffix):
         assert abs(float(m.loss(wav, mel, gc, l2).detach()) - ref) < 2e-5 * abs(ref)
 
 
+@pytest.mark.parametrize('case,batch_size,gc_enable,dirs', [('two_speakers', 3, True, ('spk_a', 'spk_b')), ('one_speaker', 2, False, ('spk_a',))])
+def test_crop_feeder_yields_the_batches_of_the_reference_feeder(tmp_path, case, batch_size, gc_enable, dirs):
+    """tests/golden/make_reference_feeder_golden.py ran the reference's DataFeederWavenet.make_batches() twice on this data set:
+    path filtering by train.txt, the offset-2 start, skipped missing files, reshuffles on wrap-around, hop-aligned crops, the
+    shuffle of 32 batches' worth of examples and the speaker ids must come out identically, batch for batch."""
+    from tacotron_wavenet_vocoder_korean_b200.train_vocoder import WavenetCropFeeder
+    from tests.train_helpers import make_feeder_dataset, FEEDER_HP
+    g = np.load(os.path.join(GOLD, 'ref_feeder.npz'))
+    make_feeder_dataset(str(tmp_path))
+    hp = type('HP', (), dict(FEEDER_HP))()
+    f = WavenetCropFeeder([str(tmp_path / d) for d in dirs], batch_size, 50, hp, gc_enable=gc_enable, seed=123,
+                          crop_rng=np.random.RandomState(77))          # the reference crops with the global RNG, seeded 77 there
+    assert f.sample_size == int(g[case + '_sample_size']) == 96
+    ref_paths = dict(x.split(':') for x in g[case + '_path_dict'].tolist())
+    n = int(g[case + '_n_batches'])
+    assert n == 64
+    for b in range(n):
+        wav, mel, ids = next(f)
+        np.testing.assert_array_equal(wav, g[case + '_wav'][b, :, :, 0])
+        np.testing.assert_array_equal(mel, g[case + '_mel'][b])
+        if gc_enable:
+            np.testing.assert_array_equal(ids, g[case + '_ids'][b])
+        else:
+            assert ids is None
+    assert {os.path.basename(k): ','.join(v) for k, v in f.path_dict.items()} == ref_paths      # same files kept, same final order
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])

@@ -54,3 +54,28 @@ def well_conditioned(w):
     b[2 * k:] = -0.5
     w['wavenet/conv1d_2/bias'] = b
     return w
+
+
+# ---- a small on-disk data set in the format preprocess.py writes (datasets/moon.py:158-172), for the feeder pin ----------------
+FEEDER_HP = dict(sample_size=100, hop_size=12, num_mels=5, skip_path_filter=False)
+
+
+def make_feeder_dataset(root, dirs=('spk_a', 'spk_b'), n_files=(7, 5), seed=5):
+    """Deterministic npz files + train.txt under root/<dir>: audio (frames*hop,), mel (frames, num_mels), time_steps, mel_frames.
+    Some utterances are shorter than sample_size (filtered by train.txt), one listed file is missing on disk."""
+    import os
+    rs = np.random.RandomState(seed)
+    hop, C = FEEDER_HP['hop_size'], FEEDER_HP['num_mels']
+    for di, (d, n) in enumerate(zip(dirs, n_files)):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+        lines = []
+        for i in range(n):
+            frames = int(rs.randint(5, 30))
+            name = 'utt%d_%02d.npz' % (di, i)
+            audio = (rs.rand(frames * hop) * 2 - 1).astype(np.float32)
+            mel = rs.randn(frames, C).astype(np.float32)
+            if not (di == 0 and i == 3):                   # listed in train.txt but absent on disk (datafeeder_wavenet.py:132-135)
+                np.savez(os.path.join(root, d, name), audio=audio, mel=mel, time_steps=frames * hop, mel_frames=frames)
+            lines.append('|'.join(['a', 'm', 'l', str(frames * hop), str(frames), 'text', name]))
+        with open(os.path.join(root, d, 'train.txt'), 'w', encoding='utf-8') as f:
+            f.write('\n'.join(lines) + '\n')
