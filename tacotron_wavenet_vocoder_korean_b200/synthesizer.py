@@ -29,24 +29,19 @@ def get_time():
 
 
 def attention_trim_index(alignment, seq_len, reduction_factor):
-    """synthesizer.py:235-256: walk the per-step argmax of the alignment (T_in, T_dec) until the last attended
-    token has been held (up to 5 steps) or left; returns the number of spectrogram frames to keep."""
-    attention_argmax = alignment.argmax(0)
-    end_idx = min(seq_len - 1, int(attention_argmax.max()))
-    max_counter = min(int((attention_argmax == end_idx).sum()), 5)
-    end_idx_counter = 0
-    jdx = 0
-    for jdx, attend_idx in enumerate(attention_argmax):
-        if len(attention_argmax) > jdx + 1:
-            if attend_idx == end_idx:
-                end_idx_counter += 1
-            if attend_idx == end_idx and attention_argmax[jdx + 1] > end_idx:
-                break
-            if end_idx_counter >= max_counter:
-                break
-        else:
-            break
-    return reduction_factor * jdx + 3
+    """End-of-sentence trimming of synthesizer.py:235-256 for one alignment (T_in, T_dec): the number of spectrogram
+    frames to keep.  With a = per-decoder-step argmax and `last` = min(seq_len - 1, max(a)), decoding is considered finished
+    at the first step j (before the final one) where either `last` has been attended min(#steps on `last`, 5) times, or
+    `last` is attended and the next step moves past it; otherwise at the final step.  Frames kept = r * j + 3."""
+    a = np.asarray(alignment).argmax(0)
+    if a.size <= 1:
+        return 3
+    last = min(int(seq_len) - 1, int(a.max()))
+    on_last = a[:-1] == last
+    held = min(int((a == last).sum()), 5)
+    stop = (np.cumsum(on_last) >= held) | (on_last & (a[1:] > last))
+    j = int(np.argmax(stop)) if stop.any() else a.size - 1
+    return reduction_factor * j + 3
 
 
 class Synthesizer(object):

@@ -128,6 +128,20 @@ def test_crop_feeder_yields_the_batches_of_the_reference_feeder(tmp_path, case, 
     assert {os.path.basename(k): ','.join(v) for k, v in f.path_dict.items()} == ref_paths      # same files kept, same final order
 
 
+def test_attention_trim_matches_reference_synthesizer():
+    """tests/golden/make_reference_trim_golden.py ran the reference's plot_graph_and_save_audio (synthesizer.py:198-277) on 400
+    alignment paths; the number of frames it keeps must equal synthesizer.attention_trim_index on the same paths."""
+    from tacotron_wavenet_vocoder_korean_b200.synthesizer import attention_trim_index
+    g = np.load(os.path.join(GOLD, 'ref_trim.npz'))
+    T, r = int(g['t_dec']), int(g['reduction_factor'])
+    assert len(set(g['kept'].tolist())) > 10                          # the cases spread over early / late / never-finished endings
+    for p, L, kept in zip(g['paths'], g['lens'], g['kept']):
+        n_in = int(max(L, p.max() + 1))
+        al = np.zeros((n_in, T), np.float32)
+        al[p, np.arange(T)] = 1.0
+        assert min(attention_trim_index(al, int(L), r), T * r) == int(kept), (p.tolist(), int(L))
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
