@@ -195,7 +195,9 @@ def get_arguments(argv=None):
 
 def validate_directories(config):
     """utils/__init__.py:100-140: --logdir excludes --logdir_root / --restore_from; default root ./logdir-wavenet;
-    a new run goes to <root>/train/<timestamp> and restores from --restore_from (or from itself)."""
+    a new run goes to <root>/train/<timestamp> and restores from --restore_from (or from itself).  Difference kept on purpose:
+    the reference writes params.json when the run directory is created and re-reads it when --logdir continues a run; here
+    params.json is written next to every checkpoint (`save`) and a continued run keeps the hparams of the current process."""
     if config.logdir and config.logdir_root:
         raise ValueError("--logdir and --logdir_root cannot be specified at the same time.")
     if config.logdir and config.restore_from:
