@@ -142,6 +142,54 @@ def test_attention_trim_matches_reference_synthesizer():
         assert min(attention_trim_index(al, int(L), r), T * r) == int(kept), (p.tolist(), int(L))
 
 
+# ---- the reference's own generate.py main() (tests/golden/make_reference_generate_golden.py) ---------------------------------
+def _generate_main_inputs(kw, g):
+    om = oracle_model(kw, synth.make_weights(**kw))
+    N = kw['batch_size']
+    lc = om.upsample(np.tile(g['mel'][None], (N, 1, 1)))                     # generate.py:153-155: ONE mel tiled over the batch
+    return om, lc, np.full(N, 1, np.int32), np.random.RandomState(int(g['numpy_seed']))
+
+
+def test_oracle_reproduces_reference_generate_main_mol():
+    """generate.py main() of the reference, scalar input / MoL head / input_type 'raw', 2 rows x 60 samples: silent seed + one
+    random sample (generate.py:186-188), per-sample loop (:202-233), output slice (:240) and save_wav."""
+    from tacotron_wavenet_vocoder_korean_b200 import audio
+    g = np.load(os.path.join(GOLD, 'ref_generate_main.npz'))
+    kw = synth.tiny_mol(2)
+    om, lc, gc, rs = _generate_main_inputs(kw, g)
+    x0 = (2 * rs.rand(2) - 1).reshape(2, 1)                                  # generate.py:188, numpy's global RNG
+    T = g['mol_wave'].shape[1]
+    out = om.generate(T, x0, g['mol_uniforms'], lc_up=lc, gc_ids=gc)
+    assert np.abs(out - g['mol_wave']).max() < 1e-4                          # free-running for 60 steps
+    import io
+    from scipy.io import wavfile
+    for n in range(2):
+        buf = io.BytesIO()
+        audio.save_wav(out[n].copy(), buf, 24000)
+        buf.seek(0)
+        assert np.abs(wavfile.read(buf)[1].astype(np.int32) - g['mol_pcm'][n]).max() <= 1
+
+
+@pytest.mark.parametrize('tag,temperature', [('mulaw_t1', 1.0), ('mulaw_t07', 0.7)])
+def test_oracle_reproduces_reference_generate_main_mulaw(tag, temperature):
+    """generate.py main() of the reference, one-hot input / softmax head / input_type 'mulaw-quantize': seed 128 ... + randint
+    (:190-192), temperature rescaling and np.random.choice per row and step (:213-231), mu_law_decode (:246-247): the integer
+    samples must be IDENTICAL."""
+    g = np.load(os.path.join(GOLD, 'ref_generate_main.npz'))
+    kw = MULAW_LC
+    om, lc, gc, rs = _generate_main_inputs(kw, g)
+    Q = kw['quantization_channels']
+    wave = g[tag + '_wave']
+    T = wave.shape[1]
+    x0 = rs.randint(Q, size=2).reshape(2, 1).astype(np.float32)              # generate.py:192
+    u = np.array([[rs.random_sample() for _ in range(2)] for _ in range(T)]).T      # np.random.choice: one double per row, step-major
+    ids = om.generate(T, x0, u, lc_up=lc, gc_ids=gc, temperature=temperature)
+    table = oracle.mu_law_decode(np.arange(Q, dtype=np.float32), Q)
+    ref_ids = np.abs(wave[:, :, None] - table[None, None, :]).argmin(-1)
+    assert np.abs(table[ref_ids] - wave).max() < 1e-6
+    assert np.array_equal(ids.astype(np.int64), ref_ids)
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
@@ -163,6 +211,32 @@ def test_cuda_generation_matches_reference_goldens(name):
     else:
         p = torch.softmax(torch.from_numpy(lg).double(), -1).float().numpy()
         assert np.abs(p - g['outputs']).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_reference_generate_main():
+    """The persistent kernel against the waveforms the reference's own generate.py main() produced (ref_generate_main.npz)."""
+    from tacotron_wavenet_vocoder_korean_b200.wavenet import WaveNetModel
+    g = np.load(os.path.join(GOLD, 'ref_generate_main.npz'))
+    seed = int(g['numpy_seed'])
+    for kw, tag, temperature in ((synth.tiny_mol(2), 'mol', 1.0), (MULAW_LC, 'mulaw_t1', 1.0), (MULAW_LC, 'mulaw_t07', 0.7)):
+        net = WaveNetModel(train_mode=False, **kw)
+        net.load_state_dict(synth.make_weights(**kw))
+        lc = net.create_upsample(np.tile(g['mel'][None], (2, 1, 1)))
+        rs = np.random.RandomState(seed)
+        wave = g[tag + '_wave']
+        T = wave.shape[1]
+        if kw['scalar_input']:
+            x0 = (2 * rs.rand(2) - 1).reshape(2, 1).astype(np.float32)
+            out = net.generate(T, x0, g['mol_uniforms'], lc_up=lc, gc_ids=[1, 1]).cpu().numpy()
+            assert np.abs(out - wave).max() < 1e-4
+        else:
+            Q = kw['quantization_channels']
+            x0 = rs.randint(Q, size=2).reshape(2, 1).astype(np.float32)
+            u = np.array([[rs.random_sample() for _ in range(2)] for _ in range(T)]).T
+            ids = net.generate(T, x0, u, lc_up=lc, gc_ids=[1, 1], temperature=temperature).cpu().numpy()
+            table = oracle.mu_law_decode(np.arange(Q, dtype=np.float32), Q)
+            assert np.array_equal(ids.astype(np.int64), np.abs(wave[:, :, None] - table[None, None, :]).argmin(-1))
 
 
 @pytest.mark.gpu
