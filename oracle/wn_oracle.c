@@ -10,7 +10,11 @@
  * tests/golden/ref_mol.npz / ref_mulaw.npz with the generating script
  * (tests/golden/make_reference_goldens.py) and this oracle reproduces them to 2e-5 on the
  * logits, samples and probabilities (tests/test_reference_pin.py), including every variable
- * name / shape and the queue layout.  What stays UNPINNED is the arithmetic inside TF's own
+ * name / shape and the queue layout.  The whole loop is pinned too: the reference's generate.py
+ * main() was run unmodified on the stand-in (tests/golden/make_reference_generate_golden.py ->
+ * ref_generate_main.npz) and orc_generate reproduces its waveforms from the same seeds -- mu-law
+ * integer samples identical at temperature 1.0 and 0.7, the MoL waveform within 2.1e-7.
+ * What stays UNPINNED is the arithmetic inside TF's own
  * kernels (conv1d, conv2d_transpose, softmax, random_uniform), restated from their published
  * definitions.  Further pins: (a) the known-answer values in the reference's comments,
  * (b) an independent numpy restatement (oracle/np_oracle.py), (c) torch's conv_transpose2d
