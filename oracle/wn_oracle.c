@@ -614,7 +614,7 @@ int orc_generate(orc_model *m, const orc_plan *plan, int T, int n_forced, const 
     if (check_complete(m)) return -1;
     const orc_config *c = &m->cfg;
     const int N = c->batch, L = c->n_layers, R = c->residual_channels, D = c->dilation_channels;
-    const int S = c->skip_channels, G = c->gc_channels, C = c->lc_channels, O = m->out_dim;
+    const int S = c->skip_channels, G = c->gc_channels, C = c->lc_channels;
     const int ifw = c->initial_filter_width, Q = c->quantization_channels;
     orc_plan p = *plan;
     if (!is_pow2(p.M) || D % p.M || !is_pow2(p.Mt) || S % p.Mt) { snprintf(m->err, sizeof m->err, "bad plan M/Mt"); return -1; }
