@@ -106,6 +106,24 @@ class WaveNetTrainer(object):
         shapes = synth.weight_shapes(**self.kw)
         return {k: tuple(shapes[k]) for k in self.variable_names}
 
+    def _check_gc_range(self, ids):
+        """Speaker ids index the embedding table on the device, so they are range-checked first.  Host data is checked on the
+        host; a CUDA tensor is checked once per (storage, version) -- reading it back costs a device synchronisation, which
+        a training loop that reuses its id tensor must not pay every step."""
+        card = self._cfg.gc_cardinality
+        if torch.is_tensor(ids) and ids.is_cuda:
+            key = (ids.data_ptr(), ids._version, tuple(ids.shape))
+            if getattr(self, '_gc_checked', None) == key:
+                return
+            lo, hi = int(ids.min()), int(ids.max())
+            self._gc_checked = key
+        else:
+            a = np.asarray(ids.cpu() if torch.is_tensor(ids) else ids)
+            lo, hi = int(a.min()), int(a.max())
+        if lo < 0 or hi >= card:
+            self._gc_checked = None
+            raise ValueError("global condition id out of range [0, %d)" % card)
+
     # ---- the step ---------------------------------------------------------------------------------------------------
     def loss_and_grads(self, input_batch, local_condition=None, global_condition_batch=None, l2_regularization_strength=None):
         """add_loss + compute_gradients.  input_batch (N, sample_size[, 1]) float in [-1, 1]; local_condition
@@ -127,9 +145,8 @@ class WaveNetTrainer(object):
             if self._cfg.gc_channels:
                 if global_condition_batch is None:
                     raise ValueError("global_condition_batch is required (global_condition_channels=%d)" % self._cfg.gc_channels)
+                self._check_gc_range(global_condition_batch)
                 gc = torch.as_tensor(global_condition_batch, device=self.device).reshape(N).to(torch.int32).contiguous()
-                if int(gc.min()) < 0 or int(gc.max()) >= self._cfg.gc_cardinality:
-                    raise ValueError("global condition id out of range [0, %d)" % self._cfg.gc_cardinality)
             l2 = -1.0 if l2_regularization_strength is None else float(l2_regularization_strength)
             self._keep = (wav, mel, gc)
             self._check(_train_lib.lib().wnt_loss_and_grads(
