@@ -86,6 +86,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def cpu_model_name():
+    """the host CPU the baselines ran on."""
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.lower().startswith('model name'):
+                    return line.split(':', 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_throughput(steps, threads):
     """The CPU oracle (plain-C restatement of the reference loop) on `ROWS` rows x `steps` steps of the
     workload; rows are spread over host threads.  Returns samples/s."""
@@ -139,8 +151,8 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "steps_per_row": T_STEPS},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": "%d rows x %d steps of the workload per bench step, rows over %d host threads "
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
+                             "host_cores": cores, "sample": "%d rows x %d steps of the workload per bench step, rows over %d host threads "
                                        "(oracle/wn_oracle.c; the TF 1.x reference is not installable)" % (ROWS, sample_steps, threads)},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "per_step_values": vals}
@@ -313,8 +325,8 @@ def main():
         threads = min(os.cpu_count() or 1, ROWS)
         steps = 1500
         v = cpu_port_throughput(steps, threads)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": "%d rows x %d steps of the same workload, rows over %d host threads (oracle/wn_oracle.c, plain-C "
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
+               "host_cores": os.cpu_count(), "sample": "%d rows x %d steps of the same workload, rows over %d host threads (oracle/wn_oracle.c, plain-C "
                          "restatement; the TF 1.x reference cannot be installed)" % (ROWS, steps, threads),
                "reference_structure": {"value": cpu_reference_structure_throughput(300), "unit": "samples/s",
                                        "sample": "%d rows x 300 steps, numpy restatement in the per-sample Python loop of "
