@@ -136,3 +136,23 @@ def test_training_entry_points_need_train_mode_and_a_loss_first():
         net.add_loss(None)                      # generation-mode model (wavenet/model.py:26 train_mode)
     with pytest.raises(RuntimeError):
         net.add_optimizer(None, None)           # "Supposes that initialize function has already been called" (:315)
+
+
+def test_integration_md_stub_matches_the_shipped_binding():
+    """The ctypes structures a maintainer of the reference is told to add must have the layout of the
+    binding this package ships (and therefore of include/wn_b200.h)."""
+    import ctypes as C
+    import re
+    from tacotron_wavenet_vocoder_korean_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md'), encoding='utf-8').read()
+    block = re.search(r"```python\n# wavenet/b200.py(.*?)```", text, re.S).group(1)
+    classes = block[block.index('class WnConfig'):block.index('def b200_generate')]
+    ns = {'C': C}
+    exec(classes, ns)
+    for name in ('WnConfig', 'WnGenerateArgs'):
+        doc, real = ns[name], getattr(_lib, name)
+        assert C.sizeof(doc) == C.sizeof(real), name
+        assert [(n, getattr(doc, n).offset, getattr(doc, n).size) for n, _ in doc._fields_] == \
+               [(n, getattr(real, n).offset, getattr(real, n).size) for n, _ in real._fields_], name
+    for fn in re.findall(r"_lib\.(wn_\w+)\(", block):
+        assert fn in _lib.EXPORTS, fn
