@@ -65,7 +65,7 @@ typedef struct wnt_info {
 
 typedef struct wnt_handle wnt_handle;
 
-/* WaveNetModel(train_mode=True, ...) */
+/* WaveNetModel(train_mode=True, ...) as train_vocoder.py:100-116 constructs it (wavenet/model.py:8-30) */
 int wnt_create(const wnt_config *cfg, wnt_handle **out);
 void wnt_destroy(wnt_handle *h);
 const char *wnt_last_error(const wnt_handle *h);       /* h may be NULL: last create error */
@@ -86,8 +86,8 @@ int64_t wnt_variable_names(const wnt_handle *h, char *out, int64_t n);
  * after any direct write to params_dev call this to refresh the compute-dtype copy. */
 int wnt_params_changed(wnt_handle *h, void *stream);
 
-/* net.add_loss(input_batch, local_condition, global_condition_batch, l2_regularization_strength) evaluated with its
- * gradients (optimizer.compute_gradients, wavenet/model.py:327):
+/* net.add_loss(input_batch, local_condition, global_condition_batch, l2_regularization_strength) (wavenet/model.py:247-312,
+ * train_vocoder.py:122) evaluated with its gradients (optimizer.compute_gradients, wavenet/model.py:327):
  *   wav_dev (N, sample_size) fp32 in [-1,1]; mel_dev (N, mel_frames, lc_channels) fp32 or NULL; gc_ids_dev (N) int32 or
  *   NULL; l2_strength < 0 means None.  Writes the scalar loss to loss_dev[0] and d loss / d params to the bound grads.
  * Asynchronous on `stream`. */
