@@ -118,6 +118,8 @@ class Synthesizer(object):
                     current = "%s.%d%s" % (root, idx, ext or '.wav')
                 else:
                     os.makedirs(base_path, exist_ok=True)
+                    # the reference names this "<base_path>/<time>.wav" for every sentence of the batch (synthesizer.py:206,265), so
+                    # sentences synthesised within one second overwrite each other; the sentence index keeps them apart here
                     current = "{}/{}.{}.wav".format(base_path, get_time(), idx)
                 mel_path = current.replace(".wav", ".npy")
                 np.save(mel_path, mel)                                            # synthesizer.py:279-280
