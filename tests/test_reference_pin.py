@@ -342,6 +342,30 @@ def _taco_case(tag):
     return g, hp, ns, w, ids, lens, spk, steps, (g['manual_alignments'] if 'manual_alignments' in g.files else None)
 
 
+def test_host_side_of_synthesize_matches_reference_synthesizer():
+    """tests/golden/make_reference_synth_golden.py ran the reference's Synthesizer.load + Synthesizer.synthesize unmodified on three
+    Korean sentences for two speakers.  This repository's host steps (tokeniser, padding, input_lengths, attention trimming, output
+    naming) around the Tacotron oracle must reproduce the sequences it fed, the network outputs and the trimmed mel files it wrote."""
+    from oracle.taco_oracle import TacotronOracle
+    from tacotron_wavenet_vocoder_korean_b200.synthesizer import attention_trim_index
+    from tacotron_wavenet_vocoder_korean_b200.text import text_to_sequence, prepare_inputs
+    g = np.load(os.path.join(GOLD, 'ref_synth_main.npz'))
+    texts, spk = g['texts'].tolist(), g['speakers']
+    sequences = prepare_inputs([text_to_sequence(t) for t in texts])                  # synthesizer.py:94-95
+    assert np.array_equal(sequences, g['sequences'])
+    lengths = np.array([int(np.argmax(a == 1)) + 1 for a in sequences])               # :126
+    assert np.array_equal(lengths, g['input_lengths'])
+    hp = synth.taco_tiny()
+    steps = g['alignments'].shape[2]
+    mel, lin, al = TacotronOracle(hp, synth.make_taco_weights(hp, 2, seed=4321), 2).synthesize(sequences, lengths, spk, max_iters=steps)
+    assert np.abs(mel - g['mel_outputs']).max() < 2e-6 and np.abs(al - g['alignments']).max() < 1e-6
+    assert g['files'].tolist() == ['s.%d.npy' % i for i in range(len(texts))]         # add_postfix(path, idx) -> <root>.<idx>.<ext>
+    for i in range(len(texts)):
+        end = attention_trim_index(al[i], len(sequences[i]), hp['reduction_factor'])   # :235-256
+        ref = g['mel%d' % i]
+        assert mel[i][:end].shape == ref.shape and np.abs(mel[i][:end] - ref).max() < 2e-6
+
+
 @pytest.mark.parametrize('tag', TACO_FULL)
 def test_taco_oracle_matches_reference_full_graph(tag):
     """Tacotron.initialize (inference) of the reference, run unmodified on the numpy TF stand-ins: the reference's AttentionWrapper
