@@ -85,6 +85,34 @@ def test_training_loss_matches_reference_graph_at_reference_layer_sizes():
     assert abs(float(m.loss(wav, mel, gc, 0.01).detach()) - float(g['loss_l2'])) < 2e-5 * abs(float(g['loss_l2']))
 
 
+def test_optimizer_plumbing_matches_reference_add_optimizer():
+    """tests/golden/make_reference_optimizer_golden.py recorded what the reference's add_optimizer (wavenet/model.py:314-346) asks
+    TensorFlow for: exponential_decay(wavenet_learning_rate, global_step, wavenet_decay_steps, wavenet_decay_rate) with no staircase,
+    AdamOptimizer(lr) with TF's default betas / epsilon, clip_by_global_norm(., 1.0) only behind wavenet_clip_gradients,
+    ExponentialMovingAverage(0.9999) over every trainable variable, in the order gradients -> apply -> EMA."""
+    import inspect
+    import json
+    from tacotron_wavenet_vocoder_korean_b200.hparams import hparams
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.train import WaveNetTrainer, learning_rate_at
+    g = json.load(open(os.path.join(GOLD, 'ref_optimizer.json')))
+    for k, v in g['hparams'].items():
+        assert getattr(hparams, k) == v, k                                       # hparams.py mirror
+    for clip in (True, False):
+        r = g['clip_%s' % clip]
+        assert r['calls'] == ['compute_gradients', 'apply_gradients', 'ema.apply']
+        assert r['adam_args'] == ['lr'] and r['adam_kwargs'] == {} and r['ema_kwargs'] == {} and r['ema_over_all_trainables']
+        assert r['exponential_decay']['extra_args'] == [] and r['exponential_decay']['extra_kwargs'] == {}      # staircase=False
+        assert r['applied_clipped'] == clip and (r.get('clip_norm') == 1.0) == clip
+    d = g['clip_True']['exponential_decay']
+    for step in (0, 1, 1000, 300000, 450000):
+        assert abs(learning_rate_at(hparams, step) - d['learning_rate'] * d['decay_rate'] ** (step / d['decay_steps'])) < 1e-15
+    defaults = {k: v.default for k, v in inspect.signature(WaveNetTrainer.apply).parameters.items() if v.default is not inspect.Parameter.empty}
+    assert (defaults['beta1'], defaults['beta2'], defaults['epsilon']) == (0.9, 0.999, 1e-8)      # tf.train.AdamOptimizer defaults
+    assert defaults['ema_decay'] == g['clip_True']['ema_decay'] == 0.9999 and defaults['clip_norm'] == 0.0
+    src = inspect.getsource(WaveNetTrainer.train_step)
+    assert "clip_norm=1.0 if get('wavenet_clip_gradients'" in src                # the clip norm the reference passes, behind the same flag
+
+
 ONE_HOT_CASES = {'': lambda: synth.tiny_mulaw(2), '_lc_gc': lambda: dict(synth.tiny_train(3), scalar_input=False)}
 
 
