@@ -66,7 +66,7 @@ def remember(fn):
     return wrapped
 
 
-def run_main(kw, input_type, temperature, uniforms=None):
+def run_main(kw, input_type, temperature, uniforms=None, seed_audio=None):
     """-> (float waveforms handed to save_wav, int16 wav files written, the mel)."""
     sys.path.insert(1, ROOT)
     from tacotron_wavenet_vocoder_korean_b200 import synth
@@ -84,6 +84,9 @@ def run_main(kw, input_type, temperature, uniforms=None):
     ref_gen.mu_law_decode = remember(ORIG['decode'])
     handed = []
     real_save = ref_gen.audio.save_wav
+    if seed_audio is not None:                   # --wav_seed: librosa.load / librosa.effects.trim are third party; the file content is given
+        ref_gen.librosa.load = lambda filename, sr=None, mono=True: (np.asarray(seed_audio, np.float32), sr)
+        ref_gen.audio.trim_silence = lambda wav, hp: wav
 
     def save_wav(wav, path, sr):
         handed.append(np.array(wav, copy=True))
@@ -102,6 +105,8 @@ def run_main(kw, input_type, temperature, uniforms=None):
         np.save(os.path.join(d, 'mel.npy'), mel)
         argv = ['generate.py', d, '--mel', os.path.join(d, 'mel.npy'), '--batch_size', str(N), '--logdir', os.path.join(d, 'out'),
                 '--temperature', str(temperature), '--gc_cardinality', str(kw['global_condition_cardinality']), '--gc_id', '1']
+        if seed_audio is not None:
+            argv += ['--wav_seed', os.path.join(d, 'seed.wav')]
         old = sys.argv
         sys.argv = argv
         np.random.seed(NUMPY_SEED)
@@ -131,6 +136,9 @@ def main():
     tf.global_variables = lambda: list(tf.S.variables.values())
     tf.train.Saver = lambda var_list=None: types.SimpleNamespace(restore=lambda sess, path: None)
     tf.train.get_checkpoint_state = lambda logdir: types.SimpleNamespace(model_checkpoint_path=logdir + '/model.ckpt-1234')
+    tf.size = lambda x: int(np.asarray(x).size)                 # create_seed (generate.py:101-103)
+    tf.constant = lambda v, *a, **k: v
+    tf.cond = lambda pred, a, b: a() if pred else b()
     sys.path.insert(0, REF)
     for m in ('utils', 'hparams', 'wavenet', 'generate'):
         sys.modules.pop(m, None)
@@ -150,6 +158,17 @@ def main():
         assert np.array_equal(mel, mel2)
         out[tag + '_wave'] = wav
         out[tag + '_pcm'] = pcm
+    # --wav_seed priming (generate.py:168-182): the first receptive_field samples of the seed are fed with zero local condition
+    rs = np.random.RandomState(14)
+    seed_audio = np.clip(0.4 * np.sin(np.arange(40) * 0.3) + 0.05 * rs.randn(40), -1, 1).astype(np.float32)
+    kw = synth.tiny_mol(2)
+    rf = 1 + sum(kw['dilations']) + kw['initial_filter_width'] - 1
+    u = np.random.RandomState(UNIFORM_SEED + 1).uniform(1e-5, 1 - 1e-5, (2, rf - 1 + T_MEL * 6, kw['out_channels'] // 3 + 1)).astype(np.float32)
+    wav, pcm, _ = run_main(kw, 'raw', 1.0, uniforms=u, seed_audio=seed_audio)
+    out.update(seed_audio=seed_audio, mol_seeded_wave=wav, mol_seeded_uniforms=u)
+    kw = dict(synth.tiny_mulaw(2), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8, global_condition_cardinality=3)
+    wav, pcm, _ = run_main(kw, 'mulaw-quantize', 1.0, seed_audio=seed_audio)
+    out['mulaw_seeded_wave'] = wav
     np.savez_compressed(os.path.join(HERE, 'ref_generate_main.npz'), numpy_seed=np.int64(NUMPY_SEED), **out)
     print({k: (v.shape, v.dtype) for k, v in out.items()})
     print(out['mol_wave'][:, :6], out['mulaw_t1_wave'][:, :6])

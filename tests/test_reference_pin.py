@@ -218,6 +218,34 @@ def test_oracle_reproduces_reference_generate_main_mulaw(tag, temperature):
     assert np.array_equal(ids.astype(np.int64), ref_ids)
 
 
+def test_oracle_reproduces_reference_generate_main_with_wav_seed():
+    """--wav_seed (generate.py:168-182): the first receptive_field samples of the seed prime the queues with ZERO local condition,
+    the last of them enters the main loop together with lc row 0.  In this repository's terms: forced = seed[:rf], n_forced = rf,
+    lc_shift = rf - 1, the first rf - 1 outputs are discarded."""
+    g = np.load(os.path.join(GOLD, 'ref_generate_main.npz'))
+    seed = g['seed_audio']
+    # scalar input: the priming steps draw (and discard) samples too, so they consume uniforms
+    kw = synth.tiny_mol(2)
+    om, lc, gc, _ = _generate_main_inputs(kw, g)
+    rf = oracle.receptive_field(2, kw['dilations'], True, kw['initial_filter_width'])
+    T = g['mol_seeded_wave'].shape[1]
+    forced = np.tile(seed[:rf][None], (2, 1))
+    out = om.generate(rf - 1 + T, forced, g['mol_seeded_uniforms'], lc_up=lc, lc_shift=rf - 1, gc_ids=gc)
+    assert np.abs(out[:, rf - 1:] - g['mol_seeded_wave']).max() < 1e-4
+    # one-hot input: mu_law_encode of the seed; np.random.choice is first called in the main loop
+    kw = MULAW_LC
+    Q = kw['quantization_channels']
+    om, lc, gc, rs = _generate_main_inputs(kw, g)
+    rf = oracle.receptive_field(2, kw['dilations'], False, kw['initial_filter_width'])
+    forced = np.tile(oracle.mu_law_encode(seed[:rf], Q).astype(np.float32)[None], (2, 1))
+    u = np.zeros((2, rf - 1 + T))
+    u[:, rf - 1:] = np.array([[rs.random_sample() for _ in range(2)] for _ in range(T)]).T
+    ids = om.generate(rf - 1 + T, forced, u, lc_up=lc, lc_shift=rf - 1, gc_ids=gc)[:, rf - 1:]
+    table = oracle.mu_law_decode(np.arange(Q, dtype=np.float32), Q)
+    wave = g['mulaw_seeded_wave']
+    assert np.array_equal(ids.astype(np.int64), np.abs(wave[:, :, None] - table[None, None, :]).argmin(-1))
+
+
 # ---- the CUDA path against the same reference-generated vectors ------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['ref_mol', 'ref_mulaw'])
