@@ -1,9 +1,13 @@
 # coding: utf-8
-"""The oracle and the CUDA path against golden vectors produced by THE REFERENCE'S OWN wavenet/model.py, mixture.py and
-ops.py, executed on a numpy TensorFlow stand-in (tests/golden/tf_numpy_shim.py, tests/golden/make_reference_goldens.py).
+"""The oracles, the host code and the CUDA path against golden vectors produced by THE REFERENCE'S OWN Python, executed
+unmodified on numpy TensorFlow stand-ins (tests/golden/tf_numpy_shim.py, tf_contrib_shim.py; one generating script per fixture,
+tests/golden/make_reference_*.py): wavenet/model.py + mixture.py + ops.py (incremental generation, add_loss for both heads,
+add_optimizer's plumbing), generate.py main() end to end (free-running and --wav_seed priming), the tacotron package and
+synthesizer.py load / synthesize end to end, the vocoder data feeder, utils/audio.py, text/korean.py, utils/__init__.py.
 This pins everything the reference's Python decides (wiring, variable names/shapes, queue order, conditioning alignment,
-sampling formulas, loss construction); TensorFlow's own kernels are restated in the stand-in, hence tolerances of a few
-float32 ulps of the logits instead of bit equality."""
+sampling formulas, loss construction, seeds, trimming, file naming); TensorFlow's own kernels are restated in the stand-ins,
+hence tolerances of a few float32 ulps on floating-point outputs; integer outputs (mu-law samples, token ids, feeder batches,
+frame counts) are compared for equality."""
 import os
 
 import numpy as np
