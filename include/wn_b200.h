@@ -61,6 +61,7 @@ typedef struct wn_config {
 
 #define WN_FLAG_GENERIC_KERNEL 1       /* never pick a compile-time specialised kernel instantiation */
 #define WN_FLAG_NO_DIE_AWARE 2         /* single-homed mailboxes (no die calibration); also env WN_NO_DIE_AWARE */
+#define WN_FLAG_NO_CLUSTER 4           /* never use the thread-block-cluster / DSMEM layer kernel; also env WN_NO_CLUSTER */
 
 /* Floating-point evaluation order implemented by the kernel (DESIGN.md "Pinned arithmetic").
  * Field meaning is identical to oracle/wn_oracle.c's orc_plan. */
@@ -80,6 +81,7 @@ typedef struct wn_info {
     int64_t kernel_launches;           /* kernels launched by this handle so far */
     int32_t static_shape;              /* 0: runtime-shaped kernel; 1: cfg2 shape, 2: cfg1 shape, 3: hparams.py default shape */
     int32_t die_aware;                 /* 1: mailboxes are dual-homed (one L2 copy per die), set by wn_finalize */
+    int32_t cluster_path;              /* 1: layer chain runs in 8-CTA clusters with DSMEM hops (set by wn_finalize) */
 } wn_info;
 
 typedef struct wn_handle wn_handle;

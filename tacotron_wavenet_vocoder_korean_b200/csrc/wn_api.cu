@@ -174,6 +174,13 @@ struct wn_handle {
     int smem_layer = 0, smem_tail = 0, smem_samp = 0, smem_launch = 0;
     const void *kernel = nullptr;
     const void *kernel_many = nullptr;     // variant used when >= kManyRows rows are in flight (or null)
+    // round-2 cluster path (wn_kernel_v2.cuh): layer chain in 8-CTA clusters + tail/sampler kernel on the SMs left over
+    bool v2_planned = false, v2 = false;
+    const void *kernel_v2_layers = nullptr, *kernel_v2_tail = nullptr;
+    int v2_grid_layers = 0, v2_smem_layers = 0, v2_smem_tail = 0;
+    cudaStream_t v2_sa = nullptr, v2_sb = nullptr;
+    cudaEvent_t v2_fork = nullptr, v2_join_a = nullptr, v2_join_b = nullptr;
+    std::string v2_note;
     DevBuf layer_img, tail_img, samp_img, gc_table, wc_onehot, upk, mbox, ring, ring_off, status;
     DevBuf prof, mb_tab;
     bool prof_on = false;
@@ -311,6 +318,11 @@ void wn_destroy(wn_handle *h)
                       &h->ring_off, &h->status, &h->prof, &h->mb_tab, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
                       &h->h_out, &h->h_logits};
     for (DevBuf *b : bufs) b->release();
+    if (h->v2_sa) cudaStreamDestroy(h->v2_sa);
+    if (h->v2_sb) cudaStreamDestroy(h->v2_sb);
+    if (h->v2_fork) cudaEventDestroy(h->v2_fork);
+    if (h->v2_join_a) cudaEventDestroy(h->v2_join_a);
+    if (h->v2_join_b) cudaEventDestroy(h->v2_join_b);
     delete h;
 }
 
@@ -458,11 +470,18 @@ static int plan_layout(wn_handle *h, int sm_count)
     // compile-time specialised instantiation, when the planned shapes coincide with one
     h->kernel = (const void *)wn_persistent_kernel;
     h->kernel_many = nullptr;
+    h->v2_planned = false;
     if (!(c.flags & WN_FLAG_GENERIC_KERNEL) && inf.weights_in_global == 0) {
         if (shape_matches<ShapeCfg2>(p)) {
             h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg2>;
             h->kernel_many = (const void *)wn_persistent_kernel_s<ShapeCfg2WS>;
             inf.static_shape = 1;
+            // cluster path: same plan, same mailboxes; needs ceil(L/2) clusters of 8 CTAs + Mt + 1 further SMs
+            h->v2_planned = !(c.flags & WN_FLAG_NO_CLUSTER) && !getenv("WN_NO_CLUSTER") &&
+                            V2L<ShapeCfg2>::total_floats(N) * 4 <= kMaxDynSmem && ((L + 1) / 2) * V2_CS + Mt + 1 <= sm_count;
+            h->v2_grid_layers = ((L + 1) / 2) * V2_CS;
+            h->v2_smem_layers = V2L<ShapeCfg2>::total_floats(N) * 4;
+            h->v2_smem_tail = std::max(h->smem_tail, h->smem_samp);
         }
         else if (shape_matches<ShapeCfg1>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg1>; inf.static_shape = 2; }
         else if (shape_matches<ShapeHparams>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeHparams>; inf.static_shape = 3; }
@@ -685,6 +704,39 @@ int wn_finalize(wn_handle *h)
     else if (h->info.static_shape == 3) CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel_s<ShapeHparams>, WN_NT, h->smem_launch));
     else CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wn_persistent_kernel, WN_NT, h->smem_launch));
     if ((long)occ * h->sm_count < grid) return fail(h, WN_ERR_CUDA, "cannot co-schedule %d CTAs (occupancy %d x %d SMs)", grid, occ, h->sm_count);
+    h->v2 = false;
+    h->info.cluster_path = 0;
+    if (h->v2_planned) {
+        h->kernel_v2_layers = (const void *)wn_layers_kernel_v2<ShapeCfg2>;
+        h->kernel_v2_tail = (const void *)wn_tail_kernel_v2<ShapeCfg2>;
+        cudaError_t e = cudaFuncSetAttribute(h->kernel_v2_layers, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_tail);
+        int n_clusters = 0;
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(h->v2_grid_layers);
+            lc.blockDim = dim3(V2_NT);
+            lc.dynamicSmemBytes = (size_t)h->v2_smem_layers;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = V2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            e = cudaOccupancyMaxActiveClusters(&n_clusters, h->kernel_v2_layers, &lc);
+        }
+        if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
+        else if (n_clusters * V2_CS < h->v2_grid_layers) h->v2_note = "cluster path disabled: only " + std::to_string(n_clusters) + " clusters of 8 are co-resident";
+        else {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = least priority (numerically greatest)
+            if (!h->v2_sa) e = cudaStreamCreateWithPriority(&h->v2_sa, cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess && !h->v2_sb) e = cudaStreamCreateWithPriority(&h->v2_sb, cudaStreamNonBlocking, lo);
+            if (e == cudaSuccess && !h->v2_fork) e = cudaEventCreateWithFlags(&h->v2_fork, cudaEventDisableTiming);
+            if (e == cudaSuccess && !h->v2_join_a) e = cudaEventCreateWithFlags(&h->v2_join_a, cudaEventDisableTiming);
+            if (e == cudaSuccess && !h->v2_join_b) e = cudaEventCreateWithFlags(&h->v2_join_b, cudaEventDisableTiming);
+            if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
+            else { h->v2 = true; h->info.cluster_path = 1; h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt + 1) + " tail CTAs"; }
+        }
+    }
     (void)St; (void)Sm;
     h->finalized = true;
     return WN_OK;
@@ -788,6 +840,21 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
         p.prof = (long long *)h->prof.p;
     }
     void *args[] = {&p};
+    if (h->v2) {
+        // kernel A (layer clusters) and kernel B (tail + sampler) run concurrently on two internal streams,
+        // forked from and joined back into the caller's stream
+        CUDA_TRY(h, cudaEventRecord(h->v2_fork, st));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sa, h->v2_fork, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sb, h->v2_fork, 0));
+        CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
+        CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_tail, dim3(p.Mt + 1), dim3(WN_NT), args, (size_t)h->v2_smem_tail, h->v2_sb));
+        CUDA_TRY(h, cudaEventRecord(h->v2_join_a, h->v2_sa));
+        CUDA_TRY(h, cudaEventRecord(h->v2_join_b, h->v2_sb));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->v2_join_a, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->v2_join_b, 0));
+        h->launches += 2;
+        return WN_OK;
+    }
     const void *fn = (h->kernel_many && a->rows >= kManyRows) ? h->kernel_many : h->kernel;
     CUDA_TRY(h, cudaLaunchCooperativeKernel(fn, dim3(p.grid), dim3(WN_NT), args, (size_t)h->smem_launch, st));
     h->launches++;

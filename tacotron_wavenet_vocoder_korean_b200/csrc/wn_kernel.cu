@@ -120,6 +120,16 @@ struct Prof {
     {
         if (slot) { long long now = clock64(); acc[phase] += now - last; last = now; }
     }
+    // accumulate a GPU-global nanosecond timestamp (low 40 bits): the difference of two CTAs' sums over the same steps
+    // is the mean latency between the two events (cross-SM, unlike clock64)
+    __device__ __forceinline__ void stamp(int idx)
+    {
+        if (slot) {
+            unsigned long long g;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+            acc[idx] += (long long)(g & 0xffffffffffULL);
+        }
+    }
     __device__ __forceinline__ void flush(bool writer = (threadIdx.x == 0))
     {
         if (slot && writer)
@@ -784,6 +794,7 @@ __device__ void sampler_role(const WnParams &p)
 
 #include "wn_kernel_static.cuh"
 #include "wn_kernel_ws.cuh"
+#include "wn_kernel_v2.cuh"
 
 // LL-mailbox ping-pong between CTA 0 and CTA 1: average round trip in clock cycles (diagnostic).
 __device__ void pingpong_role(u64 *box, int iters, long long *out)

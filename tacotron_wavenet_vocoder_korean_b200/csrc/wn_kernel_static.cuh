@@ -377,6 +377,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
             }
             if (__syncthreads_or(ab.flag)) return;
             pf.mark(0);
+            pf.stamp(10);
             {
                 float dot = butterfly<Post1::TPC>(dot_wreg<Post1::N4, Post1::U>(w1r, reinterpret_cast<const float4 *>(xc1)));
                 if (lead1) c1s[xp_c1] = relu32(fadd(b1v, dot));
@@ -387,6 +388,7 @@ __device__ void tail_role_s(const WnParams &p, int mt)
                 float dot = butterfly<Post2::TPC>(dot_wreg<Post2::N4, Post2::U>(w2r, reinterpret_cast<const float4 *>(xc2)));
                 if (lead2) ll_post(mb, dst0 + (size_t)b * Mt * O, dot, seq);
             }
+            pf.stamp(11);
             __syncthreads();
             pf.mark(2);
         }
@@ -492,6 +494,7 @@ __device__ void sampler_role_s(const WnParams &p)
             }
             if (__syncthreads_or(ab.flag)) return;
             pf.mark(0);
+            pf.stamp(10);
 
             float sample;
             if (SH::SCALAR) {
@@ -524,6 +527,7 @@ __device__ void sampler_role_s(const WnParams &p)
             if (tid == 0) p.out_samples[(size_t)b * p.T + t] = sample;
             if (has_next) feed(b, (t + 1 < p.n_forced) ? next_forced : sample, seq + 1u);
             else __syncthreads();
+            pf.stamp(11);
             pf.mark(2);
         }
     }

@@ -1,0 +1,661 @@
+// wn_kernel_v2.cuh -- round-2 layer kernel of the WaveNet sample loop: thread-block clusters + distributed shared memory.
+//
+// Why (profiles/r02_probe_cluster.md): a layer-to-layer hop through an L2 mailbox costs ~930 cycles in the live kernel,
+// the same 4-senders-to-4-receivers exchange through DSMEM (st.async + mbarrier complete_tx) ~510 including the combine.
+// B200 co-schedules at most 15 clusters of 8 CTAs (120 CTAs = 30 layers x M = 4; 16-CTA clusters: only 7), so
+//   * kernel A (this file, `wn_layers_kernel_v2`): 120 CTAs, cluster = 2 consecutive layers x 4 CTAs, 384 threads:
+//       CHAIN group (warps 8-11): wait input -> combine -> filter/gate from registers -> tanh*sigmoid -> partial dense from
+//         registers -> send.  Even layer -> odd layer: DSMEM.  Odd layer -> next cluster: LL mailbox in L2 (wn_kernel.cu).
+//       HELPER group (warps 0-7): dilation-ring push, skip 1x1 from REGISTERS + running skip sum, pre-activations of the
+//         next step (dilated tap + local condition) from shared memory.  The siblings' gated activations arrive by DSMEM.
+//   * kernel B (`wn_tail_kernel_v2`): the tail / sampler roles of wn_kernel_static.cuh on the 28 SMs the clusters cannot
+//       use, launched on a second stream; it talks to kernel A through the same L2 mailboxes as before.
+//
+// The evaluation plan (DESIGN.md "Pinned arithmetic") is IDENTICAL to wn_persistent_kernel_s<ShapeCfg2>: every dot
+// product is the same set of canonical 4-element fma chains combined by the same ascending butterfly, only the
+// assignment of chunks to lanes changed:
+//   filter/gate: lane = canonical chunk (k = 4*lane .. 4*lane+3), a warp owns 8 columns (4 channels x {filter, gate});
+//     ONE conflict-free LDS.128 of x per thread instead of 8 broadcast ones (256 -> 32 LSU wavefronts per row-step),
+//     partial sums are reduced with a transposing butterfly (9 shuffles, the first three levels halve the live values);
+//   dense: lane & 7 = canonical chunk of the CTA's 32 gated channels, 4 outputs per lane.
+// Included by wn_kernel.cu after wn_kernel_ws.cuh (uses its mbarrier helpers).
+#pragma once
+
+constexpr int V2_NT = 384;       // threads per layer CTA: 8 helper warps + 4 chain warps (<= 168 registers per thread)
+constexpr int V2_HALF = 256;     // helper threads (warps 0-7); the chain group is warps 8-11
+constexpr int V2_CHAIN = 128;
+constexpr int V2_CS = 8;         // CTAs per cluster: 2 layers x M = 4
+
+__device__ __forceinline__ unsigned v2_cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned v2_cluster_id()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t v2_mapa(uint32_t addr, unsigned rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void v2_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void v2_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 4-byte store into a peer CTA's shared memory; completes `bytes` on the peer's mbarrier when it lands
+__device__ __forceinline__ void v2_st_async(uint32_t raddr, float v, uint32_t rbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(__float_as_uint(v)),
+                 "r"(rbar)
+                 : "memory");
+}
+// named barrier over the 256 threads of one group, OR-reducing the abort flag
+__device__ __forceinline__ int v2_group_sync_or(int id, int flag)
+{
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "barrier.red.or.pred q, %2, 256, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(flag), "r"(id)
+        : "memory");
+    return r;
+}
+
+// 8 partial column sums per lane, lane = canonical chunk: returns the full sum of column (lane & 7) in every lane.
+// Level `off` of the ascending butterfly a[c] += a[c ^ off] (oracle mv_plan); at the first three levels each lane keeps
+// the columns whose index bit equals its lane bit and ships the others, so 4 + 2 + 1 shuffles instead of 3 x 8.
+__device__ __forceinline__ float v2_reduce8(const float (&v)[8], int lane)
+{
+    const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0, b2 = (lane & 4) != 0;
+    float n4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float keep = b0 ? v[2 * k + 1] : v[2 * k];
+        const float send = b0 ? v[2 * k] : v[2 * k + 1];
+        n4[k] = fadd(keep, __shfl_xor_sync(FULL, send, 1));
+    }
+    float n2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float keep = b1 ? n4[2 * q + 1] : n4[2 * q];
+        const float send = b1 ? n4[2 * q] : n4[2 * q + 1];
+        n2[q] = fadd(keep, __shfl_xor_sync(FULL, send, 2));
+    }
+    const float keep = b2 ? n2[1] : n2[0];
+    const float send = b2 ? n2[0] : n2[1];
+    float r = fadd(keep, __shfl_xor_sync(FULL, send, 4));
+    r = fadd(r, __shfl_xor_sync(FULL, r, 8));
+    r = fadd(r, __shfl_xor_sync(FULL, r, 16));
+    return r;
+}
+// 4 partial sums per lane over 8 lanes (lane & 7 = canonical chunk): full sum of value (lane & 3) in every lane
+__device__ __forceinline__ float v2_reduce4(const float (&v)[4], int lane)
+{
+    const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+    float n2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float keep = b0 ? v[2 * q + 1] : v[2 * q];
+        const float send = b0 ? v[2 * q] : v[2 * q + 1];
+        n2[q] = fadd(keep, __shfl_xor_sync(FULL, send, 1));
+    }
+    const float keep = b1 ? n2[1] : n2[0];
+    const float send = b1 ? n2[0] : n2[1];
+    float r = fadd(keep, __shfl_xor_sync(FULL, send, 2));
+    r = fadd(r, __shfl_xor_sync(FULL, r, 4));
+    return r;
+}
+
+// shared-memory layout of a v2 layer CTA, in floats from g_smem
+template <class SH>
+struct V2L {
+    using Cur = typename SH::Cur;
+    using Lc = typename SH::Lc;
+    using Gc = typename SH::Gc;
+    using Skip = typename SH::Skip;
+    static constexpr int BIAS = 2 * SH::Dm + SH::R + SH::Sm;                 // bfg | bd | bs
+    static constexpr int WOLD = Cur::NPASS * Cur::CH * WN_NT, WLC = Lc::NPASS * Lc::CH * WN_NT, WGC = Gc::NPASS * Gc::CH * WN_NT;
+    static constexpr int OFF_BFG = 0, OFF_BD = 2 * SH::Dm, OFF_BS = OFF_BD + SH::R;
+    static constexpr int OFF_WOLD = BIAS, OFF_WLC = OFF_WOLD + WOLD, OFF_WGC = OFF_WLC + WLC;
+    static constexpr int OFF_XS = OFF_WGC + WGC;                              // chain: layer input of the row in flight
+    static constexpr int XSH = SH::R / 2 + 4;                                 // K-half stride of xs: the two halves fall in different banks
+    static constexpr int OFF_ZS = OFF_XS + 2 * XSH;                           // chain: own gated slice for the dense (2 buffers)
+    static constexpr int OFF_XSOLD = OFF_ZS + 2 * SH::Dm;                     // helper: dilated tap, padded for Cur
+    static constexpr int OFF_LCS = OFF_XSOLD + Cur::TPC * Cur::XS;            // helper: lc row, padded for Lc
+    static constexpr int OFF_GVEC = OFF_LCS + Lc::TPC * Lc::XS;               // prologue: speaker embedding
+    static constexpr int OFF_BAR = (OFF_GVEC + Gc::TPC * Gc::XS + 3) & ~3;    // mbarriers (8 B each): 5 x 32 rows + image
+    static constexpr int OFF_ROWS = OFF_BAR + 2 * (5 * WN_MAX_BATCH + 2);
+    // per row
+    static constexpr int ZF = Skip::TPC * Skip::XS;                           // full gated vector, padded for Skip
+    static constexpr int R_INX = 0;                                            // [M][R] partial inputs (DSMEM inbox)
+    static constexpr int R_Z = SH::M * SH::R;                                  // [ZF]
+    static constexpr int R_ACC = R_Z + ZF;                                     // [Sm] running skip sum of layer l-1
+    static constexpr int R_XRAW = R_ACC + SH::Sm;                              // [R] combined layer input
+    static constexpr int R_PRE = R_XRAW + SH::R;                               // [2 Dm] pre-activations of the next step
+    static constexpr int R_BFGN = R_PRE + 2 * SH::Dm;                          // [2 Dm] bias + speaker contribution
+    static constexpr int ROWF = R_BFGN + 2 * SH::Dm;
+    __host__ __device__ static constexpr int total_floats(int n_rows) { return OFF_ROWS + n_rows * ROWF; }
+};
+
+template <int N4>
+__device__ __forceinline__ void v2_load_wreg(float4 (&wv)[N4], const float *packed_base, int slot)
+{
+    const float4 *w4 = reinterpret_cast<const float4 *>(packed_base) + slot;
+#pragma unroll
+    for (int i = 0; i < N4; ++i) wv[i] = __ldg(w4 + (size_t)i * WN_NT);
+}
+
+// ---- bounded waits whose state lives in registers ---------------------------------------------------------------
+// (wn_kernel.cu's watchdog_check takes its state by reference into a noinline function, which pins it to local memory
+//  and puts an LDL in front of every barrier.)  Returns the (initialised) start time, or -1 when the launch is aborting.
+__device__ __noinline__ long long v2_watchdog(int32_t *status, long long t0)
+{
+    if (t0 == 0) t0 = clock64();
+    if (ld_volatile_i32(status) != 0) return -1;
+    if (clock64() - t0 > WATCHDOG_CYCLES) {
+        if (atomicCAS(status, 0, 1) == 0) { status[1] = 1000 + (int)blockIdx.x; status[2] = (int)threadIdx.x; }
+        return -1;
+    }
+    return t0;
+}
+struct V2Ab {
+    int32_t *status;
+    int dead;          // this thread has seen the abort: every later wait falls through (the data is garbage from then on)
+};
+__device__ __forceinline__ void v2_mbar_wait(uint64_t *bar, unsigned parity, V2Ab &ab)
+{
+    if (mbar_try(bar, parity) || ab.dead) return;
+    unsigned spins = 0;
+    long long t0 = 0;
+    while (!mbar_try(bar, parity)) {
+        if (((++spins) & 0xffu) == 0) {
+            t0 = v2_watchdog(ab.status, t0);
+            if (t0 < 0) { ab.dead = 1; break; }
+        }
+    }
+}
+__device__ __forceinline__ float v2_ll_wait(const MBox &mb, const u64 *logical, unsigned seq, V2Ab &ab)
+{
+    const u64 *p = mb.rd(logical);
+    u64 v = ld_relaxed_u64(p);
+    unsigned spins = 0;
+    long long t0 = 0;
+    while ((unsigned)(v >> 32) != seq && !ab.dead) {
+        if (((++spins) & 0x3ffu) == 0) {
+            t0 = v2_watchdog(ab.status, t0);
+            if (t0 < 0) { ab.dead = 1; break; }
+        }
+        v = ld_relaxed_u64(p);
+    }
+    return __uint_as_float((unsigned)v);
+}
+// n (<= 4) words p[i*stride], loads issued together
+__device__ __forceinline__ void v2_ll_wait_n(const MBox &mb, const u64 *logical, size_t stride, int n, unsigned seq, V2Ab &ab, float *out)
+{
+    const u64 *pp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pp[i] = (i < n) ? mb.rd(logical + i * stride) : nullptr;
+    u64 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (i < n) ? ld_relaxed_u64(pp[i]) : ((u64)seq << 32);
+    unsigned spins = 0;
+    long long t0 = 0;
+    while (!ab.dead) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ok = ok && ((unsigned)(v[i] >> 32) == seq);
+        if (ok) break;
+        if (((++spins) & 0x3ffu) == 0) {
+            t0 = v2_watchdog(ab.status, t0);
+            if (t0 < 0) { ab.dead = 1; break; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n && (unsigned)(v[i] >> 32) != seq) v[i] = ld_relaxed_u64(pp[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = __uint_as_float((unsigned)v[i]);
+}
+// plain named barrier over the 256-thread helper group
+__device__ __forceinline__ void v2_group_sync(int id)
+{
+    asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+}
+// the 128-thread chain group: barrier 1
+__device__ __forceinline__ void v2_chain_sync()
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+__device__ __forceinline__ int v2_chain_sync_or(int flag)
+{
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "barrier.red.or.pred q, 1, 128, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(flag)
+        : "memory");
+    return r;
+}
+
+template <class SH>
+__device__ void layer_role_v2(const WnParams &p, const int l, const int m)
+{
+    using Cur = typename SH::Cur;        // packed for 256 slots: col = slot / 4, chunk = slot % 4, 8 float4
+    using Lc = typename SH::Lc;
+    using Gc = typename SH::Gc;
+    using Dense = typename SH::Dense;    // col = slot / 2, chunk = slot % 2, 4 float4
+    using Skip = typename SH::Skip;      // col = slot / 2, chunk = slot % 2, 16 float4
+    using LY = V2L<SH>;
+    static_assert(Cur::TPC == 4 && Cur::N4 == 8 && Cur::U == 8 && Cur::NPASS == 1, "v2 mapping assumes the cfg-2 fg shape");
+    static_assert(Dense::TPC == 2 && Dense::N4 == 4 && Dense::U == 4 && Dense::NPASS == 1, "v2 mapping assumes the cfg-2 dense shape");
+    static_assert(Skip::TPC == 2 && Skip::NPASS == 1 && Lc::TPC == 4 && Gc::TPC == 4, "v2 mapping assumes the cfg-2 shapes");
+    constexpr int R = SH::R, M = SH::M, Dm = SH::Dm, Sm = SH::Sm, D = SH::D, ncol2 = 2 * SH::Dm;
+    static_assert(R == 128 && D == 128 && Sm == 128 && M == 4 && Dm == 32, "v2 mapping: 128-wide vectors, 4 CTAs per layer");
+    static_assert(SH::SCALAR, "v2 layer kernel is instantiated for scalar-input models");
+
+    float *smem = g_smem;
+    const int tid = threadIdx.x;
+    const int N = p.N, L = p.L;
+    const int cta = l * M + m;
+    const float *gimg = p.layer_img + (size_t)cta * p.layer_img_floats;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + LY::OFF_BAR);
+    uint64_t *xbar = bars, *zbar = bars + WN_MAX_BATCH, *abar = bars + 2 * WN_MAX_BATCH, *fullb = bars + 3 * WN_MAX_BATCH,
+             *prdy = bars + 4 * WN_MAX_BATCH, *ldbar = bars + 5 * WN_MAX_BATCH;
+    float *rows = smem + LY::OFF_ROWS;
+
+    const unsigned lbase = (unsigned)(l & 1) * 4u;            // cluster rank of this layer's CTA 0
+    const bool in_dsmem = (l & 1) == 1;                       // odd layers are fed by their cluster mate
+    const bool out_dsmem = (l & 1) == 0 && l + 1 < L;
+    const bool has_next_layer = l + 1 < L;
+
+    // ---- barriers, resident image (TMA bulk copies), scratch --------------------------------------------------
+    if (tid == 0) {
+        for (int b = 0; b < WN_MAX_BATCH; ++b) {
+            mbar_init(&xbar[b], 1); mbar_init(&zbar[b], 1); mbar_init(&abar[b], 1); mbar_init(&fullb[b], 1); mbar_init(&prdy[b], 1);
+        }
+        mbar_init(ldbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes1 = (uint32_t)LY::BIAS * 4u, bytes2 = (uint32_t)(LY::WOLD + LY::WLC + LY::WGC) * 4u;
+        v2_expect_tx(ldbar, bytes1 + bytes2);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                     "l"(gimg + p.off_bfg), "r"(bytes1), "r"(smem_u32(ldbar))
+                     : "memory");
+        const uint32_t CHK = 30720u;
+        for (uint32_t o = 0; o < bytes2; o += CHK) {
+            const uint32_t sz = (bytes2 - o < CHK) ? (bytes2 - o) : CHK;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32((const char *)(smem + LY::OFF_WOLD) + o)),
+                         "l"((const char *)(gimg + p.old.off) + o), "r"(sz), "r"(smem_u32(ldbar))
+                         : "memory");
+        }
+    }
+    for (int i = LY::OFF_XS + tid; i < LY::OFF_BAR; i += V2_NT) smem[i] = 0.0f;
+    for (int i = tid; i < N * LY::ROWF; i += V2_NT) rows[i] = 0.0f;
+    while (!mbar_try(ldbar, 0)) {}
+    __syncthreads();
+    if (tid == 0) {
+        for (int b = 0; b < N; ++b) {
+            if (in_dsmem) v2_expect_tx(&xbar[b], (uint32_t)(M * R * 4));
+            v2_expect_tx(&zbar[b], (uint32_t)((M - 1) * Dm * 4));
+            if (in_dsmem) v2_expect_tx(&abar[b], (uint32_t)(Sm * 4));
+        }
+    }
+    // every CTA of the cluster has initialised and armed its barriers before anyone stores into a peer
+    v2_cluster_sync();
+
+    const float *bfg = smem + LY::OFF_BFG, *bd = smem + LY::OFF_BD, *bs = smem + LY::OFF_BS;
+    float *xs = smem + LY::OFF_XS, *zs = smem + LY::OFF_ZS, *xs_old = smem + LY::OFF_XSOLD, *lcs = smem + LY::OFF_LCS,
+          *gvec = smem + LY::OFF_GVEC;
+    const float *w_old_s = smem + LY::OFF_WOLD, *w_lc_s = smem + LY::OFF_WLC, *w_gc_s = smem + LY::OFF_WGC;
+
+    const int d = p.dil[l];
+    const int nin = (l == 0) ? 1 : M;
+    float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
+    V2Ab ab{p.status, 0};
+    const MBox mb = make_mbox(p);
+    const size_t rowx = (size_t)L * M * R, rowa = (size_t)L * M * Sm;
+
+    if (tid < V2_HALF) {
+        // =========================== HELPER group (warps 0-7) ===================================================
+        const int ht = tid;
+        const int c4 = ht & 3, c2 = ht & 1;
+        const int grp4 = ht >> 2, col2 = ht >> 1;
+        const bool lead4 = c4 == 0, lead2 = c2 == 0;
+        const float *xc_old = xs_old + c4 * Cur::XS;
+        const float *xc_lc = lcs + c4 * Lc::XS;
+        const float *xc_gc = gvec + c4 * Gc::XS;
+        const float *w_old = w_old_s + ht * 4, *w_lc = w_lc_s + ht * 4, *w_gc = w_gc_s + ht * 4;
+        const int xp_x = (ht < R) ? Cur::xpad(ht) : 0;
+        const int xp_lc = (SH::HAS_LC && ht < SH::C) ? Lc::xpad(ht) : 0;
+        float4 wsk[Skip::N4];                                   // skip 1x1 slice: 64 registers, resident
+        v2_load_wreg<Skip::N4>(wsk, gimg + p.skip.off, ht);
+        const float bsv = bs[col2];
+        Prof hp((p.prof && ht == 0) ? p.prof + (size_t)cta * 16 : nullptr);
+
+        // ---- prologue: speaker contribution folded into the biases, pre-activations for t = 0 ------------------
+        for (int b = 0; b < N; ++b) {
+            float *rb = rows + (size_t)b * LY::ROWF;
+            float *bfgN = rb + LY::R_BFGN, *pre_b = rb + LY::R_PRE;
+            if (SH::HAS_GC) {
+                if (ht < SH::G) gvec[Gc::xpad(ht)] = __ldg(p.gc_table + (size_t)p.gc_id[b] * SH::G + ht);
+                v2_group_sync(2);
+                matvec_s<Gc>(w_gc, xc_gc, grp4, lead4, ncol2, [&](int col, float dot) { bfgN[col] = fadd(bfg[col], dot); });
+            } else {
+                if (ht < ncol2) bfgN[ht] = bfg[ht];
+            }
+            v2_group_sync(2);
+            // dilated tap = zeros, lc = zeros at t = 0 (xs_old / lcs are zero-initialised)
+            matvec_s<Cur>(w_old, xc_old, grp4, lead4, ncol2, [&](int col, float dot) { pre_b[col] = fadd(bfgN[col], dot); });
+            if (SH::HAS_LC) {
+                v2_group_sync(2);
+                matvec_s<Lc>(w_lc, xc_lc, grp4, lead4, ncol2, [&](int col, float dot) { pre_b[col] = fadd(pre_b[col], dot); });
+            }
+            v2_group_sync(2);
+        }
+        if (ht == 0)
+            for (int b = 0; b < N; ++b) mbar_arrive(&prdy[b]);           // phase 0: pre for t = 0 is ready
+
+        // acc hand-over to layer l+1, CTA m: DSMEM inside the cluster, LL mailbox otherwise (and to the tail)
+        const u64 *mba_in = p.mb_acc + ((size_t)(l > 0 ? l - 1 : 0) * M + m) * Sm + col2;
+        const u64 *mba_out = p.mb_acc + ((size_t)l * M + m) * Sm + col2;
+        const uint32_t r_acc = v2_mapa(smem_u32(rows + LY::R_ACC + col2), 4u + (unsigned)m);
+        const uint32_t r_abar = v2_mapa(smem_u32(&abar[0]), 4u + (unsigned)m);
+        const float4 *xc_skip = reinterpret_cast<const float4 *>(rows + LY::R_Z + c2 * Skip::XS);
+
+        for (int t = 0; t < p.T; ++t) {
+            // abort is agreed on by the whole group, at a step boundary (every 16th, to keep it off the per-row path)
+            if ((t & 15) == 0 && v2_group_sync_or(2, ab.dead)) break;
+            const unsigned seq = (unsigned)t + 1u;
+            const unsigned par = (unsigned)t & 1u;
+            for (int b = 0; b < N; ++b) {
+                if (t >= p.T_row[b]) continue;
+                hp.start();
+                float *rb = rows + (size_t)b * LY::ROWF;
+                const bool has_next = (t + 1 < p.T_row[b]);
+                MDst da{nullptr, nullptr};
+                if (!out_dsmem) da = mb_dst(mb, mba_out + b * rowa);
+                // early loads for the next step's pre-activations (independent of this step's x unless d == 1)
+                float oldv = 0.0f, lcv = 0.0f;
+                if (has_next && d >= 2 && ht < R) oldv = __ldcg(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);
+                if (SH::HAS_LC && has_next && ht < SH::C) {
+                    long idx = (long)t - p.lc_shift;
+                    if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) lcv = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
+                }
+                pin(oldv); pin(lcv);
+                v2_mbar_wait(&fullb[b], par, ab);                       // x and the own z slice of (b, t) are in rows[b]
+                hp.mark(7);
+                if (ht < R) {
+                    const float xme = rb[LY::R_XRAW + ht];
+                    if (d >= 2) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + ht, xme);
+                    if (d == 1) oldv = xme;
+                    xs_old[xp_x] = oldv;
+                }
+                if (SH::HAS_LC && ht < SH::C) lcs[xp_lc] = lcv;
+                v2_mbar_wait(&zbar[b], par, ab);                        // the three siblings' slices have landed
+                if (ht == 0) v2_expect_tx(&zbar[b], (uint32_t)((M - 1) * Dm * 4));
+                v2_group_sync(2);
+                hp.mark(8);
+                // skip 1x1 column col2 over K half c2, from registers, + running skip sum
+                {
+                    const float4 *zc = xc_skip + (size_t)b * (LY::ROWF / 4);
+                    constexpr int PER = Skip::N4 / Skip::U;
+                    float acc[Skip::U];
+#pragma unroll
+                    for (int u = 0; u < Skip::U; ++u) {
+                        float a = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < PER; ++i) {
+                            const float4 ww = wsk[u * PER + i], xx = zc[u * PER + i];
+                            a = ffma(ww.x, xx.x, a);
+                            a = ffma(ww.y, xx.y, a);
+                            a = ffma(ww.z, xx.z, a);
+                            a = ffma(ww.w, xx.w, a);
+                        }
+                        acc[u] = a;
+                    }
+#pragma unroll
+                    for (int off = 1; off < Skip::U; off <<= 1)
+#pragma unroll
+                        for (int c = 0; c < Skip::U; c += 2 * off) acc[c] = fadd(acc[c], acc[c + off]);
+                    const float dsk = butterfly<2>(acc[0]);
+                    if (lead2) {
+                        float v = fadd(bsv, dsk);
+                        if (l > 0) {
+                            float a;
+                            if (in_dsmem) {
+                                v2_mbar_wait(&abar[b], par, ab);
+                                a = rb[LY::R_ACC + col2];
+                            } else {
+                                a = v2_ll_wait(mb, mba_in + b * rowa, seq, ab);
+                            }
+                            v = fadd(a, v);
+                        }
+                        if (out_dsmem) v2_st_async(r_acc + (uint32_t)b * (LY::ROWF * 4), v, r_abar + (uint32_t)b * 8u);
+                        else ll_post(da, v, seq);
+                    }
+                }
+                hp.mark(9);
+                // pre-activations of the next step: (bias(+gc) + W_old . x_l(t+1-d)) + W_lc . lc(t)
+                if (has_next) {
+                    float *pre_b = rb + LY::R_PRE;
+                    const float *bias_b = rb + LY::R_BFGN;
+                    float pv = butterfly<4>(dot_regs<Cur::N4, Cur::U>(reinterpret_cast<const float4 *>(w_old), reinterpret_cast<const float4 *>(xc_old)));
+                    pv = fadd(bias_b[grp4], pv);
+                    if (SH::HAS_LC)
+                        pv = fadd(pv, butterfly<4>(dot_regs<Lc::N4, Lc::U>(reinterpret_cast<const float4 *>(w_lc), reinterpret_cast<const float4 *>(xc_lc))));
+                    if (lead4) pre_b[grp4] = pv;
+                }
+                v2_group_sync(2);
+                // all lead2 threads are past their abar wait: re-arm it for the next step
+                if (ht == 0) {
+                    if (in_dsmem) v2_expect_tx(&abar[b], (uint32_t)(Sm * 4));
+                    mbar_arrive(&prdy[b]);                               // pre[b] for t+1 written, rows[b] free
+                }
+                hp.mark(10);
+            }
+        }
+        if (p.prof && ht == 0)
+            for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[i];
+    } else {
+        // =========================== CHAIN group (warps 8-11) ===================================================
+        // "Fat" threads, one warp per SM sub-partition: thread = (filter/gate column c, K half) holds 64 weights of the
+        // current tap and evaluates canonical chunks khalf*16 .. khalf*16+15 (in-thread tree, ONE shuffle level);
+        // for the dense 1x1 thread = output r over the CTA's whole 32-channel slice (8 canonical chunks, no shuffle).
+        const int ct = tid - V2_HALF;
+        const int c = ct >> 1, khalf = ct & 1;                       // column c = 2*j + gate
+        const bool gate = (c & 1) != 0;
+        const int zj = c >> 1;                                       // gated channel inside the CTA
+        float4 wfg[16];
+        {
+            // packed slot (wn_params.h, Cur: TPC 4, 8 float4): col*4 + k/32, float4 index (k%32)/4
+            const float4 *pk = reinterpret_cast<const float4 *>(gimg + p.cur.off);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wfg[i] = __ldg(pk + (size_t)(i & 7) * WN_NT + c * 4 + khalf * 2 + (i >> 3));
+        }
+        float4 wdn[8];
+        {
+            // Dense: TPC 2, 4 float4: slot r*2 + k/16, float4 index (k%16)/4
+            const float4 *pd = reinterpret_cast<const float4 *>(gimg + p.dense.off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wdn[i] = __ldg(pd + (size_t)(i & 3) * WN_NT + ct * 2 + (i >> 2));
+        }
+        const float4 *xh4 = reinterpret_cast<const float4 *>(xs + khalf * LY::XSH);
+        const int xp = (ct >> 6) * LY::XSH + (ct & 63);              // where combined input ct goes in xs
+        // z hand-over: of the four threads that hold z_j, thread q = 0 keeps it, q = 1..3 ship it to sibling (m + q) & 3
+        const unsigned zq = (unsigned)ct & 3u;
+        const int zidx = Skip::xpad(m * Dm + zj);
+        const uint32_t r_z = v2_mapa(smem_u32(rows + LY::R_Z + zidx), lbase + (((unsigned)m + zq) & 3u));
+        const uint32_t r_zbar = v2_mapa(smem_u32(&zbar[0]), lbase + (((unsigned)m + zq) & 3u));
+        const float bdv = bd[ct];
+        uint32_t r_x[4], r_xb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            r_x[k] = v2_mapa(smem_u32(rows + LY::R_INX + m * R + ct), 4u + (unsigned)k);
+            r_xb[k] = v2_mapa(smem_u32(&xbar[0]), 4u + (unsigned)k);
+        }
+        const u64 *mbx_in = p.mb_x + ((size_t)l * M) * R + ct;
+        const u64 *mbx_out = p.mb_x + ((size_t)(l + 1) * M + m) * R + ct;
+        Prof pf((p.prof && ct == 0) ? p.prof + (size_t)cta * 16 : nullptr);
+        unsigned item = 0;                                           // parity selects the zs buffer
+
+        for (int t = 0; t < p.T; ++t) {
+            if ((t & 15) == 0 && v2_chain_sync_or(ab.dead)) break;
+            const unsigned seq = (unsigned)t + 1u;
+            const unsigned par = (unsigned)t & 1u;
+            for (int b = 0; b < N; ++b) {
+                if (t >= p.T_row[b]) continue;
+                pf.start();
+                float *rb = rows + (size_t)b * LY::ROWF;
+                float *zsb = zs + (item & 1u) * Dm;
+                ++item;
+                MDst dx{nullptr, nullptr};
+                if (has_next_layer && !out_dsmem) dx = mb_dst(mb, mbx_out + b * rowx);
+                v2_mbar_wait(&prdy[b], par, ab);                       // pre[b] of this step written, rows[b] free
+                const float pre_v = rb[LY::R_PRE + c];
+                // 1. layer input r = ct: sum of the partial residual outputs of layer l-1
+                {
+                    float v;
+                    if (in_dsmem) {
+                        v2_mbar_wait(&xbar[b], par, ab);
+                        pf.mark(0);
+                        pf.stamp(10);
+                        const float *in = rb + LY::R_INX + ct;
+                        v = fadd(fadd(fadd(in[0], in[R]), in[2 * R]), in[3 * R]);
+                    } else {
+                        float q[4];
+                        v2_ll_wait_n(mb, mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
+                        pf.mark(0);
+                        pf.stamp(10);
+                        v = q[0];
+#pragma unroll
+                        for (int i = 1; i < 4; ++i)
+                            if (i < nin) v = fadd(v, q[i]);
+                    }
+                    xs[xp] = v;
+                    rb[LY::R_XRAW + ct] = v;
+                }
+                pf.mark(1);
+                v2_chain_sync();
+                if (in_dsmem && ct == 0) v2_expect_tx(&xbar[b], (uint32_t)(M * R * 4));     // every reader is past its wait
+                pf.mark(2);
+                // 2. current-tap filter/gate column over one K half, from registers; gated activation
+                {
+                    float acc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 xv = xh4[i];
+                        float a = 0.0f;
+                        a = ffma(wfg[i].x, xv.x, a);
+                        a = ffma(wfg[i].y, xv.y, a);
+                        a = ffma(wfg[i].z, xv.z, a);
+                        a = ffma(wfg[i].w, xv.w, a);
+                        acc[i] = a;
+                    }
+#pragma unroll
+                    for (int off = 1; off < 16; off <<= 1)
+#pragma unroll
+                        for (int k = 0; k < 16; k += 2 * off) acc[k] = fadd(acc[k], acc[k + off]);
+                    const float dot = fadd(acc[0], __shfl_xor_sync(FULL, acc[0], 1));
+                    pf.mark(3);
+                    const float a = act_fg(fadd(pre_v, dot), gate);
+                    const float o = __shfl_xor_sync(FULL, a, 2);
+                    const float z = gate ? fmul(o, a) : fmul(a, o);
+                    if (zq == 0) {
+                        zsb[zj] = z;
+                        rb[LY::R_Z + zidx] = z;
+                    } else {
+                        v2_st_async(r_z + (uint32_t)b * (LY::ROWF * 4), z, r_zbar + (uint32_t)b * 8u);
+                    }
+                }
+                pf.mark(4);
+                v2_chain_sync();
+                if (!has_next_layer && ct == 0) mbar_arrive(&fullb[b]);   // last layer: its helper (skip -> tail) is on the sample chain
+                pf.mark(5);
+                // 3. partial dense 1x1, output r = ct over the CTA's 32 gated channels, + residual -> layer l+1
+                if (has_next_layer) {
+                    const float4 *z4 = reinterpret_cast<const float4 *>(zsb);
+                    const float xres = rb[LY::R_XRAW + ct];
+                    float acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 zv = z4[i];
+                        float a = 0.0f;
+                        a = ffma(wdn[i].x, zv.x, a);
+                        a = ffma(wdn[i].y, zv.y, a);
+                        a = ffma(wdn[i].z, zv.z, a);
+                        a = ffma(wdn[i].w, zv.w, a);
+                        acc[i] = a;
+                    }
+#pragma unroll
+                    for (int off = 1; off < 8; off <<= 1)
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2 * off) acc[k] = fadd(acc[k], acc[k + off]);
+                    const float v = (m == 0) ? fadd(fadd(xres, bdv), acc[0]) : acc[0];
+                    if (out_dsmem) {
+                        const uint32_t ro = (uint32_t)b * (LY::ROWF * 4), bo = (uint32_t)b * 8u;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v2_st_async(r_x[k] + ro, v, r_xb[k] + bo);
+                    } else {
+                        ll_post(dx, v, seq);
+                    }
+                    // the helper streams 50 KB of shared memory per row: release it only after the dense has read its operands
+                    __syncwarp();
+                    if (ct == 0) mbar_arrive(&fullb[b]);
+                }
+                pf.stamp(11);
+                pf.mark(6);
+            }
+        }
+        if (p.prof && ct == 0) {
+            for (int i = 0; i < 7; ++i) p.prof[(size_t)cta * 16 + i] = pf.acc[i];
+            p.prof[(size_t)cta * 16 + 14] = pf.acc[10];
+            p.prof[(size_t)cta * 16 + 15] = pf.acc[11];
+        }
+    }
+    // no CTA of the cluster leaves while a peer may still store into its shared memory
+    __syncthreads();
+    v2_cluster_sync();
+}
+
+// Kernel A: the layer chain.  grid = 8 * ceil(L / 2), cluster of 8 = layers 2c and 2c+1.
+template <class SH>
+__global__ void __cluster_dims__(V2_CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers_kernel_v2(const __grid_constant__ WnParams p)
+{
+    const unsigned crank = v2_cluster_ctarank();
+    const int l = (int)v2_cluster_id() * 2 + (int)(crank >> 2), m = (int)(crank & 3u);
+    if (l < p.L) {
+        layer_role_v2<SH>(p, l, m);
+    } else {
+        v2_cluster_sync();
+        __syncthreads();
+        v2_cluster_sync();
+    }
+}
+
+// Kernel B: tail + sampler roles (wn_kernel_static.cuh) on the SMs the clusters leave free.
+template <class SH>
+__global__ void __launch_bounds__(WN_NT, 1) wn_tail_kernel_v2(const __grid_constant__ WnParams p)
+{
+    const int cta = (int)blockIdx.x;
+    if (cta < SH::Mt) tail_role_s<SH>(p, cta);
+    else sampler_role_s<SH>(p);
+}
