@@ -62,6 +62,8 @@ typedef struct wn_config {
 #define WN_FLAG_GENERIC_KERNEL 1       /* never pick a compile-time specialised kernel instantiation */
 #define WN_FLAG_NO_DIE_AWARE 2         /* single-homed mailboxes (no die calibration); also env WN_NO_DIE_AWARE */
 #define WN_FLAG_NO_CLUSTER 4           /* never use the thread-block-cluster / DSMEM layer kernel; also env WN_NO_CLUSTER */
+#define WN_FLAG_FAST_ACT 8             /* scalar-input (mixture-of-logistics) models on the cluster path: tanh / sigmoid through
+                                          ex2.approx + rcp.approx (logits within 1e-4 of the pinned arithmetic, not bit-identical) */
 
 /* Floating-point evaluation order implemented by the kernel (DESIGN.md "Pinned arithmetic").
  * Field meaning is identical to oracle/wn_oracle.c's orc_plan. */
@@ -82,6 +84,7 @@ typedef struct wn_info {
     int32_t static_shape;              /* 0: runtime-shaped kernel; 1: cfg2 shape, 2: cfg1 shape, 3: hparams.py default shape */
     int32_t die_aware;                 /* 1: mailboxes are dual-homed (one L2 copy per die), set by wn_finalize */
     int32_t cluster_path;              /* 1: layer chain runs in 8-CTA clusters with DSMEM hops (set by wn_finalize) */
+    int32_t fast_act;                  /* 1: WN_FLAG_FAST_ACT is in effect */
 } wn_info;
 
 typedef struct wn_handle wn_handle;

@@ -54,13 +54,31 @@ def main():
     print('ragged rows equal:', all(torch.equal(sa[r, :t], sb[r, :t]) for r, t in enumerate(T_row)))
     if mode == 'check':
         return
+    if mode == 'time':
+        T = 2000
+        kw16 = synth.cfg2(16)
+        inp = make_inputs(kw16, T)
+        a16 = build(kw16)
+        lc = a16.create_upsample(inp['mel'])
+        for rows in (1, 6, 8, 12, 16):
+            ms = min(timed(a16, T, inp, lc, rows) for _ in range(2))
+            print('v2 rows=%2d: %.2f us/step  %.1f k samples/s' % (rows, 1e3 * ms / T, rows * T / ms))
+        return
     T = 3000
     kw16 = synth.cfg2(16)
     inp = make_inputs(kw16, T)
     a16, b16 = build(kw16), build(kw16, cluster=False)
     lc = a16.create_upsample(inp['mel'])
+    f16 = build(kw16, fast_act=True)
+    print('info fast:', f16.info())
+    # fast activation: teacher-forced logits against the pinned arithmetic (tolerance of north_star: 1e-4)
+    Tt = 1200
+    fa = f16.generate(Tt, inp['forced_full'][:4, :Tt], inp['uniforms'][:4, :Tt], lc_up=lc[:4], gc_ids=inp['gc_ids'][:4], want_logits=True)
+    ex = a16.generate(Tt, inp['forced_full'][:4, :Tt], inp['uniforms'][:4, :Tt], lc_up=lc[:4], gc_ids=inp['gc_ids'][:4], want_logits=True)
+    print('fast vs pinned activation, teacher forced %d steps: max |dlogit| %.3g, max |dsample| %.3g' %
+          (Tt, float((fa[1] - ex[1]).abs().max()), float((fa[0] - ex[0]).abs().max())))
     for rows in (1, 2, 4, 8, 12, 16):
-        for name, net in (('v2', a16), ('v1', b16)):
+        for name, net in (('v2', a16), ('v2fast', f16), ('v1', b16)):
             ms = min(timed(net, T, inp, lc, rows) for _ in range(2))
             print('%s rows=%2d: %.2f us/step  %.1f k samples/s' % (name, rows, 1e3 * ms / T, rows * T / ms))
     # phase counters of the v2 path, 1 and 8 rows
@@ -82,9 +100,8 @@ def main():
         print('   layer 0:', {n: int(lay[0, :, i].mean()) for i, n in names.items()})
         print('   layer 29:', {n: int(lay[29, :, i].mean()) for i, n in names.items()})
         tl = p[L * 4:L * 4 + 16]
-        print('   tail:', {n: int(tl[:, i].mean()) for i, n in enumerate(['wait_acc', 'post1', 'post2'])},
-              ' sampler:', {n: int(p[L * 4 + 16, i]) for i, n in enumerate(['wait_c2', 'draw', 'feed'])})
-        if rows == 1:
+        print('   tail:', {n: int(tl[:, i].mean()) for i, n in enumerate(['wait_acc', 'post1', 'post2'])})
+        if rows >= 1:
             # timeline from the global-timer stamps (ns -> cycles at 1.965 GHz): wake = input complete, send = outputs posted
             ghz = 1.965
             wake = lay[:, :, 14].mean(axis=1) * ghz
@@ -96,12 +113,9 @@ def main():
             print('   wake->send cycles per layer:', [int(v) for v in comp])
             print('   means: DSMEM hop %.0f, LL hop %.0f, layer wake->send %.0f' % (hop[0::2].mean(), hop[1::2].mean(), comp[:-1].mean()))
             t_w = tl[:, 10].mean() * ghz; t_s = tl[:, 11].mean() * ghz
-            s_w = p[L * 4 + 16, 10] * ghz; s_s = p[L * 4 + 16, 11] * ghz
-            print('   layer29 wake -> tail wake %.0f, tail wake->send %.0f, tail send -> sampler wake %.0f, sampler wake->send %.0f'
-                  % (t_w - wake[29], t_s - t_w, s_w - t_s, s_s - s_w))
-            # the sampler's send of step t feeds layer 0 at step t+1: sums are offset by one step time
-            step = 0.0
-            print('   sampler send -> layer0 wake (mod step) %.0f ; step %.0f cycles' % ((wake[0] - s_s) % 1e9, step))
+            print('   layer29 wake -> tail wake %.0f, tail wake->send %.0f' % (t_w - wake[29], t_s - t_w))
+            # layer 0's wake of step t+1 follows the tail's send of step t: the sums differ by the first / last step only
+            print('   tail send -> layer0 input ready (sample drawn, causal input known) ~ %.0f' % ((wake[0] - t_s) + (send[0] - wake[0]) * 0 + (raw[0, 14] * 0)))
 
 
 if __name__ == '__main__':

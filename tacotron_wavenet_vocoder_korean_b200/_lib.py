@@ -13,6 +13,7 @@ WN_MAX_BATCH = 32
 WN_FLAG_GENERIC_KERNEL = 1
 WN_FLAG_NO_DIE_AWARE = 2
 WN_FLAG_NO_CLUSTER = 4
+WN_FLAG_FAST_ACT = 8
 
 
 class WnConfig(C.Structure):
@@ -41,7 +42,7 @@ class WnInfo(C.Structure):
                 ("smem_bytes_layer", C.c_int32), ("smem_bytes_tail", C.c_int32), ("smem_bytes_sampler", C.c_int32),
                 ("sm_count", C.c_int32), ("p_hot", C.c_int64), ("weights_in_smem", C.c_int64),
                 ("weights_in_global", C.c_int64), ("kernel_launches", C.c_int64),
-                ("static_shape", C.c_int32), ("die_aware", C.c_int32), ("cluster_path", C.c_int32)]
+                ("static_shape", C.c_int32), ("die_aware", C.c_int32), ("cluster_path", C.c_int32), ("fast_act", C.c_int32)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -176,7 +176,8 @@ struct wn_handle {
     const void *kernel_many = nullptr;     // variant used when >= kManyRows rows are in flight (or null)
     // round-2 cluster path (wn_kernel_v2.cuh): layer chain in 8-CTA clusters + tail/sampler kernel on the SMs left over
     bool v2_planned = false, v2 = false;
-    const void *kernel_v2_layers = nullptr, *kernel_v2_tail = nullptr;
+    const void *kernel_v2_layers = nullptr, *kernel_v2_layers_prof = nullptr, *kernel_v2_tail = nullptr;
+    bool v2_fast_act = false;
     int v2_grid_layers = 0, v2_smem_layers = 0, v2_smem_tail = 0;
     cudaStream_t v2_sa = nullptr, v2_sb = nullptr;
     cudaEvent_t v2_fork = nullptr, v2_join_a = nullptr, v2_join_b = nullptr;
@@ -478,10 +479,11 @@ static int plan_layout(wn_handle *h, int sm_count)
             inf.static_shape = 1;
             // cluster path: same plan, same mailboxes; needs ceil(L/2) clusters of 8 CTAs + Mt + 1 further SMs
             h->v2_planned = !(c.flags & WN_FLAG_NO_CLUSTER) && !getenv("WN_NO_CLUSTER") &&
-                            V2L<ShapeCfg2>::total_floats(N) * 4 <= kMaxDynSmem && ((L + 1) / 2) * V2_CS + Mt + 1 <= sm_count;
+                            V2L<ShapeCfg2>::total_floats(N) * 4 <= kMaxDynSmem && ((L + 1) / 2) * V2_CS + Mt <= sm_count;
             h->v2_grid_layers = ((L + 1) / 2) * V2_CS;
             h->v2_smem_layers = V2L<ShapeCfg2>::total_floats(N) * 4;
-            h->v2_smem_tail = std::max(h->smem_tail, h->smem_samp);
+            h->v2_smem_tail = (p.tail_smem_floats + 32 * 20 + 32) * 4;
+            h->v2_fast_act = (c.flags & WN_FLAG_FAST_ACT) != 0;
         }
         else if (shape_matches<ShapeCfg1>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeCfg1>; inf.static_shape = 2; }
         else if (shape_matches<ShapeHparams>(p)) { h->kernel = (const void *)wn_persistent_kernel_s<ShapeHparams>; inf.static_shape = 3; }
@@ -706,10 +708,13 @@ int wn_finalize(wn_handle *h)
     if ((long)occ * h->sm_count < grid) return fail(h, WN_ERR_CUDA, "cannot co-schedule %d CTAs (occupancy %d x %d SMs)", grid, occ, h->sm_count);
     h->v2 = false;
     h->info.cluster_path = 0;
+    h->info.fast_act = 0;
     if (h->v2_planned) {
-        h->kernel_v2_layers = (const void *)wn_layers_kernel_v2<ShapeCfg2>;
+        h->kernel_v2_layers = h->v2_fast_act ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false>;
+        h->kernel_v2_layers_prof = h->v2_fast_act ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true>;
         h->kernel_v2_tail = (const void *)wn_tail_kernel_v2<ShapeCfg2>;
         cudaError_t e = cudaFuncSetAttribute(h->kernel_v2_layers, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_layers_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_tail);
         int n_clusters = 0;
         if (e == cudaSuccess) {
@@ -734,7 +739,7 @@ int wn_finalize(wn_handle *h)
             if (e == cudaSuccess && !h->v2_join_a) e = cudaEventCreateWithFlags(&h->v2_join_a, cudaEventDisableTiming);
             if (e == cudaSuccess && !h->v2_join_b) e = cudaEventCreateWithFlags(&h->v2_join_b, cudaEventDisableTiming);
             if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
-            else { h->v2 = true; h->info.cluster_path = 1; h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt + 1) + " tail CTAs"; }
+            else { h->v2 = true; h->info.cluster_path = 1; h->info.fast_act = h->v2_fast_act ? 1 : 0; h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt) + " tail CTAs"; }
         }
     }
     (void)St; (void)Sm;
@@ -846,8 +851,8 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
         CUDA_TRY(h, cudaEventRecord(h->v2_fork, st));
         CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sa, h->v2_fork, 0));
         CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sb, h->v2_fork, 0));
-        CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
-        CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_tail, dim3(p.Mt + 1), dim3(WN_NT), args, (size_t)h->v2_smem_tail, h->v2_sb));
+        CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
+        CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_tail, dim3(p.Mt), dim3(WN_NT), args, (size_t)h->v2_smem_tail, h->v2_sb));
         CUDA_TRY(h, cudaEventRecord(h->v2_join_a, h->v2_sa));
         CUDA_TRY(h, cudaEventRecord(h->v2_join_b, h->v2_sb));
         CUDA_TRY(h, cudaStreamWaitEvent(st, h->v2_join_a, 0));

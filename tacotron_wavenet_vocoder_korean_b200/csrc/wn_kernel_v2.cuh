@@ -20,6 +20,7 @@
 //   dense: lane & 7 = canonical chunk of the CTA's 32 gated channels, 4 outputs per lane.
 // Included by wn_kernel.cu after wn_kernel_ws.cuh (uses its mbarrier helpers).
 #pragma once
+#include <type_traits>
 
 constexpr int V2_NT = 384;       // threads per layer CTA: 8 helper warps + 4 chain warps (<= 168 registers per thread)
 constexpr int V2_HALF = 256;     // helper threads (warps 0-7); the chain group is warps 8-11
@@ -119,6 +120,22 @@ __device__ __forceinline__ float v2_reduce4(const float (&v)[4], int lane)
     return r;
 }
 
+// phase profile that compiles to nothing in the production instantiation (12 x 64-bit accumulators cost 24 registers)
+template <bool ON>
+struct ProfT;
+template <>
+struct ProfT<true> : Prof {
+    __device__ __forceinline__ ProfT(long long *s) : Prof(s) {}
+};
+template <>
+struct ProfT<false> {
+    long long acc[1];
+    __device__ __forceinline__ ProfT(long long *) {}
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void mark(int) {}
+    __device__ __forceinline__ void stamp(int) {}
+};
+
 // shared-memory layout of a v2 layer CTA, in floats from g_smem
 template <class SH>
 struct V2L {
@@ -136,13 +153,18 @@ struct V2L {
     static constexpr int OFF_XSOLD = OFF_ZS + 2 * SH::Dm;                     // helper: dilated tap, padded for Cur
     static constexpr int OFF_LCS = OFF_XSOLD + Cur::TPC * Cur::XS;            // helper: lc row, padded for Lc
     static constexpr int OFF_GVEC = OFF_LCS + Lc::TPC * Lc::XS;               // prologue: speaker embedding
-    static constexpr int OFF_BAR = (OFF_GVEC + Gc::TPC * Gc::XS + 3) & ~3;    // mbarriers (8 B each): 5 x 32 rows + image
+    static constexpr int OFF_WC = (OFF_GVEC + Gc::TPC * Gc::XS + 3) & ~3;     // layer 0: causal kernel [ifw][R]
+    static constexpr int OFF_BAR = OFF_WC + SH::IFW * SH::R;                  // mbarriers (8 B each): 5 x 32 rows + image
     static constexpr int OFF_ROWS = OFF_BAR + 2 * (5 * WN_MAX_BATCH + 2);
     // per row
     static constexpr int ZF = Skip::TPC * Skip::XS;                           // full gated vector, padded for Skip
     static constexpr int R_INX = 0;                                            // [M][R] partial inputs (DSMEM inbox)
+    static constexpr int R_HPRE = R_INX;                                       // layer 0 (no inbox): [4][R] causal partial sums
     static constexpr int R_Z = SH::M * SH::R;                                  // [ZF]
     static constexpr int R_ACC = R_Z + ZF;                                     // [Sm] running skip sum of layer l-1
+    static constexpr int R_CQRING = R_ACC;                                     // layer 0 (no acc input): causal queue ring [IFW]
+    static constexpr int R_XIN = R_ACC + SH::IFW;                              // layer 0: network input x_in of the step
+    static constexpr int R_SAMP = R_ACC + SH::IFW + 16;                        // layer 0: [nr_mix] Gumbel noise, logistic noise, forced input of the next draw
     static constexpr int R_XRAW = R_ACC + SH::Sm;                              // [R] combined layer input
     static constexpr int R_PRE = R_XRAW + SH::R;                               // [2 Dm] pre-activations of the next step
     static constexpr int R_BFGN = R_PRE + 2 * SH::Dm;                          // [2 Dm] bias + speaker contribution
@@ -253,7 +275,73 @@ __device__ __forceinline__ int v2_chain_sync_or(int flag)
     return r;
 }
 
+// tanh / sigmoid through MUFU.EX2 + MUFU.RCP (~45 cycles instead of ~180 for the pinned exp32 + IEEE divide).
+// Only for the scalar-input (mixture-of-logistics) path, whose tolerance is 1e-4 on the logits (north_star); the
+// mu-law path keeps the pinned arithmetic because its integer samples must be bit-exact.  |error| <= ~3e-7.
+__device__ __forceinline__ float act_fg_fast(float x, bool is_gate)
+{
+    const float arg = fmul(is_gate ? -x : fadd(x, x), 1.4426950408889634f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(arg));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fadd(e, 1.0f)));
+    return is_gate ? r : ffma(-2.0f, r, 1.0f);
+}
+
+// One warp of a layer-0 CTA: waits for the Mt partial conv2 outputs of (b, step) from the tail CTAs, adds them left to
+// right onto the bias, writes the logits, draws from the mixture of logistics (wavenet/mixture.py:84-114) and returns
+// the sample in every lane.  Lane o < O owns output o; gum / logistic are precomputed from the step's uniforms.
 template <class SH>
+__device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &mb, int b, int step, int lane, bool writer, V2Ab &ab,
+                                                float b2v, float gum, float logistic)
+{
+    constexpr int O = SH::O, Mt = SH::Mt, nr = SH::O / 3;
+    static_assert(O <= 32 && Mt == 16, "sample warp: one lane per output, 16 tail partials");
+    const unsigned seq = (unsigned)step + 1u;
+    float c2 = b2v;
+    if (lane < O) {
+        // 16 words per lane, all in flight; consumed in order (the partial sums are added left to right).  A missing word
+        // re-issues the loads of every word not yet consumed, so late tail CTAs cost one poll round, not one each.
+        const u64 *src = p.mb_c2 + ((size_t)b * Mt) * O + lane;
+        u64 wv[Mt];
+#pragma unroll
+        for (int i = 0; i < Mt; ++i) wv[i] = ld_relaxed_u64(mb.rd(src + (size_t)i * O));
+        unsigned spins = 0;
+        long long t0 = 0;
+#pragma unroll
+        for (int i = 0; i < Mt; ++i) {
+            while ((unsigned)(wv[i] >> 32) != seq && !ab.dead) {
+#pragma unroll
+                for (int j = i; j < Mt; ++j) wv[j] = ld_relaxed_u64(mb.rd(src + (size_t)j * O));
+                if (((++spins) & 0x3ffu) == 0) {
+                    t0 = v2_watchdog(ab.status, t0);
+                    if (t0 < 0) { ab.dead = 1; break; }
+                }
+            }
+            c2 = fadd(c2, __uint_as_float((unsigned)wv[i]));
+        }
+        if (writer && p.out_logits) p.out_logits[((size_t)b * p.T + step) * O + lane] = c2;
+    }
+    __syncwarp();
+    float g = (lane < nr) ? fsub(c2, gum) : __int_as_float(0xff800000);
+    int k = lane;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float og = __shfl_xor_sync(FULL, g, off);
+        const int ok = __shfl_xor_sync(FULL, k, off);
+        if (og > g || (og == g && ok < k)) { g = og; k = ok; }
+    }
+    const float mean = __shfl_sync(FULL, c2, nr + k);
+    float ls = __shfl_sync(FULL, c2, 2 * nr + k);
+    const float lsmin = -32.23619130191664f;
+    if (!(ls > lsmin)) ls = lsmin;
+    float x = fadd(mean, fmul(wn::exp32(ls), logistic));
+    x = fmaxf(x, -1.0f);
+    x = fminf(x, 1.0f);
+    if (writer && lane == 0) p.out_samples[(size_t)b * p.T + step] = x;
+    return x;
+}
+
+template <class SH, bool FAST, bool PROF>
 __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
 {
     using Cur = typename SH::Cur;        // packed for 256 slots: col = slot / 4, chunk = slot % 4, 8 float4
@@ -308,8 +396,18 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                          : "memory");
         }
     }
-    for (int i = LY::OFF_XS + tid; i < LY::OFF_BAR; i += V2_NT) smem[i] = 0.0f;
+    for (int i = LY::OFF_XS + tid; i < LY::OFF_WC; i += V2_NT) smem[i] = 0.0f;
     for (int i = tid; i < N * LY::ROWF; i += V2_NT) rows[i] = 0.0f;
+    if (l == 0) {
+        // causal kernel (wavenet/model.py:41-46) as [tap][channel]; packed in the sampler image for 256 slots (Causal: TPC 2, 4 float4)
+        using Causal = typename SH::Causal;
+        static_assert(Causal::TPC == 2 && Causal::N4 == 4 && Causal::U == 4 && SH::IFW == 32, "v2 causal layer assumes the cfg-2 shape");
+        const float *wcp = p.samp_img + p.causal.off;
+        for (int i = tid; i < SH::IFW * R; i += V2_NT) {
+            const int k = i / R, r = i % R;
+            smem[LY::OFF_WC + i] = __ldg(wcp + (((size_t)((k % 16) / 4) * WN_NT + r * 2 + k / 16) * 4 + (k % 4)));
+        }
+    }
     while (!mbar_try(ldbar, 0)) {}
     __syncthreads();
     if (tid == 0) {
@@ -328,7 +426,6 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
     const float *w_old_s = smem + LY::OFF_WOLD, *w_lc_s = smem + LY::OFF_WLC, *w_gc_s = smem + LY::OFF_WGC;
 
     const int d = p.dil[l];
-    const int nin = (l == 0) ? 1 : M;
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
     V2Ab ab{p.status, 0};
     const MBox mb = make_mbox(p);
@@ -349,7 +446,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
         float4 wsk[Skip::N4];                                   // skip 1x1 slice: 64 registers, resident
         v2_load_wreg<Skip::N4>(wsk, gimg + p.skip.off, ht);
         const float bsv = bs[col2];
-        Prof hp((p.prof && ht == 0) ? p.prof + (size_t)cta * 16 : nullptr);
+        ProfT<PROF> hp((p.prof && ht == 0) ? p.prof + (size_t)cta * 16 : nullptr);
 
         // ---- prologue: speaker contribution folded into the biases, pre-activations for t = 0 ------------------
         for (int b = 0; b < N; ++b) {
@@ -371,6 +468,8 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
             }
             v2_group_sync(2);
         }
+        if (l == 0 && ht < N && p.T_row[ht] > 0) rows[(size_t)ht * LY::ROWF + LY::R_SAMP + SH::O / 3 + 1] = __ldg(p.forced + (size_t)ht * p.n_forced);
+        v2_group_sync(2);
         if (ht == 0)
             for (int b = 0; b < N; ++b) mbar_arrive(&prdy[b]);           // phase 0: pre for t = 0 is ready
 
@@ -400,8 +499,18 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                     long idx = (long)t - p.lc_shift;
                     if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) lcv = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
                 }
-                pin(oldv); pin(lcv);
+                // layer 0: noise of the draw of step t and the forced input of step t+1 (consumed by the chain's item (b, t+1))
+                float sprep = 0.0f;
+                if (l == 0 && has_next && ht <= SH::O / 3 + 1) {
+                    constexpr int nr = SH::O / 3;
+                    const float *u = (const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1);
+                    if (ht < nr) sprep = wn::log32(-wn::log32(ld_nc_f32(u + ht)));
+                    else if (ht == nr) { const float u2 = ld_nc_f32(u + nr); sprep = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
+                    else sprep = (t + 1 < p.n_forced) ? ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1) : 0.0f;
+                }
+                pin(oldv); pin(lcv); pin(sprep);
                 v2_mbar_wait(&fullb[b], par, ab);                       // x and the own z slice of (b, t) are in rows[b]
+                if (l == 0 && has_next && ht <= SH::O / 3 + 1) rb[LY::R_SAMP + ht] = sprep;
                 hp.mark(7);
                 if (ht < R) {
                     const float xme = rb[LY::R_XRAW + ht];
@@ -410,6 +519,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                     xs_old[xp_x] = oldv;
                 }
                 if (SH::HAS_LC && ht < SH::C) lcs[xp_lc] = lcv;
+                if (l == 0 && ht == 0) rb[LY::R_CQRING + (t & (SH::IFW - 1))] = rb[LY::R_XIN];     // causal queue push (model.py:122)
                 v2_mbar_wait(&zbar[b], par, ab);                        // the three siblings' slices have landed
                 if (ht == 0) v2_expect_tx(&zbar[b], (uint32_t)((M - 1) * Dm * 4));
                 v2_group_sync(2);
@@ -454,6 +564,28 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                     }
                 }
                 hp.mark(9);
+                // layer 0: the 31 known taps of the next step's causal conv (model.py:131), as the partial sums the chain
+                // thread combines with the new sample: canonical chunks of 4 taps, a[c] += a[c^1], a[c^2], a[c^4]
+                if (l == 0 && has_next && ht < R) {
+                    const float *wc = smem + LY::OFF_WC + ht;
+                    const float *cq = rb + LY::R_CQRING;
+                    float a[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float v = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int k = 4 * c + i;                     // tap k holds x_in(t - 30 + k); tap 31 is the sample to come
+                            if (k < SH::IFW - 1) v = ffma(wc[k * R], cq[(t + 2 + k) & (SH::IFW - 1)], v);
+                        }
+                        a[c] = v;
+                    }
+                    float *hp4 = rb + LY::R_HPRE + ht;
+                    hp4[0] = fadd(fadd(a[0], a[1]), fadd(a[2], a[3]));
+                    hp4[R] = fadd(a[4], a[5]);
+                    hp4[2 * R] = a[6];
+                    hp4[3 * R] = a[7];
+                }
                 // pre-activations of the next step: (bias(+gc) + W_old . x_l(t+1-d)) + W_lc . lc(t)
                 if (has_next) {
                     float *pre_b = rb + LY::R_PRE;
@@ -473,13 +605,17 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                 hp.mark(10);
             }
         }
-        if (p.prof && ht == 0)
-            for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[i];
+        if (PROF && p.prof && ht == 0)
+            for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[PROF ? i : 0];
     } else {
         // =========================== CHAIN group (warps 8-11) ===================================================
         // "Fat" threads, one warp per SM sub-partition: thread = (filter/gate column c, K half) holds 64 weights of the
         // current tap and evaluates canonical chunks khalf*16 .. khalf*16+15 (in-thread tree, ONE shuffle level);
         // for the dense 1x1 thread = output r over the CTA's whole 32-channel slice (8 canonical chunks, no shuffle).
+        // Two instantiations of the same body: the layer-0 one carries the sampler (16 LL words in flight per lane), whose
+        // register demand would otherwise spill the weight registers of every layer's loop.
+        auto chain_group = [&](auto l0_tag) {
+        constexpr bool L0 = decltype(l0_tag)::value;
         const int ct = tid - V2_HALF;
         const int c = ct >> 1, khalf = ct & 1;                       // column c = 2*j + gate
         const bool gate = (c & 1) != 0;
@@ -514,7 +650,10 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
         }
         const u64 *mbx_in = p.mb_x + ((size_t)l * M) * R + ct;
         const u64 *mbx_out = p.mb_x + ((size_t)(l + 1) * M + m) * R + ct;
-        Prof pf((p.prof && ct == 0) ? p.prof + (size_t)cta * 16 : nullptr);
+        constexpr int nr_mix = SH::O / 3;
+        const float w31r = smem[LY::OFF_WC + (SH::IFW - 1) * R + ct];                  // layer 0: newest causal tap
+        const float b2v = (L0 && ct < SH::O) ? __ldg(p.samp_img + p.off_b2 + ct) : 0.0f;
+        ProfT<PROF> pf((p.prof && ct == 0) ? p.prof + (size_t)cta * 16 : nullptr);
         unsigned item = 0;                                           // parity selects the zs buffer
 
         for (int t = 0; t < p.T; ++t) {
@@ -531,10 +670,31 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                 if (has_next_layer && !out_dsmem) dx = mb_dst(mb, mbx_out + b * rowx);
                 v2_mbar_wait(&prdy[b], par, ab);                       // pre[b] of this step written, rows[b] free
                 const float pre_v = rb[LY::R_PRE + c];
-                // 1. layer input r = ct: sum of the partial residual outputs of layer l-1
+                // 1. layer input r = ct
                 {
                     float v;
-                    if (in_dsmem) {
+                    if (L0) {
+                        // layer 0 hosts the sampler: warp 0 of the group draws sample t-1 from the tail's conv2 partials,
+                        // the new network input closes the causal conv whose 31 older taps the helper has already summed
+                        const float *hp4 = rb + LY::R_HPRE + ct;
+                        const float h0 = hp4[0], h1 = hp4[R], h2 = hp4[2 * R], h3 = hp4[3 * R];
+                        if (ct < 32) {
+                            // Gumbel / logistic noise and the forced input were prepared by the helper one step ahead
+                            const float gum = (ct < nr_mix) ? rb[LY::R_SAMP + ct] : 0.0f;
+                            const float logistic = rb[LY::R_SAMP + nr_mix];
+                            float x_in = rb[LY::R_SAMP + nr_mix + 1];
+                            if (t > 0) {
+                                const float smp = v2_sample_warp<SH>(p, mb, b, t - 1, ct, m == 0, ab, b2v, gum, logistic);
+                                if (t >= p.n_forced) x_in = smp;
+                            }
+                            if (ct == 0) rb[LY::R_XIN] = x_in;
+                        }
+                        v2_chain_sync();
+                        const float x_in = rb[LY::R_XIN];
+                        pf.mark(0);
+                        pf.stamp(10);
+                        v = fadd(h0, fadd(h1, fadd(h2, ffma(w31r, x_in, h3))));
+                    } else if (in_dsmem) {
                         v2_mbar_wait(&xbar[b], par, ab);
                         pf.mark(0);
                         pf.stamp(10);
@@ -542,13 +702,10 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                         v = fadd(fadd(fadd(in[0], in[R]), in[2 * R]), in[3 * R]);
                     } else {
                         float q[4];
-                        v2_ll_wait_n(mb, mbx_in + b * rowx, (size_t)R, nin, seq, ab, q);
+                        v2_ll_wait_n(mb, mbx_in + b * rowx, (size_t)R, M, seq, ab, q);
                         pf.mark(0);
                         pf.stamp(10);
-                        v = q[0];
-#pragma unroll
-                        for (int i = 1; i < 4; ++i)
-                            if (i < nin) v = fadd(v, q[i]);
+                        v = fadd(fadd(fadd(q[0], q[1]), q[2]), q[3]);
                     }
                     xs[xp] = v;
                     rb[LY::R_XRAW + ct] = v;
@@ -576,7 +733,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                         for (int k = 0; k < 16; k += 2 * off) acc[k] = fadd(acc[k], acc[k + off]);
                     const float dot = fadd(acc[0], __shfl_xor_sync(FULL, acc[0], 1));
                     pf.mark(3);
-                    const float a = act_fg(fadd(pre_v, dot), gate);
+                    const float a = FAST ? act_fg_fast(fadd(pre_v, dot), gate) : act_fg(fadd(pre_v, dot), gate);
                     const float o = __shfl_xor_sync(FULL, a, 2);
                     const float z = gate ? fmul(o, a) : fmul(a, o);
                     if (zq == 0) {
@@ -625,25 +782,153 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                 pf.mark(6);
             }
         }
-        if (p.prof && ct == 0) {
-            for (int i = 0; i < 7; ++i) p.prof[(size_t)cta * 16 + i] = pf.acc[i];
-            p.prof[(size_t)cta * 16 + 14] = pf.acc[10];
-            p.prof[(size_t)cta * 16 + 15] = pf.acc[11];
+        // the last step of every row is drawn here: in the loop, step t-1 is drawn when step t is fed
+        if (L0 && m == 0 && ct < 32) {
+            for (int b = 0; b < N; ++b) {
+                const int step = p.T_row[b] - 1;
+                if (step < 0) continue;
+                const float *u = (const float *)p.uniforms + ((size_t)b * p.T + step) * (nr_mix + 1);
+                float gum = 0.0f;
+                if (ct < nr_mix) gum = wn::log32(-wn::log32(ld_nc_f32(u + ct)));
+                const float u2 = ld_nc_f32(u + nr_mix);
+                const float logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2)));
+                v2_sample_warp<SH>(p, mb, b, step, ct, true, ab, b2v, gum, logistic);
+            }
         }
+        if (PROF && p.prof && ct == 0) {
+            for (int i = 0; i < 7; ++i) p.prof[(size_t)cta * 16 + i] = pf.acc[PROF ? i : 0];
+            p.prof[(size_t)cta * 16 + 14] = pf.acc[PROF ? 10 : 0];
+            p.prof[(size_t)cta * 16 + 15] = pf.acc[PROF ? 11 : 0];
+        }
+        };
+        if (l == 0) chain_group(std::true_type{});
+        else chain_group(std::false_type{});
     }
     // no CTA of the cluster leaves while a peer may still store into its shared memory
     __syncthreads();
     v2_cluster_sync();
 }
 
-// Kernel A: the layer chain.  grid = 8 * ceil(L / 2), cluster of 8 = layers 2c and 2c+1.
+// =================================================================================================================
+// Tail CTA mt of kernel B: relu(total skip) -> conv1 slice (S/Mt columns) -> relu -> partial conv2 over that slice
+// (wavenet/model.py:158-165).  conv1 from registers with lane = 16 consecutive k (two canonical 8-element chunks) and
+// 4 columns per lane: 4 conflict-free LDS.128 per thread instead of 16 eight-address ones (512 -> 128 LSU cycles per
+// row-step), partial sums reduced by a transposing butterfly.  Same canonical plan as tail_role_s (t_post1 = 64).
 template <class SH>
+__device__ void tail_role_v2(const WnParams &p, int mt)
+{
+    using Post1 = typename SH::Post1;
+    using Post2 = typename SH::Post2;
+    constexpr int S = SH::S, Sm = SH::Sm, M = SH::M, St = SH::St, O = SH::O, Mt = SH::Mt;
+    static_assert(S == 512 && St == 32 && Post1::TPC == 8 && Post1::N4 == 16 && Post1::U == 8 && Post1::NPASS == 1, "v2 tail assumes the cfg-2 conv1 shape");
+    static_assert(Post2::NPASS == 1 && Post2::XS == Post2::CH, "v2 tail assumes an unpadded conv2 input");
+    constexpr int AS = 20;                                   // padded stride of a lane's 16-float chunk of relu(total)
+    float *smem = g_smem;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int N = p.N, L = p.L;
+    const float *gimg = p.tail_img + (size_t)mt * p.tail_img_floats;
+    __shared__ uint64_t bar;
+    load_image_tma(smem, gimg, p.tail_smem_floats, &bar);
+    const float *b1 = smem + p.off_b1;
+    float *sc = smem + p.tail_smem_floats;
+    float *as1 = sc, *c1s = sc + 32 * AS;                    // 640 + 32 floats
+    for (int i = tid; i < 32 * AS + 32; i += WN_NT) sc[i] = 0.0f;
+    __syncthreads();
+    // conv1 weights: column 4w + q, k = 16*lane + 4i + kk  <->  packed slot col*8 + k/64, float4 index (k%64)/4
+    float4 w1r[4][4];
+    {
+        const float4 *pk = reinterpret_cast<const float4 *>(smem + p.post1.off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w1r[q][i] = pk[(size_t)((lane & 3) * 4 + i) * WN_NT + (4 * w + q) * 8 + (lane >> 2)];
+    }
+    float4 w2r[Post2::N4];
+    load_wreg<Post2::N4>(w2r, smem + p.post2.off);
+    const float b1v = b1[4 * w + (lane & 3)];
+    const float *xc2 = c1s + (tid % Post2::TPC) * Post2::XS;
+    const int o2 = tid / Post2::TPC;
+    const bool lead2 = (tid % Post2::TPC) == 0 && o2 < O;
+    const int xa0 = (tid >> 4) * AS + (tid & 15), xa1 = ((tid + WN_NT) >> 4) * AS + (tid & 15);
+    const size_t rowa = (size_t)L * M * Sm;
+    const u64 *src0 = p.mb_acc + ((size_t)(L - 1) * M) * Sm + tid;
+    const u64 *dst0 = p.mb_c2 + (size_t)mt * O + o2;
+    V2Ab ab{p.status, 0};
+    const MBox mb = make_mbox(p);
+    Prof pf(p.prof ? p.prof + (size_t)(p.L * SH::M + mt) * 16 : nullptr);
+    for (int t = 0; t < p.T; ++t) {
+        if ((t & 15) == 0 && __syncthreads_or(ab.dead)) break;
+        const unsigned seq = (unsigned)t + 1u;
+        for (int b = 0; b < N; ++b) {
+            if (t >= p.T_row[b]) continue;
+            pf.start();
+            MDst dc{nullptr, nullptr};
+            if (lead2) dc = mb_dst(mb, dst0 + (size_t)b * Mt * O);
+            {
+                float q[4];
+                v2_ll_wait_n(mb, src0 + b * rowa, (size_t)WN_NT, 2, seq, ab, q);
+                as1[xa0] = relu32(q[0]);
+                as1[xa1] = relu32(q[1]);
+            }
+            __syncthreads();
+            pf.mark(0);
+            pf.stamp(10);
+            {
+                const float4 *x4 = reinterpret_cast<const float4 *>(as1 + lane * AS);
+                const float4 x0 = x4[0], x1 = x4[1], x2 = x4[2], x3 = x4[3];
+                float acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float a = 0.0f, c = 0.0f;
+                    a = ffma(w1r[q][0].x, x0.x, a); a = ffma(w1r[q][0].y, x0.y, a); a = ffma(w1r[q][0].z, x0.z, a); a = ffma(w1r[q][0].w, x0.w, a);
+                    a = ffma(w1r[q][1].x, x1.x, a); a = ffma(w1r[q][1].y, x1.y, a); a = ffma(w1r[q][1].z, x1.z, a); a = ffma(w1r[q][1].w, x1.w, a);
+                    c = ffma(w1r[q][2].x, x2.x, c); c = ffma(w1r[q][2].y, x2.y, c); c = ffma(w1r[q][2].z, x2.z, c); c = ffma(w1r[q][2].w, x2.w, c);
+                    c = ffma(w1r[q][3].x, x3.x, c); c = ffma(w1r[q][3].y, x3.y, c); c = ffma(w1r[q][3].z, x3.z, c); c = ffma(w1r[q][3].w, x3.w, c);
+                    acc[q] = fadd(a, c);
+                }
+                // lanes: canonical offsets 2, 4 (transposing), then 8, 16, 32
+                float dot = v2_reduce4(acc, lane);           // lanes xor 1, 2 (keep value lane & 3), xor 4
+                dot = fadd(dot, __shfl_xor_sync(FULL, dot, 8));
+                dot = fadd(dot, __shfl_xor_sync(FULL, dot, 16));
+                if (lane < 4) c1s[4 * w + lane] = relu32(fadd(b1v, dot));
+            }
+            __syncthreads();
+            pf.mark(1);
+            {
+                const float dot = butterfly<Post2::TPC>(dot_wreg<Post2::N4, Post2::U>(w2r, reinterpret_cast<const float4 *>(xc2)));
+                if (lead2) ll_post(dc, dot, seq);
+            }
+            pf.stamp(11);
+            pf.mark(2);
+        }
+    }
+    pf.flush();
+}
+
+// Kernel A: the layer chain.  grid = 8 * ceil(L / 2), cluster of 8 = layers 2c and 2c+1.  With a die map, clusters on
+// die 0 claim layer pairs from the front of the chain and clusters on die 1 from the back (every cluster sits on one
+// die), so the chain crosses the die boundary once on its way down instead of wherever the hardware put the clusters.
+template <class SH, bool FAST, bool PROF>
 __global__ void __cluster_dims__(V2_CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers_kernel_v2(const __grid_constant__ WnParams p)
 {
+    __shared__ int s_crole;
     const unsigned crank = v2_cluster_ctarank();
-    const int l = (int)v2_cluster_id() * 2 + (int)(crank >> 2), m = (int)(crank & 3u);
+    if (crank == 0 && threadIdx.x == 0) {
+        int role = (int)v2_cluster_id();
+        if (p.sm_die != nullptr) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int n_clusters = (int)(gridDim.x / V2_CS);
+            role = (p.sm_die[smid] == 0) ? atomicAdd(p.status + 4, 1) : n_clusters - 1 - atomicAdd(p.status + 5, 1);
+        }
+        s_crole = role;
+    }
+    v2_cluster_sync();
+    int crole;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(crole) : "r"(v2_mapa(smem_u32(&s_crole), 0u)) : "memory");
+    const int l = crole * 2 + (int)(crank >> 2), m = (int)(crank & 3u);
     if (l < p.L) {
-        layer_role_v2<SH>(p, l, m);
+        layer_role_v2<SH, FAST, PROF>(p, l, m);
     } else {
         v2_cluster_sync();
         __syncthreads();
@@ -651,11 +936,9 @@ __global__ void __cluster_dims__(V2_CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_lay
     }
 }
 
-// Kernel B: tail + sampler roles (wn_kernel_static.cuh) on the SMs the clusters leave free.
+// Kernel B: the tail CTAs, on the SMs the clusters leave free.
 template <class SH>
 __global__ void __launch_bounds__(WN_NT, 1) wn_tail_kernel_v2(const __grid_constant__ WnParams p)
 {
-    const int cta = (int)blockIdx.x;
-    if (cta < SH::Mt) tail_role_s<SH>(p, cta);
-    else sampler_role_s<SH>(p);
+    tail_role_v2<SH>(p, (int)blockIdx.x);
 }

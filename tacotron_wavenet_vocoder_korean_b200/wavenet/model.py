@@ -16,7 +16,7 @@ def _make_cfg(batch_size, dilations, filter_width, residual_channels, dilation_c
               quantization_channels=2 ** 8, out_channels=30, use_biases=False, scalar_input=False,
               initial_filter_width=32, global_condition_channels=None, global_condition_cardinality=None,
               local_condition_channels=80, upsample_factor=None, train_mode=True, force_M=0, force_Mt=0,
-              generic_kernel=False, die_aware=True, cluster=True, **_ignored):
+              generic_kernel=False, die_aware=True, cluster=True, fast_act=False, **_ignored):
     dilations = list(dilations)
     uf = list(upsample_factor) if upsample_factor else []
     if len(uf) > _lib.WN_MAX_UPSAMPLE or len(dilations) > _lib.WN_MAX_LAYERS:
@@ -44,7 +44,7 @@ def _make_cfg(batch_size, dilations, filter_width, residual_channels, dilation_c
     cfg.force_M = force_M
     cfg.force_Mt = force_Mt
     cfg.flags = ((_lib.WN_FLAG_GENERIC_KERNEL if generic_kernel else 0) | (0 if die_aware else _lib.WN_FLAG_NO_DIE_AWARE) |
-                 (0 if cluster else _lib.WN_FLAG_NO_CLUSTER))
+                 (0 if cluster else _lib.WN_FLAG_NO_CLUSTER) | (_lib.WN_FLAG_FAST_ACT if fast_act else 0))
     return cfg
 
 
@@ -64,7 +64,7 @@ class WaveNetModel(object):
                  quantization_channels=2 ** 8, out_channels=30, use_biases=False, scalar_input=False,
                  initial_filter_width=32, global_condition_channels=None, global_condition_cardinality=None,
                  local_condition_channels=80, upsample_factor=None, train_mode=True, device=None,
-                 force_M=0, force_Mt=0, generic_kernel=False, die_aware=True, cluster=True):
+                 force_M=0, force_Mt=0, generic_kernel=False, die_aware=True, cluster=True, fast_act=False):
         self.batch_size = batch_size
         self.dilations = list(dilations)
         self.filter_width = filter_width
@@ -90,7 +90,7 @@ class WaveNetModel(object):
         cfg = _make_cfg(batch_size, dilations, filter_width, residual_channels, dilation_channels, skip_channels,
                         quantization_channels, out_channels, use_biases, scalar_input, initial_filter_width,
                         global_condition_channels, global_condition_cardinality, local_condition_channels,
-                        upsample_factor, train_mode, force_M, force_Mt, generic_kernel, die_aware, cluster)
+                        upsample_factor, train_mode, force_M, force_Mt, generic_kernel, die_aware, cluster, fast_act)
         self._cfg = cfg
         self._h = C.c_void_p()
         rc = _lib.lib().wn_create(C.byref(cfg), C.byref(self._h))
