@@ -191,13 +191,15 @@ int orc_receptive_field(int filter_width, const int32_t *dilations, int n, int s
 
 void orc_mu_law_encode(const float *audio, int n, int quantization_channels, int32_t *out)
 {
-    /* wavenet/ops.py:22-33; TF evaluates in fp32 with libm log1p; tf.to_int32 truncates. */
+    /* wavenet/ops.py:22-33; TF evaluates in fp32 with its own log1p; tf.to_int32 truncates.  The output is an integer
+     * code, so the evaluation is pinned (orc_log1p32, wn_math_ref.h) and the CUDA kernel must reproduce it bit for bit;
+     * against the reference's own run (libm log1p) the code can differ by 1 only where the argument sits on a cell edge. */
     float mu = (float)(quantization_channels - 1);
-    float den = log1pf(mu);
+    float den = orc_log1p32(mu);
     for (int i = 0; i < n; ++i) {
         float a = audio[i];
         float safe = fminf(fabsf(a), 1.0f);
-        float mag = log1pf(mu * safe) / den;
+        float mag = orc_log1p32(mu * safe) / den;
         float sgn = (a > 0.0f) ? 1.0f : ((a < 0.0f) ? -1.0f : 0.0f);
         float sig = sgn * mag;
         out[i] = (int32_t)((sig + 1.0f) / 2.0f * mu + 0.5f);

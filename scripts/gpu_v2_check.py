@@ -115,7 +115,9 @@ def main():
             t_w = tl[:, 10].mean() * ghz; t_s = tl[:, 11].mean() * ghz
             print('   layer29 wake -> tail wake %.0f, tail wake->send %.0f' % (t_w - wake[29], t_s - t_w))
             # layer 0's wake of step t+1 follows the tail's send of step t: the sums differ by the first / last step only
-            print('   tail send -> layer0 input ready (sample drawn, causal input known) ~ %.0f' % ((wake[0] - t_s) + (send[0] - wake[0]) * 0 + (raw[0, 14] * 0)))
+            step_cyc = None
+            smp = lay[0, :, 13].mean() * ghz       # sample drawn (sum over steps 1..T-1 of step t-1's draw)
+            print('   layer 0: sample drawn -> input ready %.0f cycles (per step, approx)' % ((wake[0] - smp) * T * rows / max(T * rows - rows, 1)))
 
 
 if __name__ == '__main__':

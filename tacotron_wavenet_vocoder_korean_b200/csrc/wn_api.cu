@@ -644,7 +644,7 @@ int wn_finalize(wn_handle *h)
 
     // ---- mailboxes: logical word space -> dual-homed 2 KB grains ----------------------------------------
     const size_t n_x = (size_t)N * L * M * R, n_z = (size_t)N * L * M * Dm, n_acc = (size_t)N * L * M * Sm, n_c2 = (size_t)N * Mt * O;
-    const size_t n_lg = (n_x + n_z + n_acc + n_c2 + 255) / 256 + 1;            // logical grains
+    const size_t n_lg = (n_x + n_z + n_acc + n_c2 + 255) / 256 + 3;            // logical grains (+ slack: readers may resolve the two grains after a word)
     calibrate_once(prop.multiProcessorCount);
     const bool want_dual = g_calib.ok && !(c.flags & WN_FLAG_NO_DIE_AWARE);
     const size_t n_raw = want_dual ? (n_lg * 5) / 2 + 64 : n_lg;

@@ -1041,7 +1041,7 @@ extern "C" __global__ void wn_mu_law_encode_kernel(const float *__restrict__ aud
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float a = audio[i];
         float safe = fminf(fabsf(a), 1.0f);
-        float mag = __fdiv_rn(log1pf(__fmul_rn(mu, safe)), log1pf(mu));
+        float mag = __fdiv_rn(wn::log1p32(__fmul_rn(mu, safe)), wn::log1p32(mu));      // pinned: integer codes are bit-exact vs the oracle
         float sgn = (a > 0.0f) ? 1.0f : ((a < 0.0f) ? -1.0f : 0.0f);
         float sig = __fmul_rn(sgn, mag);
         float v = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(sig, 1.0f), 2.0f), mu), 0.5f);

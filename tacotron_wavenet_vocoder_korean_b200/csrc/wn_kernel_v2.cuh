@@ -301,17 +301,31 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
     if (lane < O) {
         // 16 words per lane, all in flight; consumed in order (the partial sums are added left to right).  A missing word
         // re-issues the loads of every word not yet consumed, so late tail CTAs cost one poll round, not one each.
-        const u64 *src = p.mb_c2 + ((size_t)b * Mt) * O + lane;
+        // The lane's 16 words (stride O) span at most three 2 KB grains of the logical mailbox space: resolve those three
+        // grain bases once instead of a table lookup per word and per poll round.
+        const size_t w0 = (reinterpret_cast<size_t>(p.mb_c2) >> 3) + ((size_t)b * Mt) * O + lane;
+        const size_t g0 = w0 >> 8;
+        static_assert((Mt - 1) * O < 512, "sample warp: the partial words of one output fit three grains");
+        const unsigned long long *tab = reinterpret_cast<const unsigned long long *>(mb.mine);
+        const u64 *gb0 = reinterpret_cast<const u64 *>(__ldg(tab + g0));
+        const u64 *gb1 = reinterpret_cast<const u64 *>(__ldg(tab + g0 + 1));
+        const u64 *gb2 = reinterpret_cast<const u64 *>(__ldg(tab + g0 + 2));
+        auto word = [&](int i) -> const u64 * {
+            const size_t w = w0 + (size_t)i * O;
+            const size_t g = (w >> 8) - g0;
+            const u64 *base = (g == 0) ? gb0 : ((g == 1) ? gb1 : gb2);
+            return base + (w & 255);
+        };
         u64 wv[Mt];
 #pragma unroll
-        for (int i = 0; i < Mt; ++i) wv[i] = ld_relaxed_u64(mb.rd(src + (size_t)i * O));
+        for (int i = 0; i < Mt; ++i) wv[i] = ld_relaxed_u64(word(i));
         unsigned spins = 0;
         long long t0 = 0;
 #pragma unroll
         for (int i = 0; i < Mt; ++i) {
             while ((unsigned)(wv[i] >> 32) != seq && !ab.dead) {
 #pragma unroll
-                for (int j = i; j < Mt; ++j) wv[j] = ld_relaxed_u64(mb.rd(src + (size_t)j * O));
+                for (int j = i; j < Mt; ++j) wv[j] = ld_relaxed_u64(word(j));
                 if (((++spins) & 0x3ffu) == 0) {
                     t0 = v2_watchdog(ab.status, t0);
                     if (t0 < 0) { ab.dead = 1; break; }
@@ -686,6 +700,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                             if (t > 0) {
                                 const float smp = v2_sample_warp<SH>(p, mb, b, t - 1, ct, m == 0, ab, b2v, gum, logistic);
                                 if (t >= p.n_forced) x_in = smp;
+                                pf.stamp(9);
                             }
                             if (ct == 0) rb[LY::R_XIN] = x_in;
                         }
@@ -799,6 +814,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
             for (int i = 0; i < 7; ++i) p.prof[(size_t)cta * 16 + i] = pf.acc[PROF ? i : 0];
             p.prof[(size_t)cta * 16 + 14] = pf.acc[PROF ? 10 : 0];
             p.prof[(size_t)cta * 16 + 15] = pf.acc[PROF ? 11 : 0];
+            p.prof[(size_t)cta * 16 + 13] = pf.acc[PROF ? 9 : 0];
         }
         };
         if (l == 0) chain_group(std::true_type{});

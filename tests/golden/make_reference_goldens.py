@@ -10,7 +10,8 @@ Cases (seeded inputs = tests/helpers.make_inputs, weights = synth.make_weights, 
               sample_from_discretized_mix_logistic) and the drawn sample under teacher forcing, for 64 steps;
               create_upsample output; calculate_receptive_field.
   ref_mulaw   tiny mu-law model with mel + speaker conditioning: per-step softmax probabilities (predict_proba_incremental).
-  ref_cfg2    the benchmark configuration (BASELINE configs[1] layer sizes), 2 rows x 48 teacher-forced steps.
+  ref_cfg2    the benchmark configuration (BASELINE configs[1] layer sizes), 2 rows x 640 teacher-forced steps: dilation 512 reads
+              non-zero delayed taps from t = 512 on, through the reference's own queue code (model.py:49-64,145).
   ref_train   add_loss (train mode) of the tiny training model: the scalar loss the reference graph evaluates, with and
               without L2, and mu_law_encode / mu_law_decode of an amplitude grid (wavenet/ops.py).
   ref_train_onehot  add_loss for scalar_input=False (mu-law one-hot input, softmax cross-entropy head), tiny models with
@@ -115,9 +116,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'ref_train_onehot.npz'),
                         **{k + '_lc_gc': v for k, v in train_case_loss(dict(synth.tiny_train(3), scalar_input=False), 96, codec=False, snap=True).items()},
                         **train_case_loss(synth.tiny_mulaw(2), 96, codec=False, snap=True))
-    # BASELINE configs[1] layer sizes (30 layers, R=D=128, S=512, MoL-10, 80-channel mel, 2 speakers), 2 rows x 48 steps
-    g = incremental_case(synth.cfg2(2), 48)
-    g['lc_up'] = g['lc_up'][:, :48]
+    # BASELINE configs[1] layer sizes (30 layers, R=D=128, S=512, MoL-10, 80-channel mel, 2 speakers), 2 rows x 640 steps
+    g = incremental_case(synth.cfg2(2), 640)
+    g['lc_up'] = g['lc_up'][:, :640]
     del g['variable_names']
     np.savez_compressed(os.path.join(HERE, 'ref_cfg2.npz'), **g)
     rf = [ref_wavenet.WaveNetModel.calculate_receptive_field(2, [1, 2, 4, 8, 16, 32, 64, 128, 256, 512] * 5, s, 32) for s in (False, True)]

@@ -36,7 +36,8 @@ def test_mu_law_codec():
     g = np.load(os.path.join(GOLD, 'codec.npz'))
     enc = oracle.mu_law_encode(g['grid'], 256)
     assert np.array_equal(enc, g['enc'])
-    assert np.array_equal(enc, np_oracle.mu_law_encode(g['grid'], 256))
+    enc_np = np_oracle.mu_law_encode(g['grid'], 256)        # libm log1p: may differ by one code on a cell edge
+    assert np.mean(enc != enc_np) < 2e-3 and np.abs(enc - enc_np).max() <= 1
     assert enc.min() == 0 and enc.max() == 255
     codes = np.arange(256, dtype=np.float32)
     dec = oracle.mu_law_decode(codes, 256, True)
