@@ -135,6 +135,10 @@ typedef struct wn_generate_args {
     float temperature;            /* generate.py:51; only the mu-law path uses it */
     float *out_samples_dev;       /* (rows, T) fp32 */
     float *out_logits_dev;        /* optional (rows, T, out_dim) raw conv2 output, or NULL */
+    const float *mel_dev;         /* optional (rows, t_mel, lc_channels) mel frames: create_upsample (wavenet/model.py:102-111) is
+                                     then evaluated inside the generation kernel, frame by frame, instead of being materialised
+                                     (generate.py:155,200); lc_dev / t_lc are ignored, lc_shift keeps its meaning */
+    int32_t t_mel;
 } wn_generate_args;
 
 /* Stream-ordered and asynchronous: returns after the launch. */

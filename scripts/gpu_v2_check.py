@@ -52,6 +52,18 @@ def main():
     sa = a.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], T_row=T_row)
     sb = b.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], T_row=T_row)
     print('ragged rows equal:', all(torch.equal(sa[r, :t], sb[r, :t]) for r, t in enumerate(T_row)))
+    # folded create_upsample (mel frames staged by TMA) against the materialised upsampled condition
+    T2 = 1300
+    inp2 = make_inputs(kw, T2)
+    lc2 = a.create_upsample(inp2['mel'])
+    s_lc = a.generate(T2, inp2['x0'], inp2['uniforms'], lc_up=lc2, gc_ids=inp2['gc_ids'], want_logits=True)
+    s_mel = a.generate(T2, inp2['x0'], inp2['uniforms'], mel=inp2['mel'], gc_ids=inp2['gc_ids'], want_logits=True)
+    print('mel-folded == materialised lc: %s' % (torch.equal(s_lc[0], s_mel[0]) and torch.equal(s_lc[1], s_mel[1])))
+    s_lc = a.generate(T2, inp2['forced_full'][:, :400], inp2['uniforms'], lc_up=lc2, lc_shift=399, gc_ids=inp2['gc_ids'])
+    s_mel = a.generate(T2, inp2['forced_full'][:, :400], inp2['uniforms'], mel=inp2['mel'], lc_shift=399, gc_ids=inp2['gc_ids'])
+    print('mel-folded == materialised lc with priming (lc_shift 399): %s' % torch.equal(s_lc, s_mel))
+    s_v1 = b.generate(T2, inp2['x0'], inp2['uniforms'], mel=inp2['mel'], gc_ids=inp2['gc_ids'])
+    print('single-kernel path with mel argument (materialises internally) equal: %s' % torch.equal(s_v1, a.generate(T2, inp2['x0'], inp2['uniforms'], mel=inp2['mel'], gc_ids=inp2['gc_ids'])))
     if mode == 'check':
         return
     if mode == 'time':

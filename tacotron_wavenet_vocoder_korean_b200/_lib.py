@@ -53,7 +53,8 @@ class WnGenerateArgs(C.Structure):
                 ("n_forced", C.c_int32), ("forced_dev", C.c_void_p), ("lc_dev", C.c_void_p),
                 ("t_lc", C.c_int32), ("lc_shift", C.c_int32), ("gc_ids", C.POINTER(C.c_int32)),
                 ("uniforms_dev", C.c_void_p), ("temperature", C.c_float),
-                ("out_samples_dev", C.c_void_p), ("out_logits_dev", C.c_void_p)]
+                ("out_samples_dev", C.c_void_p), ("out_logits_dev", C.c_void_p),
+                ("mel_dev", C.c_void_p), ("t_mel", C.c_int32)]
 
 
 class WnMelConfig(C.Structure):

@@ -188,6 +188,7 @@ struct wn_handle {
     int mb_dual = 0;
     DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
     DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
+    DevBuf g_lc;                                              // wn_generate with mel_dev on a path that materialises the upsampled condition
     size_t mbox_bytes = 0, ring_bytes = 0;
     std::vector<int> up_off;   // float offsets of the upsample kernels inside `upk`
     int64_t launches = 0;
@@ -317,7 +318,7 @@ void wn_destroy(wn_handle *h)
     if (!h) return;
     DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
                       &h->ring_off, &h->status, &h->prof, &h->mb_tab, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
-                      &h->h_out, &h->h_logits};
+                      &h->h_out, &h->h_logits, &h->g_lc};
     for (DevBuf *b : bufs) b->release();
     if (h->v2_sa) cudaStreamDestroy(h->v2_sa);
     if (h->v2_sb) cudaStreamDestroy(h->v2_sb);
@@ -826,6 +827,28 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
     }
     p.forced = a->forced_dev;
     p.lc_up = c.lc_channels ? a->lc_dev : nullptr;
+    p.mel = nullptr;
+    if (a->mel_dev && c.lc_channels) {
+        if (!c.n_upsample) return fail(h, WN_ERR_STATE, "mel_dev given but the model has no upsampling network");
+        if (a->t_mel < 1) return fail(h, WN_ERR_ARG, "t_mel must be >= 1");
+        long hop = 1;
+        for (int i = 0; i < c.n_upsample; ++i) hop *= c.upsample_factor[i];
+        if (h->v2 && c.n_upsample == 3) {
+            // folded into the layer CTAs: mel frames are staged by TMA, nothing is materialised
+            p.mel = a->mel_dev; p.t_mel = a->t_mel; p.n_up = 3; p.hop = (int)hop;
+            p.upk = (const float *)h->upk.p;
+            for (int i = 0; i < 3; ++i) { p.up_f[i] = c.upsample_factor[i]; p.up_off[i] = h->up_off[i]; }
+            p.lc_up = nullptr;
+            p.t_lc = (int)(a->t_mel * hop);
+        } else {
+            const int t_up = (int)(a->t_mel * hop);
+            CUDA_TRY(h, h->g_lc.ensure((size_t)a->rows * t_up * c.lc_channels * 4));
+            int rc = wn_upsample(h, a->mel_dev, a->rows, a->t_mel, (float *)h->g_lc.p, st);
+            if (rc) return rc;
+            p.lc_up = (const float *)h->g_lc.p;
+            p.t_lc = t_up;
+        }
+    }
     p.uniforms = a->uniforms_dev;
     p.out_samples = a->out_samples_dev;
     p.out_logits = a->out_logits_dev;
@@ -836,7 +859,7 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
     for (int b = a->rows; b < c.batch; ++b) { p.T_row[b] = 0; p.gc_id[b] = 0; }
 
     CUDA_TRY(h, cudaMemsetAsync(h->mbox.p, 0, h->mbox_bytes, st));
-    if (h->ring_bytes) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));
+    if (h->ring_bytes && !h->v2) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));      // the cluster path reads the rings only once they hold data
     CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 32, st));
     p.prof = nullptr;
     if (h->prof_on) {
@@ -985,11 +1008,10 @@ int wn_generate_host(wn_handle *h, const wn_generate_args *a, const float *mel_h
         const int t_up = (int)(t_mel * f);
         size_t mel_bytes = (size_t)rows * t_mel * c.lc_channels * 4;
         CUDA_TRY(h, h->h_mel.ensure(mel_bytes));
-        CUDA_TRY(h, h->h_lc.ensure((size_t)rows * t_up * c.lc_channels * 4));
         CUDA_TRY(h, cudaMemcpyAsync(h->h_mel.p, mel_host, mel_bytes, cudaMemcpyHostToDevice, st));
-        int rc = wn_upsample(h, (const float *)h->h_mel.p, rows, t_mel, (float *)h->h_lc.p, st);
-        if (rc) return rc;
-        d.lc_dev = (const float *)h->h_lc.p;
+        d.mel_dev = (const float *)h->h_mel.p;       // wn_generate folds or materialises the upsampling itself
+        d.t_mel = t_mel;
+        d.lc_dev = nullptr;
         d.t_lc = t_up;
     } else if (a->lc_dev) {
         size_t b = (size_t)rows * a->t_lc * c.lc_channels * 4;

@@ -155,7 +155,7 @@ struct V2L {
     static constexpr int OFF_GVEC = OFF_LCS + Lc::TPC * Lc::XS;               // prologue: speaker embedding
     static constexpr int OFF_WC = (OFF_GVEC + Gc::TPC * Gc::XS + 3) & ~3;     // layer 0: causal kernel [ifw][R]
     static constexpr int OFF_BAR = OFF_WC + SH::IFW * SH::R;                  // mbarriers (8 B each): 5 x 32 rows + image
-    static constexpr int OFF_ROWS = OFF_BAR + 2 * (5 * WN_MAX_BATCH + 2);
+    static constexpr int OFF_ROWS = OFF_BAR + 2 * (6 * WN_MAX_BATCH + 2);
     // per row
     static constexpr int ZF = Skip::TPC * Skip::XS;                           // full gated vector, padded for Skip
     static constexpr int R_INX = 0;                                            // [M][R] partial inputs (DSMEM inbox)
@@ -168,7 +168,8 @@ struct V2L {
     static constexpr int R_XRAW = R_ACC + SH::Sm;                              // [R] combined layer input
     static constexpr int R_PRE = R_XRAW + SH::R;                               // [2 Dm] pre-activations of the next step
     static constexpr int R_BFGN = R_PRE + 2 * SH::Dm;                          // [2 Dm] bias + speaker contribution
-    static constexpr int ROWF = R_BFGN + 2 * SH::Dm;
+    static constexpr int R_MEL = R_BFGN + 2 * SH::Dm;                          // [C] mel frame of the row (TMA bulk copy, one frame = hop steps)
+    static constexpr int ROWF = R_MEL + ((SH::C + 3) & ~3);
     __host__ __device__ static constexpr int total_floats(int n_rows) { return OFF_ROWS + n_rows * ROWF; }
 };
 
@@ -250,6 +251,14 @@ __device__ __forceinline__ void v2_ll_wait_n(const MBox &mb, const u64 *logical,
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = __uint_as_float((unsigned)v[i]);
+}
+// one mel frame (C floats) global -> shared by a TMA bulk copy, completion on `bar` (one thread)
+__device__ __forceinline__ void v2_mel_load(float *dst, const float *src, uint32_t bytes, uint64_t *bar)
+{
+    v2_expect_tx(bar, bytes);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 // plain named barrier over the 256-thread helper group
 __device__ __forceinline__ void v2_group_sync(int id)
@@ -378,7 +387,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
     const float *gimg = p.layer_img + (size_t)cta * p.layer_img_floats;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + LY::OFF_BAR);
     uint64_t *xbar = bars, *zbar = bars + WN_MAX_BATCH, *abar = bars + 2 * WN_MAX_BATCH, *fullb = bars + 3 * WN_MAX_BATCH,
-             *prdy = bars + 4 * WN_MAX_BATCH, *ldbar = bars + 5 * WN_MAX_BATCH;
+             *prdy = bars + 4 * WN_MAX_BATCH, *melbar = bars + 5 * WN_MAX_BATCH, *ldbar = bars + 6 * WN_MAX_BATCH;
     float *rows = smem + LY::OFF_ROWS;
 
     const unsigned lbase = (unsigned)(l & 1) * 4u;            // cluster rank of this layer's CTA 0
@@ -390,6 +399,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
     if (tid == 0) {
         for (int b = 0; b < WN_MAX_BATCH; ++b) {
             mbar_init(&xbar[b], 1); mbar_init(&zbar[b], 1); mbar_init(&abar[b], 1); mbar_init(&fullb[b], 1); mbar_init(&prdy[b], 1);
+            mbar_init(&melbar[b], 1);
         }
         mbar_init(ldbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -483,6 +493,11 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
             v2_group_sync(2);
         }
         if (l == 0 && ht < N && p.T_row[ht] > 0) rows[(size_t)ht * LY::ROWF + LY::R_SAMP + SH::O / 3 + 1] = __ldg(p.forced + (size_t)ht * p.n_forced);
+        // folded create_upsample (model.py:102-111): frame 0 of every row, staged by a TMA bulk copy (phase 0 of melbar[b])
+        const bool fold_lc = SH::HAS_LC && p.mel != nullptr;
+        if (fold_lc && ht == 0)
+            for (int b = 0; b < N; ++b)
+                if (p.T_row[b] > 0) v2_mel_load(rows + (size_t)b * LY::ROWF + LY::R_MEL, p.mel + (size_t)b * p.t_mel * SH::C, SH::C * 4, &melbar[b]);
         v2_group_sync(2);
         if (ht == 0)
             for (int b = 0; b < N; ++b) mbar_arrive(&prdy[b]);           // phase 0: pre for t = 0 is ready
@@ -508,10 +523,39 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                 if (!out_dsmem) da = mb_dst(mb, mba_out + b * rowa);
                 // early loads for the next step's pre-activations (independent of this step's x unless d == 1)
                 float oldv = 0.0f, lcv = 0.0f;
-                if (has_next && d >= 2 && ht < R) oldv = __ldcg(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);
+                if (has_next && d >= 2 && t + 1 >= d && ht < R) oldv = __ldcg(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);   // x_l(t+1-d); the queue starts at zero (model.py:64)
+                bool mel_last = false;
+                int mel_next = 0;
                 if (SH::HAS_LC && has_next && ht < SH::C) {
                     long idx = (long)t - p.lc_shift;
-                    if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) lcv = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
+                    if (fold_lc) {
+                        // row idx of the upsampled condition = three conv2d_transpose stages of mel frame idx / hop, evaluated
+                        // exactly as wn_upsample_stage_kernel does (fmul, then fma with the left neighbour), positions < 0 are 0
+                        if (idx >= 0 && idx < (long)p.t_mel * p.hop) {
+                            const int fr = (int)(idx / p.hop);
+                            int rem = (int)(idx % p.hop);
+                            const int a2 = rem % p.up_f[2]; rem /= p.up_f[2];
+                            const int a1 = rem % p.up_f[1];
+                            const int a0 = rem / p.up_f[1];
+                            if (idx % p.hop == 0) v2_mbar_wait(&melbar[b], (unsigned)fr & 1u, ab);      // frame fr has landed
+                            mel_last = (idx % p.hop == p.hop - 1) && fr + 1 < p.t_mel;
+                            mel_next = fr + 1;
+                            const float *mf = rb + LY::R_MEL;
+                            float v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[j] = (ht - j >= 0) ? mf[ht - j] : 0.0f;
+                            const int aa[3] = {a0, a1, a2};
+#pragma unroll
+                            for (int sgi = 0; sgi < 3; ++sgi) {
+                                const float k0 = __ldg(p.upk + p.up_off[sgi] + aa[sgi] * 2), k1 = __ldg(p.upk + p.up_off[sgi] + aa[sgi] * 2 + 1);
+#pragma unroll
+                                for (int j = 0; j < 3 - sgi; ++j) v[j] = (ht - j >= 0) ? ffma(v[j + 1], k1, fmul(v[j], k0)) : 0.0f;
+                            }
+                            lcv = v[0];
+                        }
+                    } else if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) {
+                        lcv = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
+                    }
                 }
                 // layer 0: noise of the draw of step t and the forced input of step t+1 (consumed by the chain's item (b, t+1))
                 float sprep = 0.0f;
@@ -537,6 +581,9 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
                 v2_mbar_wait(&zbar[b], par, ab);                        // the three siblings' slices have landed
                 if (ht == 0) v2_expect_tx(&zbar[b], (uint32_t)((M - 1) * Dm * 4));
                 v2_group_sync(2);
+                // every thread has consumed the row's mel frame: fetch the next one, it is first read a full step from now
+                if (SH::HAS_LC && ht == 0 && mel_last)
+                    v2_mel_load(rb + LY::R_MEL, p.mel + ((size_t)b * p.t_mel + mel_next) * SH::C, SH::C * 4, &melbar[b]);
                 hp.mark(8);
                 // skip 1x1 column col2 over K half c2, from registers, + running skip sum
                 {

@@ -83,6 +83,11 @@ struct WnParams {
     const long long *ring_off;     // [L] float offset of layer l's ring block; block = [M][N][d][R]
     const float *forced;
     const float *lc_up;
+    // folded create_upsample (cluster path): mel frames + the per-stage transposed-conv kernels; lc_up is then null
+    const float *mel;              // (rows, t_mel, C) or null
+    const float *upk;              // all stage kernels, stage s at up_off[s]: (F_s, 2)
+    int32_t t_mel, n_up, hop;      // hop = prod(F_s)
+    int32_t up_f[WN_MAX_UPSAMPLE], up_off[WN_MAX_UPSAMPLE];
     const void *uniforms;
     float *out_samples;
     float *out_logits;

@@ -120,7 +120,7 @@ def main(argv=None):
     mel_input = np.load(config.mel)
     sample_size = mel_input.shape[0] * hparams.hop_size
     mel_input = np.tile(mel_input, (N, 1, 1)).astype(np.float32)                    # generate.py:153
-    upsampled = net.create_upsample(mel_input)                                        # generate.py:155,200
+    # generate.py:155,200 materialise create_upsample(mel); here the kernel evaluates it per step from TMA-staged mel frames
     Q = hparams.quantization_channels
     if config.wav_seed:
         seed = create_seed(config.wav_seed, hparams.sample_rate, Q, net.receptive_field, scalar_input)
@@ -141,7 +141,7 @@ def main(argv=None):
         uniforms = rs.random_sample((N, T))
     gc = [config.gc_id] * N if hparams.gc_channels is not None else None
     start_time = time.time()
-    out = net.generate(T, forced, uniforms, lc_up=upsampled, lc_shift=n_prime, gc_ids=gc, temperature=config.temperature)
+    out = net.generate(T, forced, uniforms, mel=mel_input, lc_shift=n_prime, gc_ids=gc, temperature=config.temperature)
     out = out[:, n_prime:]
     torch.cuda.synchronize()
     print('Generated {} samples x {} rows in {:.3f} sec'.format(sample_size, N, time.time() - start_time))

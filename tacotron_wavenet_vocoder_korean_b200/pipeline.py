@@ -64,7 +64,6 @@ class TextToSpeech(object):
             lc = torch.zeros((rows, fmax, mels[grp[0]].shape[1]), dtype=torch.float32, device=mels[grp[0]].device)
             for r, i in enumerate(grp):
                 lc[r, :mels[i].shape[0]] = mels[i]
-            up = self.wn.create_upsample(lc)
             if self.wn.scalar_input:
                 x0 = (2 * rs.rand(rows, 1) - 1).astype(np.float32)                               # generate.py:186-188
                 uni = torch.empty((rows, T, nr1), dtype=torch.float32, device=lc.device).uniform_(1e-5, 1 - 1e-5)
@@ -72,7 +71,7 @@ class TextToSpeech(object):
                 x0 = rs.randint(self.wn.quantization_channels, size=(rows, 1)).astype(np.float32)  # generate.py:190-192
                 uni = torch.rand((rows, T), dtype=torch.float64, device=lc.device)
             gc = [int(speaker_ids[i]) for i in grp] if self.wn.global_condition_channels else None
-            wav = self.wn.generate(T, x0, uni, lc_up=up, lc_shift=0, gc_ids=gc,
+            wav = self.wn.generate(T, x0, uni, mel=lc, lc_shift=0, gc_ids=gc,
                                    T_row=[int(mels[i].shape[0]) * self.hop for i in grp])
             wav = wav.cpu().numpy()
             for r, i in enumerate(grp):

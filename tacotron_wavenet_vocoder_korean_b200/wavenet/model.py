@@ -173,12 +173,14 @@ class WaveNetModel(object):
             return out
 
     def generate(self, T, forced, uniforms, lc_up=None, lc_shift=0, gc_ids=None, temperature=1.0,
-                 want_logits=False, T_row=None, sync=True):
+                 want_logits=False, T_row=None, sync=True, mel=None):
         """The fused generate.py:202-233 loop.  All tensor arguments live on the GPU (moved if not).
 
         forced   (rows, n_forced>=1): x_in(t) for t < n_forced; afterwards the drawn sample feeds back.
         uniforms (rows, T, nr_mix+1) fp32 [scalar input] or (rows, T) fp64 [mu-law].
         lc_up    (rows, T_lc, C) upsampled local condition or None; lc_shift as in include/wn_b200.h.
+        mel      (rows, T_mel, C) mel frames instead of lc_up: create_upsample is evaluated inside the kernel
+                 (frames staged by TMA), nothing is materialised.
         Returns samples (rows, T) fp32 [and logits (rows, T, out_dim)]."""
         if not self._finalized:
             raise RuntimeError("load_state_dict() must be called before generate()")
@@ -203,6 +205,10 @@ class WaveNetModel(object):
                 lc_up = torch.as_tensor(lc_up, dtype=torch.float32, device=dev).contiguous()
                 a.lc_dev, a.t_lc = lc_up.data_ptr(), lc_up.shape[1]
                 keep.append(lc_up)
+            if mel is not None:
+                mel = torch.as_tensor(mel, dtype=torch.float32, device=dev).contiguous()
+                a.mel_dev, a.t_mel = mel.data_ptr(), mel.shape[1]
+                keep.append(mel)
             a.lc_shift = int(lc_shift)
             if gc_ids is not None:
                 g = (C.c_int32 * rows)(*[int(v) for v in gc_ids])

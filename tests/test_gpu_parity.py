@@ -152,6 +152,42 @@ def test_cluster_path_equals_single_kernel_path():
             assert torch.equal(sa[r, :n], sb[r, :n]) and torch.equal(la[r, :n], lb[r, :n])
 
 
+def test_folded_upsample_equals_materialised_condition():
+    """north_star: "mel local-conditioning upsample staged via TMA".  Passing mel frames (wn_generate_args.mel_dev) makes the
+    layer CTAs evaluate create_upsample (model.py:102-111) per step from TMA-staged frames; samples and logits are
+    bit-identical to feeding the materialised (rows, T, 80) tensor, also with priming (lc_shift) and ragged rows, and
+    bit-identical to the oracle (which upsamples on the host)."""
+    kw = synth.cfg2(4)
+    net, w = build(kw)
+    T = 1500                                                    # five mel frames
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    a = net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    b = net.generate(T, inp['x0'], inp['uniforms'], mel=inp['mel'], gc_ids=inp['gc_ids'], want_logits=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    T_row = [1500, 299, 301, 0]
+    a = net.generate(T, inp['forced_full'][:, :350], inp['uniforms'], lc_up=lc, lc_shift=349, gc_ids=inp['gc_ids'], T_row=T_row)
+    b = net.generate(T, inp['forced_full'][:, :350], inp['uniforms'], mel=inp['mel'], lc_shift=349, gc_ids=inp['gc_ids'], T_row=T_row)
+    for r, n in enumerate(T_row):
+        assert torch.equal(a[r, :n], b[r, :n])
+    om = oracle_model(kw, w)
+    _oracle_threads(4)
+    try:
+        so = om.generate(600, inp['x0'], inp['uniforms'][:, :600], lc_up=om.upsample(inp['mel'])[:, :600], gc_ids=inp['gc_ids'],
+                         plan=plan_from_dict(net.plan()))
+    finally:
+        _oracle_threads(1)
+    s = net.generate(600, inp['x0'], inp['uniforms'][:, :600], mel=inp['mel'], gc_ids=inp['gc_ids']).cpu().numpy()
+    assert np.array_equal(s, so)
+    # models without the 3-stage upsampler of cfg-2 / other kernels materialise internally: same results
+    kw = synth.tiny_mol()
+    net, _ = build(kw)
+    inp = make_inputs(kw, 120)
+    a = net.generate(120, inp['x0'], inp['uniforms'], lc_up=net.create_upsample(inp['mel']), gc_ids=inp['gc_ids'])
+    b = net.generate(120, inp['x0'], inp['uniforms'], mel=inp['mel'], gc_ids=inp['gc_ids'])
+    assert torch.equal(a, b)
+
+
 def test_fast_activation_within_north_star_tolerance():
     """WN_FLAG_FAST_ACT (ex2.approx / rcp.approx gate, scalar-input path only): teacher-forced logits within 1e-4 of the
     oracle (north_star's bound for float MoL logits) over more than one receptive field, and of the reference's own run."""
