@@ -144,6 +144,28 @@ typedef struct wn_generate_args {
 /* Stream-ordered and asynchronous: returns after the launch. */
 int wn_generate(wn_handle *h, const wn_generate_args *args, void *stream);
 
+/* ONE step of the network with persistent device queues: what the reference's per-sample loop evaluates through
+ * sess.run(predict_proba_incremental) (generate.py:202-211, wavenet/model.py:215-245).  A wn_state holds the causal,
+ * local-condition and dilation queues of model.py:49-64 for `rows` utterances, zeroed like queue_initializer
+ * (generate.py:163); every wn_step advances them by one position, so a call costs O(1) in the number of steps taken.
+ * A loop of wn_step calls fed with its own draws reproduces wn_generate bit for bit (same evaluation plan). */
+typedef struct wn_state wn_state;
+int wn_state_create(wn_handle *h, int rows, wn_state **out);
+int wn_state_reset(wn_handle *h, wn_state *s, void *stream);          /* queue_initializer */
+void wn_state_destroy(wn_state *s);
+typedef struct wn_step_args {
+    int32_t rows;                 /* must equal the state's rows */
+    const float *x_in_dev;        /* (rows) network input: previous sample, or mu-law id stored as float (generate.py:204) */
+    const float *lc_row_dev;      /* (rows, lc_channels) upsampled[:, step, :] (generate.py:211) or NULL */
+    const int32_t *gc_ids;        /* HOST (rows) or NULL */
+    const void *uniforms_dev;     /* optional: (rows, out_channels/3 + 1) fp32 [scalar input] or (rows) fp64 [one-hot]: also draw */
+    float temperature;            /* generate.py:51, one-hot models, used with uniforms_dev */
+    float *out_logits_dev;        /* optional (rows, out_dim) raw conv2 output */
+    float *out_probs_dev;         /* one-hot models: optional (rows, Q) float32(softmax(float64(logits))), the node's return value */
+    float *out_sample_dev;        /* optional (rows): the drawn sample / id when uniforms_dev is given */
+} wn_step_args;
+int wn_step(wn_handle *h, wn_state *s, const wn_step_args *args, void *stream);
+
 /* Synchronises `stream` and reports WN_ERR_TIMEOUT if the kernel's watchdog aborted the last launch. */
 int wn_sync_check(wn_handle *h, void *stream);
 

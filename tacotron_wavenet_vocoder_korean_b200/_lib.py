@@ -57,6 +57,12 @@ class WnGenerateArgs(C.Structure):
                 ("mel_dev", C.c_void_p), ("t_mel", C.c_int32)]
 
 
+class WnStepArgs(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("x_in_dev", C.c_void_p), ("lc_row_dev", C.c_void_p), ("gc_ids", C.POINTER(C.c_int32)),
+                ("uniforms_dev", C.c_void_p), ("temperature", C.c_float), ("out_logits_dev", C.c_void_p),
+                ("out_probs_dev", C.c_void_p), ("out_sample_dev", C.c_void_p)]
+
+
 class WnMelConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_int32), ("fft_size", C.c_int32), ("hop_size", C.c_int32), ("win_size", C.c_int32),
                 ("num_mels", C.c_int32), ("preemphasize", C.c_int32), ("preemphasis", C.c_float),
@@ -65,7 +71,8 @@ class WnMelConfig(C.Structure):
 
 EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_plan_config", "wn_get_plan",
            "wn_get_info", "wn_receptive_field", "wn_upsample", "wn_generate", "wn_sync_check",
-           "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode", "wn_melspectrogram"]
+           "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode", "wn_melspectrogram",
+           "wn_state_create", "wn_state_reset", "wn_state_destroy", "wn_step"]
 
 _lib = None
 
@@ -103,6 +110,11 @@ def lib():
         L.wn_upsample.argtypes = [H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.wn_generate.argtypes = [H, C.POINTER(WnGenerateArgs), C.c_void_p]
         L.wn_sync_check.argtypes = [H, C.c_void_p]
+        L.wn_state_create.argtypes = [H, C.c_int, C.POINTER(H)]
+        L.wn_state_reset.argtypes = [H, H, C.c_void_p]
+        L.wn_state_destroy.argtypes = [H]
+        L.wn_state_destroy.restype = None
+        L.wn_step.argtypes = [H, H, C.POINTER(WnStepArgs), C.c_void_p]
         L.wn_generate_host.argtypes = [H, C.POINTER(WnGenerateArgs), C.c_void_p, C.c_int]
         L.wn_mu_law_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.wn_mu_law_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

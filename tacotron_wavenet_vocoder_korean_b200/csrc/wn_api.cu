@@ -188,7 +188,10 @@ struct wn_handle {
     int mb_dual = 0;
     DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
     DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
-    DevBuf g_lc;                                              // wn_generate with mel_dev on a path that materialises the upsampled condition
+    DevBuf g_lc;
+    DevBuf raw, raw_layers, step_ring_off;                    // TF-layout weights on the device + per-layer pointer table (wn_step)
+    std::map<std::string, size_t> raw_off;
+    long long step_ring_floats = 0;                                              // wn_generate with mel_dev on a path that materialises the upsampled condition
     size_t mbox_bytes = 0, ring_bytes = 0;
     std::vector<int> up_off;   // float offsets of the upsample kernels inside `upk`
     int64_t launches = 0;
@@ -318,7 +321,7 @@ void wn_destroy(wn_handle *h)
     if (!h) return;
     DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
                       &h->ring_off, &h->status, &h->prof, &h->mb_tab, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
-                      &h->h_out, &h->h_logits, &h->g_lc};
+                      &h->h_out, &h->h_logits, &h->g_lc, &h->raw, &h->raw_layers, &h->step_ring_off};
     for (DevBuf *b : bufs) b->release();
     if (h->v2_sa) cudaStreamDestroy(h->v2_sa);
     if (h->v2_sb) cudaStreamDestroy(h->v2_sb);
@@ -512,6 +515,7 @@ int wn_finalize(wn_handle *h)
     const int N = c.batch, L = c.n_layers, R = c.residual_channels, D = c.dilation_channels, S = c.skip_channels;
     const int G = c.gc_channels, C = c.lc_channels, O = h->out_dim, Q = c.quantization_channels, ifw = c.initial_filter_width;
 
+    h->raw.release();                          // wn_step's TF-layout copy follows the weights
     int dev = 0;
     cudaDeviceProp prop;
     CUDA_TRY(h, cudaGetDevice(&dev));
@@ -1041,6 +1045,152 @@ int wn_generate_host(wn_handle *h, const wn_generate_args *a, const float *mel_h
     CUDA_TRY(h, cudaMemcpyAsync(a->out_samples_dev, h->h_out.p, ob, cudaMemcpyDeviceToHost, st));
     if (a->out_logits_dev) CUDA_TRY(h, cudaMemcpyAsync(a->out_logits_dev, h->h_logits.p, ob * h->out_dim, cudaMemcpyDeviceToHost, st));
     return wn_sync_check(h, st);
+}
+
+/* ---- single step with persistent queues (wn_step.cuh) --------------------------------------------------------- */
+struct wn_state {
+    wn_handle *h;
+    int rows;
+    DevBuf buf;
+    long long stride;
+    int off_cq, off_lc, off_ring0;
+};
+
+static int ensure_raw_weights(wn_handle *h)
+{
+    if (h->raw.p) return WN_OK;
+    const wn_config &c = h->cfg;
+    const int L = c.n_layers;
+    size_t total = 0;
+    h->raw_off.clear();
+    for (auto &kv : h->w) { h->raw_off[kv.first] = total; total += (kv.second.size() + 3) & ~(size_t)3; }
+    const size_t zeros_off = total;
+    total += 1024;                                                   // shared zero vector for absent biases
+    std::vector<float> host(total, 0.0f);
+    for (auto &kv : h->w) memcpy(host.data() + h->raw_off[kv.first], kv.second.data(), kv.second.size() * 4);
+    CUDA_TRY(h, h->raw.ensure(total * 4));
+    CUDA_TRY(h, cudaMemcpy(h->raw.p, host.data(), total * 4, cudaMemcpyHostToDevice));
+    const float *base = (const float *)h->raw.p;
+    auto ptr = [&](const std::string &nm) -> const float * {
+        auto it = h->raw_off.find(nm);
+        return it == h->raw_off.end() ? base + zeros_off : base + it->second;
+    };
+    std::vector<WnStepLayer> lay(L);
+    std::vector<long long> roff(L);
+    long long rt = 0;
+    for (int l = 0; l < L; ++l) {
+        const std::string pre = "wavenet/dilated_stack/layer" + std::to_string(l) + "/dilation_layer/";
+        lay[l] = WnStepLayer{ptr(pre + "conv_filter/kernel"), ptr(pre + "conv_gate/kernel"), ptr(pre + "conv_filter/bias"), ptr(pre + "conv_gate/bias"),
+                             ptr(pre + "gc_filter/kernel"), ptr(pre + "gc_gate/kernel"), ptr(pre + "lc_filter/kernel"), ptr(pre + "lc_gate/kernel"),
+                             ptr(pre + "dense/kernel"), ptr(pre + "dense/bias"), ptr(pre + "skip/kernel"), ptr(pre + "skip/bias")};
+        roff[l] = rt;
+        rt += (long long)c.dilations[l] * c.residual_channels;
+    }
+    if (std::max(std::max(c.skip_channels, c.dilation_channels), std::max(c.residual_channels, h->out_dim)) > 1024)
+        return fail(h, WN_ERR_ARG, "wn_step: channel counts above 1024 are not supported");
+    h->step_ring_floats = rt;
+    CUDA_TRY(h, h->raw_layers.ensure(L * sizeof(WnStepLayer)));
+    CUDA_TRY(h, cudaMemcpy(h->raw_layers.p, lay.data(), L * sizeof(WnStepLayer), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, h->step_ring_off.ensure(L * sizeof(long long)));
+    CUDA_TRY(h, cudaMemcpy(h->step_ring_off.p, roff.data(), L * sizeof(long long), cudaMemcpyHostToDevice));
+    return WN_OK;
+}
+
+int wn_state_create(wn_handle *h, int rows, wn_state **out)
+{
+    if (!h || !out) return WN_ERR_ARG;
+    *out = nullptr;
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "wn_state_create before wn_finalize");
+    if (rows < 1 || rows > WN_MAX_BATCH) return fail(h, WN_ERR_ARG, "rows must be in 1..%d", WN_MAX_BATCH);
+    int rc = ensure_raw_weights(h);
+    if (rc) return rc;
+    const wn_config &c = h->cfg;
+    wn_state *s = new wn_state();
+    s->h = h; s->rows = rows;
+    s->off_cq = 4;
+    s->off_lc = s->off_cq + ((std::max(c.initial_filter_width, 1) + 3) & ~3);
+    s->off_ring0 = s->off_lc + ((std::max(c.lc_channels, 1) + 3) & ~3);
+    s->stride = s->off_ring0 + h->step_ring_floats;
+    cudaError_t e = s->buf.ensure((size_t)rows * s->stride * 4);
+    if (e != cudaSuccess) { delete s; return fail(h, WN_ERR_CUDA, "wn_state_create: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return wn_state_reset(h, s, nullptr);
+}
+
+int wn_state_reset(wn_handle *h, wn_state *s, void *stream)
+{
+    if (!h || !s) return WN_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemsetAsync(s->buf.p, 0, (size_t)s->rows * s->stride * 4, st));
+    // one-hot models: the causal queue starts with all-zero one-hot rows (ids -1), queue_initializer
+    std::vector<int> ids(3, -1);
+    ids[0] = 0;
+    for (int b = 0; b < s->rows; ++b)
+        CUDA_TRY(h, cudaMemcpyAsync((char *)s->buf.p + (size_t)b * s->stride * 4, ids.data(), 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return WN_OK;
+}
+
+void wn_state_destroy(wn_state *s)
+{
+    if (!s) return;
+    s->buf.release();
+    delete s;
+}
+
+int wn_step(wn_handle *h, wn_state *s, const wn_step_args *a, void *stream)
+{
+    if (!h || !s || !a) return WN_ERR_ARG;
+    if (s->h != h) return fail(h, WN_ERR_ARG, "wn_step: the state belongs to another handle");
+    if (a->rows != s->rows) return fail(h, WN_ERR_ARG, "wn_step: rows=%d but the state holds %d rows", a->rows, s->rows);
+    if (!a->x_in_dev) return fail(h, WN_ERR_ARG, "wn_step: x_in_dev required");
+    if (!h->finalized) return fail(h, WN_ERR_STATE, "wn_step before wn_finalize");
+    { int rc = ensure_raw_weights(h); if (rc) return rc; }
+    const wn_config &c = h->cfg;
+    if (c.gc_channels && !a->gc_ids) return fail(h, WN_ERR_ARG, "gc_ids required: the model is globally conditioned (generate.py:72-77)");
+    if (!c.scalar_input && a->uniforms_dev && !(a->temperature > 0.0f)) return fail(h, WN_ERR_ARG, "temperature must be > 0");
+    WnStepParams p;
+    memset(&p, 0, sizeof p);
+    p.rows = a->rows; p.L = c.n_layers; p.R = c.residual_channels; p.D = c.dilation_channels; p.S = c.skip_channels;
+    p.O = h->out_dim; p.Q = c.quantization_channels; p.G = c.gc_channels; p.C = c.lc_channels; p.ifw = c.initial_filter_width;
+    p.scalar = c.scalar_input; p.nr_mix = c.scalar_input ? h->out_dim / 3 : 0;
+    p.plan = h->plan;
+    for (int i = 0; i < c.n_layers; ++i) p.dil[i] = c.dilations[i];
+    const float *base = (const float *)h->raw.p;
+    auto ptr = [&](const char *nm) -> const float * { auto it = h->raw_off.find(nm); return it == h->raw_off.end() ? nullptr : base + it->second; };
+    p.layers = (const WnStepLayer *)h->raw_layers.p;
+    p.wc = ptr("wavenet/conv1d/kernel"); p.w1 = ptr("wavenet/conv1d_1/kernel"); p.w2 = ptr("wavenet/conv1d_2/kernel");
+    p.b1 = ptr("wavenet/conv1d_1/bias"); p.b2 = ptr("wavenet/conv1d_2/bias");
+    if (!p.b1 || !p.b2) {                        // absent biases: the zero vector at the end of the arena
+        size_t total = 0;
+        for (auto &kv : h->w) total += (kv.second.size() + 3) & ~(size_t)3;
+        if (!p.b1) p.b1 = base + total;
+        if (!p.b2) p.b2 = base + total;
+    }
+    p.gc_table = ptr("wavenet/gc_embedding");
+    p.state = (float *)s->buf.p; p.state_stride = s->stride;
+    p.off_cq = s->off_cq; p.off_lc = s->off_lc; p.off_ring0 = s->off_ring0;
+    p.ring_off = (const long long *)h->step_ring_off.p;
+    p.x_in = a->x_in_dev; p.lc_row = c.lc_channels ? a->lc_row_dev : nullptr;
+    for (int b = 0; b < a->rows; ++b) {
+        int gid = a->gc_ids ? a->gc_ids[b] : 0;
+        if (c.gc_channels && (gid < 0 || gid >= c.gc_cardinality)) return fail(h, WN_ERR_ARG, "gc_ids[%d]=%d outside 0..%d", b, gid, c.gc_cardinality - 1);
+        p.gc_id[b] = gid;
+    }
+    p.uniforms = a->uniforms_dev; p.temperature = a->temperature;
+    p.out_logits = a->out_logits_dev; p.out_probs = c.scalar_input ? nullptr : a->out_probs_dev; p.out_sample = a->out_sample_dev;
+    const int maxc = std::max(std::max(c.skip_channels, c.dilation_channels), std::max(c.residual_channels, h->out_dim));
+    p.smem_maxc = maxc;
+    const int R = p.R, D = p.D, S = p.S, O = p.O;
+    size_t floats = 2 * R + 3 * D + 2 * S + ((std::max(O, WN_NT) + 3) & ~3) + maxc + ((p.G + 3) & ~3) + ((p.C + 3) & ~3) + ((p.ifw + 3) & ~3) + 32 + 2 * 18 +
+                    (size_t)64 * maxc + 16;
+    const size_t smem = floats * 4;
+    if (smem > (size_t)kMaxDynSmem) return fail(h, WN_ERR_ARG, "wn_step: shared-memory need %zu exceeds the device limit", smem);
+    CUDA_TRY(h, cudaFuncSetAttribute(wn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wn_step_kernel<<<a->rows, WN_NT, smem, (cudaStream_t)stream>>>(p);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches++;
+    return WN_OK;
 }
 
 int wn_mu_law_encode(const float *audio_dev, int64_t n, int quantization_channels, int32_t *out_dev, void *stream)

@@ -597,7 +597,8 @@ __device__ void tail_role(const WnParams &p, int mt)
 
 // float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231).
 // Called by every thread of the sampler CTA; returns the drawn id (as float) to all of them.
-__device__ float mulaw_draw_cta(const float *c2s, int Q, float temperature, double u64v, float *misc, double *red, double *cdf)
+__device__ float mulaw_draw_cta(const float *c2s, int Q, float temperature, double u64v, float *misc, double *red, double *cdf,
+                                float *probs_out = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // float64 softmax (model.py:243) -> fp32; temperature + categorical draw (generate.py:219-231)
@@ -623,6 +624,7 @@ __device__ float mulaw_draw_cta(const float *c2s, int Q, float temperature, doub
     __syncthreads();
     const double den = red[8];
     float pr = act ? (float)__ddiv_rn(e, den) : 0.0f;
+    if (probs_out != nullptr && act) probs_out[tid] = pr;          // predict_proba_incremental's return value (model.py:243)
     float s = fdiv(wn::log32(pr), temperature);
     float a = s;
     for (int off = 1; off < 32; off <<= 1) {
@@ -795,6 +797,7 @@ __device__ void sampler_role(const WnParams &p)
 #include "wn_kernel_static.cuh"
 #include "wn_kernel_ws.cuh"
 #include "wn_kernel_v2.cuh"
+#include "wn_step.cuh"
 
 // LL-mailbox ping-pong between CTA 0 and CTA 1: average round trip in clock cycles (diagnostic).
 __device__ void pingpong_role(u64 *box, int iters, long long *out)

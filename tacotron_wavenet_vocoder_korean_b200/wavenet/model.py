@@ -97,7 +97,7 @@ class WaveNetModel(object):
         if rc != 0:
             raise ValueError(_lib.lib().wn_last_error(None).decode())
         self._finalized = False
-        self._inc = None            # state of the eager predict_proba_incremental emulation
+        self._inc = None            # wn_state of predict_proba_incremental: the persistent device queues
         # attribute the reference's generate.py runs through sess.run before the loop (generate.py:163);
         # the kernel zeroes its queues at every launch, so this is a no-op kept for drop-in callers.
         self.queue_initializer = lambda: None
@@ -105,6 +105,9 @@ class WaveNetModel(object):
     # ------------------------------------------------------------------ plumbing
     def __del__(self):
         try:
+            if getattr(self, "_inc", None) is not None and self._inc.value:
+                _lib.lib().wn_state_destroy(self._inc)
+                self._inc = None
             if getattr(self, "_h", None) and self._h.value:
                 _lib.lib().wn_destroy(self._h)
                 self._h = C.c_void_p()
@@ -264,46 +267,69 @@ class WaveNetModel(object):
             return out
 
     def predict_proba_incremental(self, waveform, upsampled_local_condition=None, global_condition=None,
-                                  name='wavenet', uniforms=None):
-        """Eager stand-in for the graph node of wavenet/model.py:215-245: feed ONE step, get the
-        softmax probabilities (N, Q) or, for scalar input, a sample (N, 1).
+                                  name='wavenet', uniforms=None, temperature=1.0, return_draw=False):
+        """The graph node of wavenet/model.py:215-245, evaluated eagerly: feed ONE step, get the softmax probabilities
+        (N, Q) or, for scalar input, a sample (N, 1) -- what the reference's loop obtains from sess.run (generate.py:211).
 
-        The reference evaluates this node once per audio sample through sess.run, with the queues as
-        TF variables.  Here the state is the history of fed inputs: every call replays the history
-        teacher-forced through the persistent kernel and returns the last step, which is O(T^2) and
-        meant for checking/short runs only -- `generate()` is the fused production path."""
+        The causal / local-condition / dilation queues of model.py:49-64 are persistent device buffers (wn_state) that
+        every call advances by one position (wn_step): O(1) per call, any number of calls.  `reset_incremental()` is
+        sess.run(net.queue_initializer) (generate.py:163).  For scalar input the node draws from the mixture of logistics
+        itself (mixture.py:84-114); `uniforms` (N, nr_mix + 1) makes the draw reproducible, otherwise it is random like
+        TF's.  `return_draw=True` (one-hot models, with uniforms (N,) float64) also returns the id generate.py:219-231
+        would draw on the host."""
         dev = self.device
-        w = torch.as_tensor(waveform, dtype=torch.float32, device=dev).reshape(self.batch_size, -1)[:, -1:]
-        if self._inc is None:
-            self._inc = {"x": [], "lc": [], "u": []}
-        st = self._inc
-        st["x"].append(w)
-        if self.local_condition_channels:
-            if upsampled_local_condition is None:
-                raise ValueError("upsampled_local_condition is required (model.py:125)")
-            st["lc"].append(torch.as_tensor(upsampled_local_condition, dtype=torch.float32, device=dev)
-                            .reshape(self.batch_size, 1, self.local_condition_channels))
-        T = len(st["x"])
-        nr1 = self.out_channels // 3 + 1
-        if self.scalar_input:
-            u = uniforms if uniforms is not None else torch.empty(self.batch_size, 1, nr1, device=dev).uniform_(1e-5, 1 - 1e-5)
-            st["u"].append(torch.as_tensor(u, dtype=torch.float32, device=dev).reshape(self.batch_size, 1, nr1))
-            uni = torch.cat(st["u"], dim=1)
-        else:
-            uni = torch.full((self.batch_size, T), 0.5, dtype=torch.float64, device=dev)
-        lc = torch.cat(st["lc"], dim=1) if st["lc"] else None
-        gc = None
-        if self.global_condition_channels:
-            gc = [int(v) for v in (global_condition if global_condition is not None else [0] * self.batch_size)]
-        samples, logits = self.generate(T, torch.cat(st["x"], dim=1), uni, lc_up=lc, lc_shift=0, gc_ids=gc,
-                                        want_logits=True)
-        if self.scalar_input:
-            return samples[:, -1:]
-        return torch.softmax(logits[:, -1, :].to(torch.float64), dim=-1).to(torch.float32)
+        lib = _lib.lib()
+        with self._dev_guard():
+            if self._inc is None:
+                h = C.c_void_p()
+                self._check(lib.wn_state_create(self._h, self.batch_size, C.byref(h)))
+                self._inc = h
+            N = self.batch_size
+            x = torch.as_tensor(waveform, dtype=torch.float32, device=dev).reshape(N, -1)[:, -1].contiguous()
+            a = _lib.WnStepArgs()
+            a.rows = N
+            a.x_in_dev = x.data_ptr()
+            keep = [x]
+            if self.local_condition_channels:
+                if upsampled_local_condition is None:
+                    raise ValueError("upsampled_local_condition is required (model.py:125)")
+                lc = torch.as_tensor(upsampled_local_condition, dtype=torch.float32, device=dev).reshape(N, self.local_condition_channels).contiguous()
+                a.lc_row_dev = lc.data_ptr()
+                keep.append(lc)
+            if self.global_condition_channels:
+                gids = [int(v) for v in (global_condition if global_condition is not None else [0] * N)]
+                g = (C.c_int32 * N)(*gids)
+                a.gc_ids = C.cast(g, C.POINTER(C.c_int32))
+                keep.append(g)
+            a.temperature = float(temperature)
+            if self.scalar_input:
+                nr1 = self.out_channels // 3 + 1
+                u = uniforms if uniforms is not None else torch.empty(N, nr1, device=dev).uniform_(1e-5, 1 - 1e-5)
+                u = torch.as_tensor(u, dtype=torch.float32, device=dev).reshape(N, nr1).contiguous()
+                out = torch.empty((N, 1), dtype=torch.float32, device=dev)
+                a.uniforms_dev, a.out_sample_dev = u.data_ptr(), out.data_ptr()
+                keep += [u]
+                self._check(lib.wn_step(self._h, self._inc, C.byref(a), self._stream()))
+                self._keep_step = keep
+                return out
+            probs = torch.empty((N, self.quantization_channels), dtype=torch.float32, device=dev)
+            a.out_probs_dev = probs.data_ptr()
+            draw = None
+            if return_draw:
+                if uniforms is None:
+                    raise ValueError("return_draw needs uniforms (N,) float64")
+                u = torch.as_tensor(uniforms, dtype=torch.float64, device=dev).reshape(N).contiguous()
+                draw = torch.empty((N,), dtype=torch.float32, device=dev)
+                a.uniforms_dev, a.out_sample_dev = u.data_ptr(), draw.data_ptr()
+                keep.append(u)
+            self._check(lib.wn_step(self._h, self._inc, C.byref(a), self._stream()))
+            self._keep_step = keep
+            return (probs, draw) if return_draw else probs
 
     def reset_incremental(self):
         """Counterpart of sess.run(net.queue_initializer), generate.py:163."""
-        self._inc = None
+        if self._inc is not None:
+            self._check(_lib.lib().wn_state_reset(self._h, self._inc, self._stream()))
 
     # ------------------------------------------------------------------ training (SURVEY.md 8f next-3)
     def trainer(self, sample_size, dtype='bf16'):

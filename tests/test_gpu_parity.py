@@ -344,19 +344,55 @@ def test_host_buffer_entry_point_equals_device_entry_point():
     assert np.array_equal(dev, host)
 
 
-def test_predict_proba_incremental_emulation():
+def test_predict_proba_incremental_is_a_true_single_step():
+    """the drop-in predict_proba_incremental must be an O(1) state-carrying step (wn_step, persistent device
+    queues), usable by a caller that keeps the reference's own per-sample loop (generate.py:202-233).  Drive that loop
+    shape for more than a receptive field and compare with the fused wn_generate: identical ids / samples."""
+    import time
+    # --- one-hot model: probabilities out, host-style categorical draw (generate.py:219-231) fed back --------------
     kw = synth.tiny_mulaw()
     net, w = build(kw)
     om = oracle_model(kw, w)
-    inp = make_inputs(kw, 5)
-    _, lo = om.generate(5, inp['forced_full'][:, :5], inp['uniforms'], plan=plan_from_dict(net.plan()), want_logits=True)
+    T = net.receptive_field + 60
+    inp = make_inputs(kw, T)
+    fused, logits = net.generate(T, inp['x0'], inp['uniforms'], want_logits=True)
     net.reset_incremental()
-    for t in range(5):
-        proba = net.predict_proba_incremental(inp['forced_full'][:, t:t + 1])
+    x = torch.as_tensor(inp['x0'], dtype=torch.float32).cuda()
+    ids = []
+    for t in range(T):
+        proba, draw = net.predict_proba_incremental(x, uniforms=inp['uniforms'][:, t], return_draw=True)
         assert proba.shape == (2, 256)
-        ref = np.stack([oracle.softmax_probs(r) for r in lo[:, t]])
-        np.testing.assert_allclose(proba.cpu().numpy(), ref, rtol=2e-6, atol=1e-12)
-        np.testing.assert_allclose(proba.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)   # generate.py:227 invariant
+        if t < 5 or t == T - 1:
+            ref = np.stack([oracle.softmax_probs(r) for r in logits[:, t].cpu().numpy()])
+            assert np.array_equal(proba.cpu().numpy(), ref)                         # float32(softmax(float64(.))), model.py:243
+            np.testing.assert_allclose(proba.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)   # generate.py:227 invariant
+        ids.append(draw)
+        x = draw.reshape(2, 1)
+    assert torch.equal(torch.stack(ids, dim=1), fused)
+    # --- the benchmark model: scalar input, mel + speaker conditioned, draws inside the node (mixture.py:84-114) ------
+    kw = synth.cfg2(2)
+    net, w = build(kw)
+    T = net.receptive_field + 120                                                  # 3221 calls
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+    fused = net.generate(T, inp['x0'], inp['uniforms'], mel=inp['mel'], gc_ids=inp['gc_ids'])
+    uni = torch.as_tensor(inp['uniforms']).cuda()
+    x = torch.as_tensor(inp['x0'], dtype=torch.float32).cuda()
+    out, stamps = [], []
+    for t in range(T):
+        if t in (100, 200, T - 200, T - 100):
+            torch.cuda.synchronize()
+            stamps.append(time.perf_counter())
+        x = net.predict_proba_incremental(x, lc[:, t], inp['gc_ids'], uniforms=uni[:, t])
+        out.append(x[:, 0])
+    assert torch.equal(torch.stack(out, dim=1), fused)
+    early, late = stamps[1] - stamps[0], stamps[3] - stamps[2]
+    assert late < 2.0 * early + 0.05, (early, late)                                 # O(1) per call: no history replay
+    # queue_initializer starts over
+    net.reset_incremental()
+    x0 = torch.as_tensor(inp['x0'], dtype=torch.float32).cuda()
+    again = net.predict_proba_incremental(x0, lc[:, 0], inp['gc_ids'], uniforms=uni[:, 0])
+    assert torch.equal(again[:, 0], fused[:, 0])
 
 
 def test_mu_law_codec_on_device():
