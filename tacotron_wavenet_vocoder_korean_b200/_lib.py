@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwn_b200.so")
+LIB_PATH = os.environ.get("WN_B200_LIB") or os.path.join(_HERE, "libwn_b200.so")      # WN_B200_LIB: A/B runs of two builds on one box
 
 WN_MAX_LAYERS = 256
 WN_MAX_UPSAMPLE = 8
