@@ -11,9 +11,12 @@ lib = _lib.lib()
 lib.wn_debug_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
 
 
-def build(kw, **extra):
+def build(kw, no16=False, **extra):
+    if no16:
+        os.environ['WN_NO_CLUSTER16'] = '1'
     net = WaveNetModel(train_mode=False, **kw, **extra)
     net.load_state_dict(synth.make_weights(**kw))
+    os.environ.pop('WN_NO_CLUSTER16', None)
     return net
 
 
@@ -71,10 +74,13 @@ def main():
         kw16 = synth.cfg2(16)
         inp = make_inputs(kw16, T)
         a16 = build(kw16)
+        c8 = build(kw16, no16=True)
+        print('info:', a16.info()['cluster_path'], c8.info()['cluster_path'])
         lc = a16.create_upsample(inp['mel'])
-        for rows in (1, 6, 8, 12, 16):
-            ms = min(timed(a16, T, inp, lc, rows) for _ in range(2))
-            print('v2 rows=%2d: %.2f us/step  %.1f k samples/s' % (rows, 1e3 * ms / T, rows * T / ms))
+        for rows in (1, 8, 12, 16):
+            for name, net in (('v2 16+8 clusters', a16), ('v2 8-clusters   ', c8)):
+                ms = min(timed(net, T, inp, lc, rows) for _ in range(2))
+                print('%s rows=%2d: %.2f us/step  %.1f k samples/s' % (name, rows, 1e3 * ms / T, rows * T / ms))
         return
     T = 3000
     kw16 = synth.cfg2(16)

@@ -177,6 +177,10 @@ struct wn_handle {
     // round-2 cluster path (wn_kernel_v2.cuh): layer chain in 8-CTA clusters + tail/sampler kernel on the SMs left over
     bool v2_planned = false, v2 = false;
     const void *kernel_v2_layers = nullptr, *kernel_v2_layers_prof = nullptr, *kernel_v2_tail = nullptr;
+    const void *kernel_v2_layers16 = nullptr, *kernel_v2_layers16_prof = nullptr;
+    int v2_n16 = 0;                        // > 0: layers [0, 4*n16) run in n16 clusters of 16, the rest in clusters of 8 (second launch)
+    cudaStream_t v2_sc = nullptr;
+    cudaEvent_t v2_join_c = nullptr;
     bool v2_fast_act = false;
     int v2_grid_layers = 0, v2_smem_layers = 0, v2_smem_tail = 0;
     cudaStream_t v2_sa = nullptr, v2_sb = nullptr;
@@ -325,6 +329,8 @@ void wn_destroy(wn_handle *h)
     for (DevBuf *b : bufs) b->release();
     if (h->v2_sa) cudaStreamDestroy(h->v2_sa);
     if (h->v2_sb) cudaStreamDestroy(h->v2_sb);
+    if (h->v2_sc) cudaStreamDestroy(h->v2_sc);
+    if (h->v2_join_c) cudaEventDestroy(h->v2_join_c);
     if (h->v2_fork) cudaEventDestroy(h->v2_fork);
     if (h->v2_join_a) cudaEventDestroy(h->v2_join_a);
     if (h->v2_join_b) cudaEventDestroy(h->v2_join_b);
@@ -715,36 +721,86 @@ int wn_finalize(wn_handle *h)
     h->info.cluster_path = 0;
     h->info.fast_act = 0;
     if (h->v2_planned) {
-        h->kernel_v2_layers = h->v2_fast_act ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false>;
-        h->kernel_v2_layers_prof = h->v2_fast_act ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true>;
+        const bool fa = h->v2_fast_act;
+        h->kernel_v2_layers = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false, 8> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false, 8>;
+        h->kernel_v2_layers_prof = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true, 8> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true, 8>;
+        h->kernel_v2_layers16 = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false, 16> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false, 16>;
+        h->kernel_v2_layers16_prof = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true, 16> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true, 16>;
         h->kernel_v2_tail = (const void *)wn_tail_kernel_v2<ShapeCfg2>;
-        cudaError_t e = cudaFuncSetAttribute(h->kernel_v2_layers, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_layers_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
+        cudaError_t e = cudaSuccess;
+        const void *ks[4] = {h->kernel_v2_layers, h->kernel_v2_layers_prof, h->kernel_v2_layers16, h->kernel_v2_layers16_prof};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+            e = cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
+            if (e == cudaSuccess && i >= 2) e = cudaFuncSetAttribute(ks[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_tail);
-        int n_clusters = 0;
-        if (e == cudaSuccess) {
+        auto max_clusters = [&](const void *k, int cs, int *n) -> cudaError_t {
             cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(h->v2_grid_layers);
+            lc.gridDim = dim3(cs * 32);
             lc.blockDim = dim3(V2_NT);
             lc.dynamicSmemBytes = (size_t)h->v2_smem_layers;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = V2_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             lc.attrs = at; lc.numAttrs = 1;
-            e = cudaOccupancyMaxActiveClusters(&n_clusters, h->kernel_v2_layers, &lc);
-        }
+            return cudaOccupancyMaxActiveClusters(n, k, &lc);
+        };
+        int n8 = 0, n16 = 0;
+        if (e == cudaSuccess) e = max_clusters(h->kernel_v2_layers, 8, &n8);
+        if (e == cudaSuccess && max_clusters(h->kernel_v2_layers16, 16, &n16) != cudaSuccess) { n16 = 0; cudaGetLastError(); }
         if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
-        else if (n_clusters * V2_CS < h->v2_grid_layers) h->v2_note = "cluster path disabled: only " + std::to_string(n_clusters) + " clusters of 8 are co-resident";
+        else if (n8 * V2_CS < h->v2_grid_layers) h->v2_note = "cluster path disabled: only " + std::to_string(n8) + " clusters of 8 are co-resident";
         else {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = least priority (numerically greatest)
             if (!h->v2_sa) e = cudaStreamCreateWithPriority(&h->v2_sa, cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess && !h->v2_sc) e = cudaStreamCreateWithPriority(&h->v2_sc, cudaStreamNonBlocking, hi);
             if (e == cudaSuccess && !h->v2_sb) e = cudaStreamCreateWithPriority(&h->v2_sb, cudaStreamNonBlocking, lo);
             if (e == cudaSuccess && !h->v2_fork) e = cudaEventCreateWithFlags(&h->v2_fork, cudaEventDisableTiming);
             if (e == cudaSuccess && !h->v2_join_a) e = cudaEventCreateWithFlags(&h->v2_join_a, cudaEventDisableTiming);
             if (e == cudaSuccess && !h->v2_join_b) e = cudaEventCreateWithFlags(&h->v2_join_b, cudaEventDisableTiming);
+            if (e == cudaSuccess && !h->v2_join_c) e = cudaEventCreateWithFlags(&h->v2_join_c, cudaEventDisableTiming);
             if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
-            else { h->v2 = true; h->info.cluster_path = 1; h->info.fast_act = h->v2_fast_act ? 1 : 0; h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt) + " tail CTAs"; }
+            else {
+                h->v2 = true; h->info.cluster_path = 1; h->info.fast_act = fa ? 1 : 0;
+                h->v2_n16 = 0;
+                h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt) + " tail CTAs";
+                // 16-CTA clusters (4 layers each) halve the L2 hops of the chain; at most n16 of them are co-resident, the
+                // remaining layers run in 8-CTA clusters of a second launch.  Whether the three kernels really share the GPU
+                // depends on the part's GPC layout, so the shape is tried once on a two-step dummy job.
+                const int want16 = L / 4, rem = L - 4 * (L / 4);
+                if (!getenv("WN_NO_CLUSTER16") && want16 >= 1 && n16 >= want16 && want16 * 16 + ((rem + 1) / 2) * 8 + Mt <= h->sm_count) {
+                    h->v2_n16 = want16;
+                    h->finalized = true;
+                    DevBuf dummy;
+                    const size_t nu = (size_t)2 * (O / 3 + 1);
+                    bool ok = dummy.ensure((nu + 8) * 4) == cudaSuccess && cudaMemset(dummy.p, 0, (nu + 8) * 4) == cudaSuccess;
+                    if (ok) {
+                        std::vector<float> hu(nu, 0.5f);
+                        ok = cudaMemcpy((float *)dummy.p + 8, hu.data(), nu * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+                    }
+                    if (ok) {
+                        wn_generate_args ga;
+                        memset(&ga, 0, sizeof ga);
+                        int32_t gid = 0;
+                        ga.rows = 1; ga.T = 2; ga.n_forced = 1; ga.forced_dev = (const float *)dummy.p;
+                        ga.gc_ids = c.gc_channels ? &gid : nullptr;
+                        ga.uniforms_dev = (const float *)dummy.p + 8; ga.temperature = 1.0f;
+                        ga.out_samples_dev = (float *)dummy.p + 4;
+                        ok = wn_generate(h, &ga, nullptr) == WN_OK && wn_sync_check(h, nullptr) == WN_OK;
+                    }
+                    dummy.release();
+                    h->finalized = false;
+                    if (ok) {
+                        h->info.cluster_path = 2;
+                        h->v2_note = "cluster path: " + std::to_string(want16) + " clusters of 16 + " + std::to_string((rem + 1) / 2) + " of 8 + " + std::to_string(Mt) + " tail CTAs";
+                    } else {
+                        h->v2_n16 = 0;
+                        cudaGetLastError();
+                        h->err.clear();
+                    }
+                }
+            }
         }
     }
     (void)St; (void)Sm;
@@ -878,7 +934,29 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
         CUDA_TRY(h, cudaEventRecord(h->v2_fork, st));
         CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sa, h->v2_fork, 0));
         CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sb, h->v2_fork, 0));
-        CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
+        p.claim_slot = 4;
+        if (h->v2_n16 > 0) {
+            // layers [0, 4*n16) in clusters of 16, then the rest in clusters of 8 on a second stream, then the tail
+            const int split = 4 * h->v2_n16;
+            p.layer_base = 0; p.layer_end = split;
+            CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers16_prof : h->kernel_v2_layers16, dim3(16 * h->v2_n16), dim3(V2_NT), args,
+                                         (size_t)h->v2_smem_layers, h->v2_sa));
+            if (split < p.L) {
+                WnParams p2 = p;
+                p2.layer_base = split; p2.layer_end = p.L; p2.claim_slot = 6;
+                void *args2[] = {&p2};
+                CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sc, h->v2_fork, 0));
+                CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(((p.L - split + 1) / 2) * V2_CS), dim3(V2_NT),
+                                             args2, (size_t)h->v2_smem_layers, h->v2_sc));
+                CUDA_TRY(h, cudaEventRecord(h->v2_join_c, h->v2_sc));
+                CUDA_TRY(h, cudaStreamWaitEvent(st, h->v2_join_c, 0));
+                h->launches++;
+            }
+        } else {
+            p.layer_base = 0; p.layer_end = p.L;
+            CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args,
+                                         (size_t)h->v2_smem_layers, h->v2_sa));
+        }
         CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_tail, dim3(p.Mt), dim3(WN_NT), args, (size_t)h->v2_smem_tail, h->v2_sb));
         CUDA_TRY(h, cudaEventRecord(h->v2_join_a, h->v2_sa));
         CUDA_TRY(h, cudaEventRecord(h->v2_join_b, h->v2_sb));

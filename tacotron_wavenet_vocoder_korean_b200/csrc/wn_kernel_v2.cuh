@@ -25,7 +25,7 @@
 constexpr int V2_NT = 384;       // threads per layer CTA: 8 helper warps + 4 chain warps (<= 168 registers per thread)
 constexpr int V2_HALF = 256;     // helper threads (warps 0-7); the chain group is warps 8-11
 constexpr int V2_CHAIN = 128;
-constexpr int V2_CS = 8;         // CTAs per cluster: 2 layers x M = 4
+constexpr int V2_CS = 8;         // CTAs per cluster: 2 layers x M = 4 (the portable shape; 16 = 4 layers where 7 of them fit)
 
 __device__ __forceinline__ unsigned v2_cluster_ctarank()
 {
@@ -364,8 +364,8 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
     return x;
 }
 
-template <class SH, bool FAST, bool PROF>
-__device__ void layer_role_v2(const WnParams &p, const int l, const int m)
+template <class SH, bool FAST, bool PROF, int CS>
+__device__ void layer_role_v2(const WnParams &p, const int l, const int m, const int l_local)
 {
     using Cur = typename SH::Cur;        // packed for 256 slots: col = slot / 4, chunk = slot % 4, 8 float4
     using Lc = typename SH::Lc;
@@ -390,9 +390,11 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
              *prdy = bars + 4 * WN_MAX_BATCH, *melbar = bars + 5 * WN_MAX_BATCH, *ldbar = bars + 6 * WN_MAX_BATCH;
     float *rows = smem + LY::OFF_ROWS;
 
-    const unsigned lbase = (unsigned)(l & 1) * 4u;            // cluster rank of this layer's CTA 0
-    const bool in_dsmem = (l & 1) == 1;                       // odd layers are fed by their cluster mate
-    const bool out_dsmem = (l & 1) == 0 && l + 1 < L;
+    constexpr int LPC = CS / 4;                               // consecutive layers per cluster
+    const unsigned lbase = (unsigned)l_local * 4u;            // cluster rank of this layer's CTA 0
+    const unsigned nbase = lbase + 4u;                        // ... and of the next layer's, when it is a cluster mate
+    const bool in_dsmem = l_local > 0;                        // fed by a cluster mate through distributed shared memory
+    const bool out_dsmem = l_local + 1 < LPC && l + 1 < L && l + 1 < p.layer_end;
     const bool has_next_layer = l + 1 < L;
 
     // ---- barriers, resident image (TMA bulk copies), scratch --------------------------------------------------
@@ -505,8 +507,8 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
         // acc hand-over to layer l+1, CTA m: DSMEM inside the cluster, LL mailbox otherwise (and to the tail)
         const u64 *mba_in = p.mb_acc + ((size_t)(l > 0 ? l - 1 : 0) * M + m) * Sm + col2;
         const u64 *mba_out = p.mb_acc + ((size_t)l * M + m) * Sm + col2;
-        const uint32_t r_acc = v2_mapa(smem_u32(rows + LY::R_ACC + col2), 4u + (unsigned)m);
-        const uint32_t r_abar = v2_mapa(smem_u32(&abar[0]), 4u + (unsigned)m);
+        const uint32_t r_acc = v2_mapa(smem_u32(rows + LY::R_ACC + col2), (out_dsmem ? nbase : lbase) + (unsigned)m);
+        const uint32_t r_abar = v2_mapa(smem_u32(&abar[0]), (out_dsmem ? nbase : lbase) + (unsigned)m);
         const float4 *xc_skip = reinterpret_cast<const float4 *>(rows + LY::R_Z + c2 * Skip::XS);
 
         for (int t = 0; t < p.T; ++t) {
@@ -706,8 +708,8 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m)
         uint32_t r_x[4], r_xb[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            r_x[k] = v2_mapa(smem_u32(rows + LY::R_INX + m * R + ct), 4u + (unsigned)k);
-            r_xb[k] = v2_mapa(smem_u32(&xbar[0]), 4u + (unsigned)k);
+            r_x[k] = v2_mapa(smem_u32(rows + LY::R_INX + m * R + ct), (out_dsmem ? nbase : lbase) + (unsigned)k);
+            r_xb[k] = v2_mapa(smem_u32(&xbar[0]), (out_dsmem ? nbase : lbase) + (unsigned)k);
         }
         const u64 *mbx_in = p.mb_x + ((size_t)l * M) * R + ct;
         const u64 *mbx_out = p.mb_x + ((size_t)(l + 1) * M + m) * R + ct;
@@ -968,30 +970,34 @@ __device__ void tail_role_v2(const WnParams &p, int mt)
     pf.flush();
 }
 
-// Kernel A: the layer chain.  grid = 8 * ceil(L / 2), cluster of 8 = layers 2c and 2c+1.  With a die map, clusters on
-// die 0 claim layer pairs from the front of the chain and clusters on die 1 from the back (every cluster sits on one
-// die), so the chain crosses the die boundary once on its way down instead of wherever the hardware put the clusters.
-template <class SH, bool FAST, bool PROF>
-__global__ void __cluster_dims__(V2_CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers_kernel_v2(const __grid_constant__ WnParams p)
+// Kernel A: a run of consecutive layers [p.layer_base, p.layer_end) in clusters of CS CTAs = CS / 4 layers each.  With a
+// die map, clusters on die 0 claim their layer group from the front of the run and clusters on die 1 from the back, so the
+// chain crosses the die boundary once on its way down instead of wherever the hardware put the clusters.
+// Launch shapes (wn_api.cu): 15 clusters of 8 for the whole stack, or 7 clusters of 16 (layers 0..27) plus one cluster of 8
+// (layers 28, 29) as two concurrent launches -- 16-CTA clusters halve the number of L2 hops but only 7 are co-resident.
+template <class SH, bool FAST, bool PROF, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers_kernel_v2(const __grid_constant__ WnParams p)
 {
     __shared__ int s_crole;
+    constexpr int LPC = CS / 4;
     const unsigned crank = v2_cluster_ctarank();
     if (crank == 0 && threadIdx.x == 0) {
         int role = (int)v2_cluster_id();
         if (p.sm_die != nullptr) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            const int n_clusters = (int)(gridDim.x / V2_CS);
-            role = (p.sm_die[smid] == 0) ? atomicAdd(p.status + 4, 1) : n_clusters - 1 - atomicAdd(p.status + 5, 1);
+            const int n_clusters = (int)(gridDim.x / CS);
+            role = (p.sm_die[smid] == 0) ? atomicAdd(p.status + p.claim_slot, 1) : n_clusters - 1 - atomicAdd(p.status + p.claim_slot + 1, 1);
         }
         s_crole = role;
     }
     v2_cluster_sync();
     int crole;
     asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(crole) : "r"(v2_mapa(smem_u32(&s_crole), 0u)) : "memory");
-    const int l = crole * 2 + (int)(crank >> 2), m = (int)(crank & 3u);
-    if (l < p.L) {
-        layer_role_v2<SH, FAST, PROF>(p, l, m);
+    const int l_local = (int)(crank >> 2), m = (int)(crank & 3u);
+    const int l = p.layer_base + crole * LPC + l_local;
+    if (l < p.layer_end) {
+        layer_role_v2<SH, FAST, PROF, CS>(p, l, m, l_local);
     } else {
         v2_cluster_sync();
         __syncthreads();

@@ -79,6 +79,8 @@ struct WnParams {
     const unsigned char *sm_die;   // [n_sm] die (0/1) of each SM id, or null
     int32_t mb_dual;               // 1: the two tables differ (post twice)
     int32_t pad2_;
+    int32_t layer_base, layer_end; // cluster path: this launch runs layers [layer_base, layer_end)
+    int32_t claim_slot;            // status[] index of this launch's die-aware cluster claim counters
     float *ring;                   // private dilation-queue rings
     const long long *ring_off;     // [L] float offset of layer l's ring block; block = [M][N][d][R]
     const float *forced;

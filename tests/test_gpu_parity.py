@@ -138,7 +138,7 @@ def test_cluster_path_equals_single_kernel_path():
     kw = synth.cfg2(8)
     a, _ = build(kw)
     b, _ = build(kw, cluster=False)
-    assert a.info()['cluster_path'] == 1 and b.info()['cluster_path'] == 0 and a.plan() == b.plan()
+    assert a.info()['cluster_path'] >= 1 and b.info()['cluster_path'] == 0 and a.plan() == b.plan()
     T = 700
     inp = make_inputs(kw, T)
     lc = a.create_upsample(inp['mel'])
