@@ -384,9 +384,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline line only (skip the cfg-1/3/4/5, batch-1 and 64-utterance job cells)")
-    ap.add_argument("--fast-activation", action="store_true",
-                    help="ex2/rcp.approx gate (WN_FLAG_FAST_ACT: MoL logits within 3e-6 of the pinned arithmetic, ~2 %% faster) instead of "
-                         "the default pinned exp32 + IEEE-divide gate, which is bit-identical to the CPU oracle")
+    ap.add_argument("--exact-activation", action="store_true",
+                    help="pinned exp32 + IEEE-divide gate (bit-identical to the CPU oracle) for the headline instead of the default "
+                         "ex2/rcp.approx gate (WN_FLAG_FAST_ACT: MoL logits within 3e-6 of the pinned arithmetic, tolerance 1e-4); "
+                         "the other one is always reported as an extra key")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -407,7 +408,7 @@ def main():
     # one process per GPU; at N = 1 a single-rank group, so that the job path below is the same code
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     W = max(args.warmup, 3)
-    fast = args.fast_activation
+    fast = not args.exact_activation
 
     kw, w, mel, uniforms, x0, gc = make_job(rank)
     net = WaveNetModel(train_mode=False, device=dev, fast_act=fast, **kw)

@@ -5,7 +5,7 @@
 // (the lc queue of model.py:125 holds two rows, layers read the older one, model.py:79-80) and one ring per dilation
 // queue (model.py:145) -- advanced by exactly one position per call, so a call costs O(1) in the number of steps taken.
 // One CTA per row walks the layers with the weights read from the L2-resident TF-layout copy; every dot product goes
-// through mv_plan_cta, the CTA-parallel twin of oracle/wn_oracle.c's mv_plan with the SAME evaluation plan the persistent
+// through mv_plan_cta, the CTA-parallel twin of the CPU restatement's mv_plan (pinned arithmetic) with the SAME evaluation plan the persistent
 // kernels implement, so a loop of wn_step calls reproduces wn_generate bit for bit.
 // Included by wn_kernel.cu inside its anonymous namespace.
 #pragma once

@@ -465,7 +465,14 @@ def checkpoint_state(logdir):
             for line in f:
                 if line.startswith('model_checkpoint_path:'):
                     p = line.split(':', 1)[1].strip().strip('"')
-                    return p if os.path.isabs(p) else os.path.join(logdir, p)
+                    cand = p if os.path.isabs(p) else os.path.join(logdir, p)
+                    if os.path.exists(cand + '.index'):
+                        return cand
+                    # a checkpoint directory copied from another machine records an absolute path that no longer exists
+                    local = os.path.join(logdir, os.path.basename(p))
+                    if os.path.exists(local + '.index'):
+                        return local
+                    break
     return get_most_recent_checkpoint(logdir)
 
 

@@ -94,8 +94,8 @@ class WavenetCropFeeder(object):
                 continue
             data = np.load(path)
             mel = data['mel']
-            if len(mel) >= self.max_frames and (not self.skip_path_filter or int(data['time_steps']) > self.sample_size
-                                                or 'time_steps' not in data.files):
+            if len(mel) >= self.max_frames and (not self.skip_path_filter or 'time_steps' not in data.files
+                                                or int(data['time_steps']) > self.sample_size):
                 break
         wav = np.asarray(data['audio'], np.float32).reshape(-1)
         assert len(wav) % len(mel) == 0 and len(wav) // len(mel) == self.hop_size, "audio / mel not hop-aligned (datafeeder_wavenet.py:38)"
@@ -138,8 +138,9 @@ def checkpoint_tensors(trainer):
         out['optimizer/' + name + '/Adam'] = m[name]
         out['optimizer/' + name + '/Adam_1'] = v[name]
     t = trainer.global_step
-    out['optimizer/beta1_power'] = np.array(0.9 ** (t + 1), np.float32)
-    out['optimizer/beta2_power'] = np.array(0.999 ** (t + 1), np.float32)
+    ta = getattr(trainer, 'adam_t', t)          # Adam's own step count: survives a global_step reset (--restore_from + new logdir)
+    out['optimizer/beta1_power'] = np.array(0.9 ** (ta + 1), np.float32)
+    out['optimizer/beta2_power'] = np.array(0.999 ** (ta + 1), np.float32)
     out['global_step'] = np.array(t, np.int32)
     return out
 
@@ -152,8 +153,19 @@ def save(trainer, logdir, step, hparams_dict=None):
     print('Storing checkpoint to {} ...'.format(logdir), end="")
     sys.stdout.flush()
     tf_bundle.write_bundle(prefix, checkpoint_tensors(trainer))
+    # tf.train.Saver(max_to_keep=hparams.max_checkpoints) (train_vocoder.py:126): keep the newest few, list them all
+    keep_n = int((hparams_dict or {}).get('max_checkpoints', 3) or 3)
+    steps = sorted({int(f[len('model.ckpt-'):-len('.index')]) for f in os.listdir(logdir)
+                    if f.startswith('model.ckpt-') and f.endswith('.index') and f[len('model.ckpt-'):-len('.index')].isdigit()})
+    for old in steps[:-keep_n]:
+        for f in os.listdir(logdir):
+            if f.startswith('model.ckpt-%d.' % old):
+                os.remove(os.path.join(logdir, f))
+    kept = steps[-keep_n:]
     with open(os.path.join(logdir, 'checkpoint'), 'w') as f:
-        f.write('model_checkpoint_path: "model.ckpt-%d"\nall_model_checkpoint_paths: "model.ckpt-%d"\n' % (step, step))
+        f.write('model_checkpoint_path: "model.ckpt-%d"\n' % step)
+        for k in kept:
+            f.write('all_model_checkpoint_paths: "model.ckpt-%d"\n' % k)
     if hparams_dict is not None:
         with open(os.path.join(logdir, 'params.json'), 'w', encoding='utf-8') as f:
             json.dump(hparams_dict, f, indent=4, sort_keys=True, ensure_ascii=False)
@@ -178,6 +190,12 @@ def restore(trainer, logdir):
     step = tf_bundle.global_step_of(prefix)
     print("  Global step was: {}".format(step))
     trainer.global_step = step
+    # Adam's step count from the saved beta powers (the reference's Saver restores them independently of global_step)
+    trainer.adam_t = step
+    if r.has_tensor('optimizer/beta1_power'):
+        b1p = float(np.asarray(r.get_tensor('optimizer/beta1_power')).reshape(-1)[0])
+        if 0.0 < b1p < 1.0:
+            trainer.adam_t = max(int(round(np.log(b1p) / np.log(0.9))) - 1, 0)
     return step
 
 

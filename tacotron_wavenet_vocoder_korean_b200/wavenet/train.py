@@ -156,10 +156,15 @@ class WaveNetTrainer(object):
 
     def apply(self, learning_rate, t=None, grad_scale=1.0, clip_norm=0.0, beta1=0.9, beta2=0.999, epsilon=1e-8, ema_decay=0.9999):
         """optimizer.apply_gradients + ema.apply (wavenet/model.py:333-346); increments global_step."""
-        a = _train_lib.WntAdam(learning_rate, beta1, beta2, epsilon, ema_decay, grad_scale, clip_norm, int(t if t is not None else self.global_step + 1))
+        # the bias-correction step is Adam's own counter (beta1_power / beta2_power in the TF checkpoint), which the reference's
+        # Saver restores independently of a global_step reset (train_vocoder.py --restore_from with a new logdir)
+        if getattr(self, 'adam_t', None) is None:
+            self.adam_t = self.global_step
+        a = _train_lib.WntAdam(learning_rate, beta1, beta2, epsilon, ema_decay, grad_scale, clip_norm, int(t if t is not None else self.adam_t + 1))
         with torch.cuda.device(self.device):
             self._check(_train_lib.lib().wnt_apply(self._h, C.byref(a), self._stream()))
         self.global_step += 1
+        self.adam_t += 1
 
     def train_step(self, input_batch, local_condition, global_condition_batch, hparams, l2_regularization_strength=None):
         """One `sess.run([global_step, loss, optimize])` (train_vocoder.py:169).  Under torch.distributed the gradients
