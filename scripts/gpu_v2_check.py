@@ -100,7 +100,7 @@ def main():
             ms = min(timed(net, T, inp, lc, rows) for _ in range(2))
             print('%s rows=%2d: %.2f us/step  %.1f k samples/s' % (name, rows, 1e3 * ms / T, rows * T / ms))
     # phase counters of the v2 path, 1 and 8 rows
-    for rows in (1, 8):
+    for rows in (1, 8, 16):
         lib.wn_debug_profile(a16._h, 1, None, 0)
         a16.generate(T, inp['x0'][:rows], inp['uniforms'][:rows], lc_up=lc[:rows], gc_ids=inp['gc_ids'][:rows])
         grid = a16.info()['grid']
@@ -111,7 +111,7 @@ def main():
         L = 30
         lay = p[:L * 4].reshape(L, 4, 16)
         names = {0: 'wait', 1: 'combine', 2: 'bar1', 3: 'lds+fma+reduce', 4: 'act+zsend', 5: 'bar2', 6: 'dense+send',
-                 7: 'h:wait_full', 8: 'h:ring+zwait', 9: 'h:skip+acc', 10: 'h:pre'}
+                 11: 'h:early', 7: 'h:wait_full', 8: 'h:ring+zwait', 9: 'h:skip+acc', 10: 'h:pre'}
         print('rows=%d layer phases (cycles per row-step)' % rows)
         for sel, tag in ((slice(2, L, 2), 'even layers (LL in, DSMEM out)'), (slice(1, L, 2), 'odd layers (DSMEM in, LL out)')):
             print('   %s:' % tag, {n: int(lay[sel, :, i].mean()) for i, n in names.items()})
@@ -119,6 +119,12 @@ def main():
         print('   layer 29:', {n: int(lay[29, :, i].mean()) for i, n in names.items()})
         tl = p[L * 4:L * 4 + 16]
         print('   tail:', {n: int(tl[:, i].mean()) for i, n in enumerate(['wait_acc', 'post1', 'post2'])})
+        print('   per-layer chain wait :', [int(v) for v in lay[:, :, 0].mean(axis=1)])
+        print('   per-layer chain busy :', [int(v) for v in lay[:, :, 1:7].sum(axis=2).mean(axis=1)])
+        print('   per-layer helper wait:', [int(v) for v in lay[:, :, 7].mean(axis=1)])
+        print('   per-layer helper busy:', [int(v) for v in lay[:, :, 8:11].sum(axis=2).mean(axis=1)])
+        print('   per-layer helper early:', [int(v) for v in lay[:, :, 11].mean(axis=1)])
+        print('   tail wait / busy per CTA:', [int(v) for v in tl[:, 0]], [int(v) for v in tl[:, 1:3].sum(axis=1)])
         if rows >= 1:
             # timeline from the global-timer stamps (ns -> cycles at 1.965 GHz): wake = input complete, send = outputs posted
             ghz = 1.965

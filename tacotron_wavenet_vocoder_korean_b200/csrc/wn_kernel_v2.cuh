@@ -252,6 +252,13 @@ __device__ __forceinline__ void v2_ll_wait_n(const MBox &mb, const u64 *logical,
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = __uint_as_float((unsigned)v[i]);
 }
+// volatile loads: issued where they are written (prefetches for the NEXT item must leave before this item's waits)
+__device__ __forceinline__ float v2_ld_cg_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 // one mel frame (C floats) global -> shared by a TMA bulk copy, completion on `bar` (one thread)
 __device__ __forceinline__ void v2_mel_load(float *dst, const float *src, uint32_t bytes, uint64_t *bar)
 {
@@ -511,6 +518,29 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
         const uint32_t r_abar = v2_mapa(smem_u32(&abar[0]), (out_dsmem ? nbase : lbase) + (unsigned)m);
         const float4 *xc_skip = reinterpret_cast<const float4 *>(rows + LY::R_Z + c2 * Skip::XS);
 
+        // Global loads of an item (dilated tap from the ring, materialised lc row, layer 0: the draw's uniforms / forced input).
+        // They are issued one item AHEAD (while the current item waits and computes): in a train of rows the helper is the
+        // busiest group of a CTA, and 600-1000 cycles of exposed L2 / DRAM latency per item would be added to its service time.
+        struct GLoad { float oldv, lcraw, su; };
+        auto gload = [&](int t, int b) -> GLoad {
+            GLoad g{0.0f, 0.0f, 0.0f};
+            const bool has_next = (t + 1 < p.T_row[b]);
+            if (has_next && d >= 2 && t + 1 >= d && ht < R)
+                g.oldv = v2_ld_cg_f32(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);       // x_l(t+1-d); the queue starts at zero (model.py:64)
+            if (SH::HAS_LC && !fold_lc && has_next && ht < SH::C && p.lc_up != nullptr) {
+                const long idx = (long)t - p.lc_shift;
+                if (idx >= 0 && idx < p.t_lc) g.lcraw = ld_nc_f32(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
+            }
+            if (l == 0 && has_next && ht <= SH::O / 3 + 1) {
+                constexpr int nr = SH::O / 3;
+                if (ht <= nr) g.su = ld_nc_f32((const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1) + ht);
+                else if (t + 1 < p.n_forced) g.su = ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1);
+            }
+            return g;
+        };
+        GLoad pref{0.0f, 0.0f, 0.0f};
+        int pref_t = -1, pref_b = -1;
+
         for (int t = 0; t < p.T; ++t) {
             // abort is agreed on by the whole group, at a step boundary (every 16th, to keep it off the per-row path)
             if ((t & 15) == 0 && v2_group_sync_or(2, ab.dead)) break;
@@ -523,9 +553,20 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 const bool has_next = (t + 1 < p.T_row[b]);
                 MDst da{nullptr, nullptr};
                 if (!out_dsmem) da = mb_dst(mb, mba_out + b * rowa);
-                // early loads for the next step's pre-activations (independent of this step's x unless d == 1)
-                float oldv = 0.0f, lcv = 0.0f;
-                if (has_next && d >= 2 && t + 1 >= d && ht < R) oldv = __ldcg(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);   // x_l(t+1-d); the queue starts at zero (model.py:64)
+                const GLoad cur = (pref_t == t && pref_b == b) ? pref : gload(t, b);
+                {
+                    // the item after this one; its loads leave now unless it is the same row (its ring slot may be this item's push)
+                    int tn = t, bn = b;
+                    bool hn = false;
+                    for (int k = 0; k <= N; ++k) {
+                        if (++bn >= N) { bn = 0; ++tn; }
+                        if (tn >= p.T) break;
+                        if (tn < p.T_row[bn]) { hn = true; break; }
+                    }
+                    pref_t = -1;
+                    if (hn && bn != b) { pref = gload(tn, bn); pref_t = tn; pref_b = bn; }
+                }
+                float oldv = cur.oldv, lcv = cur.lcraw;
                 bool mel_last = false;
                 int mel_next = 0;
                 if (SH::HAS_LC && has_next && ht < SH::C) {
@@ -555,20 +596,18 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                             }
                             lcv = v[0];
                         }
-                    } else if (p.lc_up != nullptr && idx >= 0 && idx < p.t_lc) {
-                        lcv = __ldg(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
                     }
                 }
                 // layer 0: noise of the draw of step t and the forced input of step t+1 (consumed by the chain's item (b, t+1))
                 float sprep = 0.0f;
                 if (l == 0 && has_next && ht <= SH::O / 3 + 1) {
                     constexpr int nr = SH::O / 3;
-                    const float *u = (const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1);
-                    if (ht < nr) sprep = wn::log32(-wn::log32(ld_nc_f32(u + ht)));
-                    else if (ht == nr) { const float u2 = ld_nc_f32(u + nr); sprep = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2))); }
-                    else sprep = (t + 1 < p.n_forced) ? ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1) : 0.0f;
+                    if (ht < nr) sprep = wn::log32(-wn::log32(cur.su));
+                    else if (ht == nr) sprep = fsub(wn::log32(cur.su), wn::log32(fsub(1.0f, cur.su)));
+                    else sprep = cur.su;
                 }
                 pin(oldv); pin(lcv); pin(sprep);
+                hp.mark(6);
                 v2_mbar_wait(&fullb[b], par, ab);                       // x and the own z slice of (b, t) are in rows[b]
                 if (l == 0 && has_next && ht <= SH::O / 3 + 1) rb[LY::R_SAMP + ht] = sprep;
                 hp.mark(7);
@@ -670,6 +709,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
         }
         if (PROF && p.prof && ht == 0)
             for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[PROF ? i : 0];
+            p.prof[(size_t)cta * 16 + 11] = hp.acc[PROF ? 6 : 0];
     } else {
         // =========================== CHAIN group (warps 8-11) ===================================================
         // "Fat" threads, one warp per SM sub-partition: thread = (filter/gate column c, K half) holds 64 weights of the
@@ -732,6 +772,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 MDst dx{nullptr, nullptr};
                 if (has_next_layer && !out_dsmem) dx = mb_dst(mb, mbx_out + b * rowx);
                 v2_mbar_wait(&prdy[b], par, ab);                       // pre[b] of this step written, rows[b] free
+                if (L0) pf.mark(0);                                    // layer 0: 'wait' = the helper's pre-activations, 'combine' = sampler + causal
                 const float pre_v = rb[LY::R_PRE + c];
                 // 1. layer input r = ct
                 {
@@ -755,7 +796,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                         }
                         v2_chain_sync();
                         const float x_in = rb[LY::R_XIN];
-                        pf.mark(0);
+                        pf.mark(1);
                         pf.stamp(10);
                         v = fadd(h0, fadd(h1, fadd(h2, ffma(w31r, x_in, h3))));
                     } else if (in_dsmem) {
