@@ -763,6 +763,27 @@ int wn_finalize(wn_handle *h)
             if (e != cudaSuccess) { h->v2_note = std::string("cluster path disabled: ") + cudaGetErrorString(e); cudaGetLastError(); }
             else {
                 h->v2 = true; h->info.cluster_path = 1; h->info.fast_act = fa ? 1 : 0;
+                // The dilation rings (scratch that never has to reach DRAM) are pinned in L2 for the generation streams: a slot is
+                // rewritten every d steps, and without the hint the write-back of its dirty lines is most of the launch's DRAM writes.
+                if (h->ring_bytes && !getenv("WN_NO_L2_PERSIST")) {
+                    int maxwin = 0, l2size = 0;
+                    cudaDeviceGetAttribute(&maxwin, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+                    cudaDeviceGetAttribute(&l2size, cudaDevAttrL2CacheSize, dev);
+                    size_t want = std::min<size_t>(h->ring_bytes, (size_t)std::max(maxwin, 0));
+                    size_t lim = std::min<size_t>(want, (size_t)l2size / 4 * 3);
+                    if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) {
+                        cudaStreamAttrValue av;
+                        memset(&av, 0, sizeof av);
+                        av.accessPolicyWindow.base_ptr = h->ring.p;
+                        av.accessPolicyWindow.num_bytes = want;
+                        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)lim / (double)want);
+                        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+                        cudaStreamSetAttribute(h->v2_sa, cudaStreamAttributeAccessPolicyWindow, &av);
+                        cudaStreamSetAttribute(h->v2_sc, cudaStreamAttributeAccessPolicyWindow, &av);
+                    }
+                    cudaGetLastError();
+                }
                 h->v2_n16 = 0;
                 h->v2_note = "cluster path: " + std::to_string(h->v2_grid_layers / V2_CS) + " clusters of 8 + " + std::to_string(Mt) + " tail CTAs";
                 // 16-CTA clusters (4 layers each) halve the L2 hops of the chain; at most n16 of them are co-resident, the
