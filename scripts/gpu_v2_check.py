@@ -123,6 +123,7 @@ def main():
         print('   per-layer chain busy :', [int(v) for v in lay[:, :, 1:7].sum(axis=2).mean(axis=1)])
         print('   per-layer helper wait:', [int(v) for v in lay[:, :, 7].mean(axis=1)])
         print('   per-layer helper busy:', [int(v) for v in lay[:, :, 8:11].sum(axis=2).mean(axis=1)])
+        print('   layer 0 sampler: pre %d, grain lookups %d, first word %d (rest of the poll + draw + barrier is in combine)' % (lay[0, :, 11].mean(), lay[0, :, 12].mean(), lay[0, :, 13].mean()))
         print('   per-layer helper early:', [int(v) for v in lay[:, :, 11].mean(axis=1)])
         print('   tail wait / busy per CTA:', [int(v) for v in tl[:, 0]], [int(v) for v in tl[:, 1:3].sum(axis=1)])
         if rows >= 1:

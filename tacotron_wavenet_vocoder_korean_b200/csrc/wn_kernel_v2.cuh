@@ -125,10 +125,12 @@ template <bool ON>
 struct ProfT;
 template <>
 struct ProfT<true> : Prof {
+    static constexpr bool on = true;
     __device__ __forceinline__ ProfT(long long *s) : Prof(s) {}
 };
 template <>
 struct ProfT<false> {
+    static constexpr bool on = false;
     long long acc[1];
     __device__ __forceinline__ ProfT(long long *) {}
     __device__ __forceinline__ void start() {}
@@ -154,7 +156,8 @@ struct V2L {
     static constexpr int OFF_LCS = OFF_XSOLD + Cur::TPC * Cur::XS;            // helper: lc row, padded for Lc
     static constexpr int OFF_GVEC = OFF_LCS + Lc::TPC * Lc::XS;               // prologue: speaker embedding
     static constexpr int OFF_WC = (OFF_GVEC + Gc::TPC * Gc::XS + 3) & ~3;     // layer 0: causal kernel [ifw][R]
-    static constexpr int OFF_BAR = OFF_WC + SH::IFW * SH::R;                  // mbarriers (8 B each): 5 x 32 rows + image
+    static constexpr int OFF_PART = OFF_WC + SH::IFW * SH::R;                 // layer 0: [Mt][32] conv2 partials of the row being drawn
+    static constexpr int OFF_BAR = OFF_PART + SH::Mt * 32;                    // mbarriers (8 B each): 5 x 32 rows + image
     static constexpr int OFF_ROWS = OFF_BAR + 2 * (6 * WN_MAX_BATCH + 2);
     // per row
     static constexpr int ZF = Skip::TPC * Skip::XS;                           // full gated vector, padded for Skip
@@ -303,17 +306,44 @@ __device__ __forceinline__ float act_fg_fast(float x, bool is_gate)
     return is_gate ? r : ffma(-2.0f, r, 1.0f);
 }
 
+// Mixture-of-logistics draw from a warp's logits (lane o < O holds logit o): wavenet/mixture.py:84-114.  Returns the
+// sample in every lane; `writer` stores it.
+template <class SH>
+__device__ __forceinline__ float v2_draw_warp(const WnParams &p, int b, int step, int lane, bool writer, float c2, float gum, float logistic)
+{
+    constexpr int nr = SH::O / 3;
+    float g = (lane < nr) ? fsub(c2, gum) : __int_as_float(0xff800000);
+    int k = lane;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float og = __shfl_xor_sync(FULL, g, off);
+        const int ok = __shfl_xor_sync(FULL, k, off);
+        if (og > g || (og == g && ok < k)) { g = og; k = ok; }
+    }
+    const float mean = __shfl_sync(FULL, c2, nr + k);
+    float ls = __shfl_sync(FULL, c2, 2 * nr + k);
+    const float lsmin = -32.23619130191664f;
+    if (!(ls > lsmin)) ls = lsmin;
+    float x = fadd(mean, fmul(wn::exp32(ls), logistic));
+    x = fmaxf(x, -1.0f);
+    x = fminf(x, 1.0f);
+    if (writer && lane == 0) p.out_samples[(size_t)b * p.T + step] = x;
+    return x;
+}
+
 // One warp of a layer-0 CTA: waits for the Mt partial conv2 outputs of (b, step) from the tail CTAs, adds them left to
 // right onto the bias, writes the logits, draws from the mixture of logistics (wavenet/mixture.py:84-114) and returns
 // the sample in every lane.  Lane o < O owns output o; gum / logistic are precomputed from the step's uniforms.
-template <class SH>
+__device__ __forceinline__ void pin_ptr(const u64 *&p) { asm volatile("" : "+l"(p)); }
+template <class SH, class PF>
 __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &mb, int b, int step, int lane, bool writer, V2Ab &ab,
-                                                float b2v, float gum, float logistic)
+                                                float b2v, float gum, float logistic, PF &pf)
 {
     constexpr int O = SH::O, Mt = SH::Mt, nr = SH::O / 3;
     static_assert(O <= 32 && Mt == 16, "sample warp: one lane per output, 16 tail partials");
     const unsigned seq = (unsigned)step + 1u;
     float c2 = b2v;
+    unsigned spins = 0;
     if (lane < O) {
         // 16 words per lane, all in flight; consumed in order (the partial sums are added left to right).  A missing word
         // re-issues the loads of every word not yet consumed, so late tail CTAs cost one poll round, not one each.
@@ -333,9 +363,9 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
             return base + (w & 255);
         };
         u64 wv[Mt];
+        if (PF::on) { pin_ptr(gb0); pin_ptr(gb1); pin_ptr(gb2); pf.mark(7); }
 #pragma unroll
         for (int i = 0; i < Mt; ++i) wv[i] = ld_relaxed_u64(word(i));
-        unsigned spins = 0;
         long long t0 = 0;
 #pragma unroll
         for (int i = 0; i < Mt; ++i) {
@@ -348,27 +378,12 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
                 }
             }
             c2 = fadd(c2, __uint_as_float((unsigned)wv[i]));
+            if (PF::on && i == 0) pf.mark(9);
         }
         if (writer && p.out_logits) p.out_logits[((size_t)b * p.T + step) * O + lane] = c2;
     }
     __syncwarp();
-    float g = (lane < nr) ? fsub(c2, gum) : __int_as_float(0xff800000);
-    int k = lane;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float og = __shfl_xor_sync(FULL, g, off);
-        const int ok = __shfl_xor_sync(FULL, k, off);
-        if (og > g || (og == g && ok < k)) { g = og; k = ok; }
-    }
-    const float mean = __shfl_sync(FULL, c2, nr + k);
-    float ls = __shfl_sync(FULL, c2, 2 * nr + k);
-    const float lsmin = -32.23619130191664f;
-    if (!(ls > lsmin)) ls = lsmin;
-    float x = fadd(mean, fmul(wn::exp32(ls), logistic));
-    x = fmaxf(x, -1.0f);
-    x = fminf(x, 1.0f);
-    if (writer && lane == 0) p.out_samples[(size_t)b * p.T + step] = x;
-    return x;
+    return v2_draw_warp<SH>(p, b, step, lane, writer, c2, gum, logistic);
 }
 
 template <class SH, bool FAST, bool PROF, int CS>
@@ -709,7 +724,6 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
         }
         if (PROF && p.prof && ht == 0)
             for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[PROF ? i : 0];
-            p.prof[(size_t)cta * 16 + 11] = hp.acc[PROF ? 6 : 0];
     } else {
         // =========================== CHAIN group (warps 8-11) ===================================================
         // "Fat" threads, one warp per SM sub-partition: thread = (filter/gate column c, K half) holds 64 weights of the
@@ -755,7 +769,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
         const u64 *mbx_out = p.mb_x + ((size_t)(l + 1) * M + m) * R + ct;
         constexpr int nr_mix = SH::O / 3;
         const float w31r = smem[LY::OFF_WC + (SH::IFW - 1) * R + ct];                  // layer 0: newest causal tap
-        const float b2v = (L0 && ct < SH::O) ? __ldg(p.samp_img + p.off_b2 + ct) : 0.0f;
+        const float b2v = (L0 && (ct & 31) < SH::O) ? __ldg(p.samp_img + p.off_b2 + (ct & 31)) : 0.0f;
         ProfT<PROF> pf((p.prof && ct == 0) ? p.prof + (size_t)cta * 16 : nullptr);
         unsigned item = 0;                                           // parity selects the zs buffer
 
@@ -782,20 +796,38 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                         // the new network input closes the causal conv whose 31 older taps the helper has already summed
                         const float *hp4 = rb + LY::R_HPRE + ct;
                         const float h0 = hp4[0], h1 = hp4[R], h2 = hp4[2 * R], h3 = hp4[3 * R];
-                        if (ct < 32) {
-                            // Gumbel / logistic noise and the forced input were prepared by the helper one step ahead
-                            const float gum = (ct < nr_mix) ? rb[LY::R_SAMP + ct] : 0.0f;
-                            const float logistic = rb[LY::R_SAMP + nr_mix];
-                            float x_in = rb[LY::R_SAMP + nr_mix + 1];
-                            if (t > 0) {
-                                const float smp = v2_sample_warp<SH>(p, mb, b, t - 1, ct, m == 0, ab, b2v, gum, logistic);
-                                if (t >= p.n_forced) x_in = smp;
-                                pf.stamp(9);
-                            }
-                            if (ct == 0) rb[LY::R_XIN] = x_in;
+                        // Gumbel / logistic noise and the forced input were prepared by the helper one step ahead.
+                        // Every warp of the group polls a quarter of the tail's 16 conv2 partials (4 words in flight per
+                        // lane: one L2 round trip instead of four for 16 words from one warp), parks them in shared memory,
+                        // and after the barrier every warp sums them in the pinned order and draws the sample redundantly:
+                        // the new input reaches all 128 threads without a second barrier.
+                        const int sl = ct & 31, cw = ct >> 5;
+                        const float gum = (sl < nr_mix) ? rb[LY::R_SAMP + sl] : 0.0f;
+                        const float logistic = rb[LY::R_SAMP + nr_mix];
+                        float x_in = rb[LY::R_SAMP + nr_mix + 1];
+                        float *part = smem + LY::OFF_PART;
+                        pf.mark(8);
+                        if (t > 0 && sl < SH::O) {
+                            constexpr int PW = SH::Mt / 4;
+                            float q[4];
+                            v2_ll_wait_n(mb, p.mb_c2 + ((size_t)b * SH::Mt + cw * PW) * SH::O + sl, (size_t)SH::O, PW, (unsigned)t, ab, q);
+#pragma unroll
+                            for (int i = 0; i < PW; ++i) part[(cw * PW + i) * 32 + sl] = q[i];
                         }
+                        pf.mark(7);
                         v2_chain_sync();
-                        const float x_in = rb[LY::R_XIN];
+                        pf.mark(9);
+                        if (t > 0) {
+                            float c2 = b2v;
+                            if (sl < SH::O) {
+#pragma unroll
+                                for (int i = 0; i < SH::Mt; ++i) c2 = fadd(c2, part[i * 32 + sl]);
+                                if (m == 0 && cw == 0 && p.out_logits) p.out_logits[((size_t)b * p.T + (t - 1)) * SH::O + sl] = c2;
+                            }
+                            const float smp = v2_draw_warp<SH>(p, b, t - 1, sl, m == 0 && cw == 0, c2, gum, logistic);
+                            if (t >= p.n_forced) x_in = smp;
+                        }
+                        if (ct == 0) rb[LY::R_XIN] = x_in;               // the helper pushes it into the causal queue
                         pf.mark(1);
                         pf.stamp(10);
                         v = fadd(h0, fadd(h1, fadd(h2, ffma(w31r, x_in, h3))));
@@ -897,7 +929,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 if (ct < nr_mix) gum = wn::log32(-wn::log32(ld_nc_f32(u + ct)));
                 const float u2 = ld_nc_f32(u + nr_mix);
                 const float logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2)));
-                v2_sample_warp<SH>(p, mb, b, step, ct, true, ab, b2v, gum, logistic);
+                v2_sample_warp<SH>(p, mb, b, step, ct, true, ab, b2v, gum, logistic, pf);
             }
         }
         if (PROF && p.prof && ct == 0) {
@@ -905,6 +937,8 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
             p.prof[(size_t)cta * 16 + 14] = pf.acc[PROF ? 10 : 0];
             p.prof[(size_t)cta * 16 + 15] = pf.acc[PROF ? 11 : 0];
             p.prof[(size_t)cta * 16 + 13] = pf.acc[PROF ? 9 : 0];
+            p.prof[(size_t)cta * 16 + 11] = pf.acc[PROF ? 8 : 0];
+            p.prof[(size_t)cta * 16 + 12] = pf.acc[PROF ? 7 : 0];       // layer 0: polling the tail partials
         }
         };
         if (l == 0) chain_group(std::true_type{});
