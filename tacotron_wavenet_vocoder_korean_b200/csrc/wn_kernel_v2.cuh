@@ -22,7 +22,12 @@
 #pragma once
 #include <type_traits>
 
-constexpr int V2_NT = 384;       // threads per layer CTA: 8 helper warps + 4 chain warps (<= 168 registers per thread)
+// Register split between the groups (setmaxnreg, one warpgroup-aligned instruction per group): 256 x HELPER + 128 x CHAIN
+// <= 65536.  The chain group's filter/gate phase wants its 16 LDS.128 of the layer input in flight over 96 weight registers;
+// at 168 ptxas splits them into two dependent batches.  Measured (profiles/r02_setmaxnreg_sweep.md): 136/232 starves the
+// helper (8 rows 24.6 us), 160/184 is best at every row count.
+constexpr int V2_REGS_HELPER = 160, V2_REGS_CHAIN = 184;
+constexpr int V2_NT = 384;       // threads per layer CTA: 8 helper warps + 4 chain warps (168 registers per thread at launch)
 constexpr int V2_HALF = 256;     // helper threads (warps 0-7); the chain group is warps 8-11
 constexpr int V2_CHAIN = 128;
 constexpr int V2_CS = 8;         // CTAs per cluster: 2 layers x M = 4 (the portable shape; 16 = 4 layers where 7 of them fit)
@@ -481,6 +486,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
 
     if (tid < V2_HALF) {
         // =========================== HELPER group (warps 0-7) ===================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_HELPER));
         const int ht = tid;
         const int c4 = ht & 3, c2 = ht & 1;
         const int grp4 = ht >> 2, col2 = ht >> 1;
@@ -726,6 +732,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
             for (int i = 7; i < 11; ++i) p.prof[(size_t)cta * 16 + i] = hp.acc[PROF ? i : 0];
     } else {
         // =========================== CHAIN group (warps 8-11) ===================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_REGS_CHAIN));
         // "Fat" threads, one warp per SM sub-partition: thread = (filter/gate column c, K half) holds 64 weights of the
         // current tap and evaluates canonical chunks khalf*16 .. khalf*16+15 (in-thread tree, ONE shuffle level);
         // for the dense 1x1 thread = output r over the CTA's whole 32-channel slice (8 canonical chunks, no shuffle).
