@@ -557,9 +557,9 @@ def main():
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_step": b_step, "steps_per_launch": T_STEPS,
                 "traffic_source": "ncu --replay-mode range over one 8 x 48000 launch (profiles/r02_traffic.json): the concurrent kernels cannot be "
                                   "profiled by kernel replay, which serialises launches",
-                "note": "weights (21.4 MB) are resident in registers / shared memory across the grid, so DRAM traffic (86 MB per launch) is far "
+                "note": "weights (21.4 MB) are resident in registers / shared memory across the grid, so DRAM traffic (53 MB per launch, rings pinned in L2) is far "
                         "below the algorithmic bytes (1.04 TB per launch); the binding limit is the dependent chain per sample: 30 layers x "
-                        "(~1050 cycles of compute + a 280-cycle DSMEM or 650-cycle L2 hop) + tail (DESIGN.md latency model, profiles/r02_*)",
+                        "(~950 cycles of compute + a 280-cycle DSMEM or 650-cycle L2 hop) + tail (DESIGN.md latency model, profiles/r02_*)",
                 "hbm_roofline_samples_per_sec": ROWS * peak * 1e9 / b_step}
 
     cpu = None
