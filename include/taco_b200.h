@@ -61,6 +61,7 @@ typedef struct taco_info {
     int64_t n_params;
     int64_t kernel_launches;                          /* kernels launched by this handle so far */
     int64_t workspace_bytes;
+    int64_t tc_gemm_launches;                         /* of kernel_launches: tcgen05 (3xTF32) conv / dense GEMMs of the CBHG stacks */
 } taco_info;
 
 typedef struct taco_handle taco_handle;

@@ -109,6 +109,43 @@ def main():
                          "h2d_bytes": int(ids_c.nbytes), "d2h_bytes": int(mel_h.nbytes + lin_h.nbytes + al_h.nbytes)},
         "gpu_launches_per_batch": int(launches), "dtype": "f32", "data": "synthetic weights, own Korean sentences", "info": m.info(),
     }
+    # per-op CUDA-event timings of one call (TACO_TIME_OPS=1 makes taco_synthesize bracket every op of its launch list)
+    os.environ['TACO_TIME_OPS'] = '1'
+    run(S, True)
+    torch.cuda.synchronize()
+    del os.environ['TACO_TIME_OPS']
+    try:
+        ops = m.debug_tensor('op_times', (-1, 6))
+    except Exception:
+        ops = None
+    if ops is not None and len(ops):
+        ops = [[float(x) for x in o] for o in ops]
+        kinds = {0: 'other', 1: 'fp32 SIMT GEMM', 2: 'tcgen05 3xTF32 GEMM (+ operand split)', 3: 'bidirectional GRU', 4: 'decoder loop'}
+        by_kind = {}
+        for ms, kind, fl, M, Nn, K in ops:
+            by_kind.setdefault(kinds[int(kind)], [0.0, 0.0, 0])
+            by_kind[kinds[int(kind)]][0] += float(ms); by_kind[kinds[int(kind)]][1] += float(fl); by_kind[kinds[int(kind)]][2] += 1
+        out["ops_ms"] = {k: {"ms": v[0], "launch_groups": v[2], "useful_gflop": v[1] / 1e9} for k, v in by_kind.items()}
+        tc = [o for o in ops if int(o[1]) == 2]
+        if tc:
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))
+            except Exception:
+                pass
+            bf16 = float(peaks.get('bf16_tflops', 0) or 0)
+            peak_tf32, src = (bf16 / 2, "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate)") if bf16 else \
+                (1125.0, "fallback: nominal dense 2250 TFLOP/s bf16 / 2 (B200_PROFILING.md)")
+            big = max(tc, key=lambda o: o[2])
+            tot_ms, tot_fl = sum(o[0] for o in tc), sum(o[2] for o in tc)
+            out["roofline"] = {
+                "bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf32, "peak_source": src,
+                "kernel": "tc::gemm_tc_kernel (largest launch: M=%d N=%d sum K=%d, operand split included in its time)" % (int(big[3]), int(big[4]), int(big[5])),
+                "achieved": 3 * big[2] / (big[0] * 1e-3) / 1e12, "frac": 3 * big[2] / (big[0] * 1e-3) / 1e12 / peak_tf32,
+                "useful_fp32_tflops": big[2] / (big[0] * 1e-3) / 1e12, "kernel_ms": float(big[0]),
+                "all_tc_launches": {"ms": float(tot_ms), "useful_gflop": float(tot_fl / 1e9), "executed_tf32_tflops": float(3 * tot_fl / (tot_ms * 1e-3) / 1e12)},
+                "note": "achieved counts the three TF32 products per fp32 multiply-add that the split executes; the path as a whole is bound by the decoder loop "
+                        "(13 grid barriers per step), see ops_ms"}
     if not a.no_cpu:
         from oracle.taco_oracle import TacotronOracle
         n_cpu, s_cpu = min(N, 8), min(S, 40)

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtaco_b200.so")
+LIB_PATH = os.environ.get("TACO_B200_LIB") or os.path.join(_HERE, "libtaco_b200.so")     # TACO_B200_LIB: A/B runs of two builds on one box
 
 TACO_MAX_PRENET = 4
 TACO_MAX_PROJ = 4
@@ -33,7 +33,8 @@ class TacoConfig(C.Structure):
 class TacoInfo(C.Structure):
     _fields_ = [("sm_count", C.c_int32), ("dec_grid", C.c_int32), ("dec_threads", C.c_int32),
                 ("dec_smem_bytes", C.c_int32), ("dec_phases_per_step", C.c_int32), ("rnn_weights_in_smem", C.c_int32),
-                ("n_params", C.c_int64), ("kernel_launches", C.c_int64), ("workspace_bytes", C.c_int64)]
+                ("n_params", C.c_int64), ("kernel_launches", C.c_int64), ("workspace_bytes", C.c_int64),
+                ("tc_gemm_launches", C.c_int64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -12,6 +12,7 @@
 
 #include "../../include/taco_b200.h"
 #include "taco_kernels.cuh"
+#include "taco_gemm_tc.cuh"
 
 using namespace taco;
 
@@ -82,6 +83,17 @@ struct taco_handle {
     int32_t *ids_lens_dev = nullptr;          // lengths + speaker ids
     size_t ids_lens_cap = 0;
     std::map<std::string, DevBuf> taps;
+
+    // tensor-core conv / dense path (taco_gemm_tc.cuh): split, transposed weights per launch group, keyed by the first W pointer
+    struct TcWeights { float *hi = nullptr, *lo = nullptr; int rows = 0, Kp = 0, Cip = 0; };
+    std::map<const void *, TcWeights> tc_w;
+    void *tc_encode = nullptr;                // cuTensorMapEncodeTiled
+    unsigned *tc_err = nullptr;
+    float *op_times_dev = nullptr;            // TACO_TIME_OPS=1: per-op event timings of the last call
+    size_t op_times_cap = 0;
+    long long *tc_dbg = nullptr;              // TACO_TC_DEBUG=1: in-kernel timeline of CTA 0 of every tensor-core launch
+    bool tc_on = false;
+    int64_t tc_launches = 0;
 };
 
 namespace {
@@ -446,6 +458,10 @@ void taco_destroy(taco_handle *h) {
     if (h->prof_dev) cudaFree(h->prof_dev);
     if (h->barrier_dev) cudaFree(h->barrier_dev);
     if (h->ids_lens_dev) cudaFree(h->ids_lens_dev);
+    if (h->tc_err) cudaFree(h->tc_err);
+    if (h->tc_dbg) cudaFree(h->tc_dbg);
+    if (h->op_times_dev) cudaFree(h->op_times_dev);
+    for (auto &kv : h->tc_w) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
     delete h;
 }
 
@@ -530,6 +546,19 @@ int taco_finalize(taco_handle *h) {
         if (per_sm < 1) return fail(h, TACO_ERR_CUDA, "the persistent decoder kernel does not fit one SM");
     }
     CK(cudaMalloc(&h->dp_dev, sizeof(DecParams)));
+    // tensor-core path of the CBHG convolutions: needs the driver's tensor-map encoder; TACO_NO_TC=1 keeps the fp32 SIMT GEMM (A/B runs)
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess)
+            return fail(h, TACO_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        h->tc_encode = fn;
+        CK(cudaMalloc(&h->tc_err, sizeof(unsigned)));
+        CK(cudaMemset(h->tc_err, 0, sizeof(unsigned)));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Layout<128>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(tc::gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Layout<256>::SMEM_BYTES));
+        h->tc_on = getenv("TACO_NO_TC") == nullptr;
+    }
     h->w.clear();
     h->finalized = true;
     return TACO_OK;
@@ -547,6 +576,7 @@ int taco_get_info(const taco_handle *h, taco_info *info) {
     info->n_params = h->n_params;
     info->kernel_launches = h->launches;
     info->workspace_bytes = (int64_t)h->ws_cap;
+    info->tc_gemm_launches = h->tc_launches;
     return TACO_OK;
 }
 
@@ -591,6 +621,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         float *e_bank, *e_proj[2], *e_hw[3], *e_xp, *memory, *keys;
         float *db[DB_COUNT], *score, *state[2], *q_row;
         float *p_bank, *p_proj[2], *p_hw[3], *p_xp, *p_out;
+        float *tc_hi, *tc_lo;
     } w;
     int enc_pre_max = c.embedding_size;
     for (int i = 0; i < c.n_enc_prenet; ++i) enc_pre_max = std::max(enc_pre_max, c.enc_prenet_sizes[i]);
@@ -604,8 +635,25 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     db_width[DB_CTX] = mem; db_width[DB_HATT] = H; db_width[DB_RH] = std::max(H, R); db_width[DB_U] = std::max(H, R); db_width[DB_Q] = A;
     for (int i = 0; i <= c.dec_layer_num; ++i) db_width[DB_O0 + i] = R;
     for (int i = 0; i < c.dec_layer_num; ++i) db_width[DB_H1 + i] = R;
+    auto rup = [](int x, int a) { return (x + a - 1) / a * a; };
+    // largest split operand of the tensor-core path: rows x channels rounded up to 32 (bank input, pooled bank, projection inputs)
+    size_t tc_elems = 0;
+    if (h->tc_on) {
+        auto upd = [&](size_t rows, int ci) { tc_elems = std::max(tc_elems, rows * (size_t)rup(ci, 32)); };
+        upd(MT, h->enc.n_in); upd(MT, h->enc.K * h->enc.C);
+        for (auto &L : h->enc.proj) upd(MT, L.co);
+        upd(MT, h->enc.U);
+        if (a->linear_dev) {
+            upd(MP, h->post.n_in); upd(MP, h->post.K * h->post.C);
+            for (auto &L : h->post.proj) upd(MP, L.co);
+            upd(MP, h->post.U);
+            upd(MP, 2 * c.post_rnn_size);
+        }
+    }
     auto plan = [&]() {
         off = 0;
+        w.tc_hi = tc_elems ? alloc(tc_elems) : nullptr;
+        w.tc_lo = tc_elems ? alloc(tc_elems) : nullptr;
         w.emb = alloc(MT * enc_pre_max);
         w.pre[0] = alloc(MT * enc_pre_max);
         w.pre[1] = alloc(MT * enc_pre_max, "enc_prenet");
@@ -664,9 +712,13 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     std::vector<GemmProb> probs;
     struct GemmLaunch { int first, count, B, T, maxN; };
     std::vector<std::function<int()>> ops;
+    struct OpMeta { float kind, flops, M, N, K; };      // kind: 0 other, 1 fp32 SIMT GEMM, 2 tensor-core GEMM (split + MMA), 3 recurrent, 4 decoder
+    std::vector<OpMeta> metas;
     auto gemm_group = [&](std::vector<GemmProb> group, int B, int T) {
         GemmLaunch L{(int)probs.size(), (int)group.size(), B, T, 0};
-        for (auto &g : group) { L.maxN = std::max(L.maxN, g.N); probs.push_back(g); }
+        double fl = 0, ksum = 0;
+        for (auto &g : group) { L.maxN = std::max(L.maxN, g.N); probs.push_back(g); fl += 2.0 * B * T * (double)g.N * g.ktaps * g.Ci; ksum += (double)g.ktaps * g.Ci; }
+        metas.push_back(OpMeta{1.f, (float)fl, (float)((double)B * T), (float)L.maxN, (float)ksum});
         ops.push_back([h, L, st]() -> int {
             dim3 grid((L.maxN + GBN - 1) / GBN, (unsigned)(((size_t)L.B * L.T + GBM - 1) / GBM), L.count);
             taco_gemm_kernel<<<grid, GTHREADS, 0, st>>>(h->probs_dev + L.first, L.B, L.T);
@@ -682,13 +734,103 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         g.N = L.co; g.act = act; g.epi = EPI_LINEAR;
         return g;
     };
+    // One launch group on the tensor cores: all problems read the same input (Ain, lda, channels Ci) and are at most 256 wide.
+    // Plan time: split + transpose the weights once per handle, encode the four tensor maps; run time: split the input, one GEMM.
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                      const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    std::string tc_fail;
+    int tc_ord = 0;
+    if (getenv("TACO_TC_DEBUG") && !h->tc_dbg) {
+        CK(cudaMalloc(&h->tc_dbg, 32 * 16 * sizeof(long long)));
+        CK(cudaMemset(h->tc_dbg, 0, 32 * 16 * sizeof(long long)));
+    }
+    if (h->tc_dbg) h->taps["tc_dbg"] = DevBuf{reinterpret_cast<float *>(h->tc_dbg), 32 * 16 * 2};
+    auto tc_group = [&](const std::vector<GemmProb> &group, int B, int T) -> bool {
+        const int Ci = group[0].Ci, Cip = rup(Ci, 32), np_ = (int)group.size();
+        int maxN = 0, maxK = 0;
+        for (auto &g : group) { maxN = std::max(maxN, g.N); maxK = std::max(maxK, g.ktaps); }
+        const int NT = maxN <= 128 ? 128 : 256;
+        const int rows_per = rup(maxN, 16), rows_total = rows_per * np_ + NT, Kp = maxK * Cip;   // + NT: the last tile may overhang
+        auto &tw = h->tc_w[group[0].W];
+        if (!tw.hi) {
+            const size_t n = (size_t)rows_total * Kp;
+            if (cudaMalloc(&tw.hi, n * sizeof(float)) != cudaSuccess || cudaMalloc(&tw.lo, n * sizeof(float)) != cudaSuccess) { tc_fail = "cudaMalloc of split weights"; return false; }
+            cudaMemsetAsync(tw.hi, 0, n * sizeof(float), st);
+            cudaMemsetAsync(tw.lo, 0, n * sizeof(float), st);
+            for (int i = 0; i < np_; ++i) {
+                const long tot = (long)group[i].N * group[i].ktaps * Ci;
+                tc::split_weight_kernel<<<(unsigned)std::min<long>((tot + 255) / 256, 2048), 256, 0, st>>>(group[i].W, group[i].ktaps, Ci, Cip, group[i].N, i * rows_per, Kp,
+                                                                                                          tw.hi, tw.lo);
+            }
+            tw.rows = rows_total; tw.Kp = Kp; tw.Cip = Cip;
+            h->launches += np_;
+        }
+        EncodeTiledFn enc = (EncodeTiledFn)h->tc_encode;
+        CUtensorMap m_ahi, m_alo, m_bhi, m_blo;
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)Cip, (cuuint64_t)T, (cuuint64_t)B};
+            cuuint64_t strides[2] = {(cuuint64_t)Cip * 4, (cuuint64_t)T * Cip * 4};
+            cuuint32_t box[3] = {(cuuint32_t)tc::TK, (cuuint32_t)tc::TM, 1}, es[3] = {1, 1, 1};
+            CUresult r1 = enc(&m_ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, w.tc_hi, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r2 = enc(&m_alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, w.tc_lo, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t bd[2] = {(cuuint64_t)Kp, (cuuint64_t)rows_total}, bs[1] = {(cuuint64_t)Kp * 4};
+            cuuint32_t bb[2] = {(cuuint32_t)tc::TK, (cuuint32_t)NT}, be[2] = {1, 1};
+            CUresult r3 = enc(&m_bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, tw.hi, bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            CUresult r4 = enc(&m_blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, tw.lo, bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS || r4 != CUDA_SUCCESS) {
+                tc_fail = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r1) + "," + std::to_string((int)r2) + "," + std::to_string((int)r3) + "," + std::to_string((int)r4) + ")";
+                return false;
+            }
+        }
+        tc::Args ta;
+        memset(&ta, 0, sizeof(ta));
+        for (int i = 0; i < np_; ++i) {
+            const GemmProb &g = group[i];
+            tc::Prob &q = ta.p[i];
+            q.bias = g.bias; q.bn_scale = g.bn_scale; q.bn_shift = g.bn_shift; q.R = g.R; q.rowvec = g.rowvec; q.C = g.C;
+            q.ldc = g.ldc; q.ldr = g.ldr; q.ldrv = g.ldrv; q.ktaps = g.ktaps; q.pl = g.pl; q.N = g.N; q.act = g.act; q.epi = g.epi == EPI_HIGHWAY ? 1 : 0; q.b_row0 = i * rows_per;
+        }
+        ta.T = T; ta.B = B; ta.Cip = Cip; ta.err = h->tc_err; ta.dbg = nullptr;
+        if (h->tc_dbg) { ta.dbg = h->tc_dbg + 16 * std::min(tc_ord, 31); ++tc_ord; }
+        const GemmProb g0 = group[0];
+        float *hi = w.tc_hi, *lo = w.tc_lo;
+        {
+            double fl = 0, ksum = 0;
+            for (auto &g : group) { fl += 2.0 * B * T * (double)g.N * g.ktaps * g.Ci; ksum += (double)g.ktaps * g.Ci; }
+            metas.push_back(OpMeta{2.f, (float)fl, (float)((double)B * T), (float)maxN, (float)ksum});
+        }
+        ops.push_back([=]() -> int {
+            const long rows = (long)B * T, tot = rows * (Cip / 4);
+            tc::split_act_kernel<<<(unsigned)std::min<long>((tot + 255) / 256, 8192), 256, 0, st>>>(g0.A, g0.lda, Ci, Cip, T, rows, g0.pool, hi, lo);
+            dim3 grid((unsigned)(B * ((T + tc::TM - 1) / tc::TM)), (unsigned)((maxN + NT - 1) / NT), (unsigned)np_);
+            if (NT == 128) tc::gemm_tc_kernel<128><<<grid, tc::THREADS, tc::Layout<128>::SMEM_BYTES, st>>>(m_ahi, m_alo, m_bhi, m_blo, ta);
+            else tc::gemm_tc_kernel<256><<<grid, tc::THREADS, tc::Layout<256>::SMEM_BYTES, st>>>(m_ahi, m_alo, m_bhi, m_blo, ta);
+            h->launches += 2;
+            h->tc_launches += 1;
+            return cudaGetLastError() == cudaSuccess ? 0 : -1;
+        });
+        return true;
+    };
+    // tensor cores when the group qualifies (plain conv / dense epilogue, 16 <= N, at most 16 problems), the fp32 SIMT GEMM otherwise
+    auto conv_group = [&](std::vector<GemmProb> group, int B, int T) -> bool {
+        // small problems stay on the SIMT kernel (TACO_TC_MIN_ROWS overrides the threshold: the parity tests push tiny cases through the tensor cores)
+        const char *mr = getenv("TACO_TC_MIN_ROWS");
+        bool ok = h->tc_on && group.size() <= (size_t)tc::MAX_PROBS && (size_t)B * T >= (size_t)(mr ? atoi(mr) : 256);
+        for (auto &g : group) ok = ok && (g.epi == EPI_LINEAR || (g.epi == EPI_HIGHWAY && (g.N & 3) == 0 && (g.ldr & 1) == 0 && (g.ldc & 1) == 0)) && g.N >= 16 && g.Ci == group[0].Ci && g.A == group[0].A && g.lda == group[0].lda && g.pool == group[0].pool;
+        if (!ok) { gemm_group(group, B, T); return true; }
+        return tc_group(group, B, T);
+    };
     auto cbhg = [&](const CbhgDev &D, const float *x, int B, int T, const float *before_highway, int ld_bh, const float *rnn_init,
-                    const int32_t *lens, float *bank, float *proj[2], float *hw[3], float *xp, float *out, const char *tag) {
+                    const int32_t *lens, float *bank, float *proj[2], float *hw[3], float *xp, float *out, const char *tag) -> bool {
         const size_t MM = (size_t)B * T;
         std::vector<GemmProb> grp;
         const int ldb = D.K * D.C;
         for (int k = 0; k < D.K; ++k) grp.push_back(mk(D.bank[k], x, D.n_in, bank + (size_t)k * D.C, ldb, ACT_RELU));
-        gemm_group(grp, B, T);
+        if (!conv_group(grp, B, T)) return false;
         const float *cur = bank;
         int ld = ldb;
         for (size_t i = 0; i < D.proj.size(); ++i) {
@@ -698,13 +840,13 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
                 g.R = x; g.ldr = D.n_in;
                 g.rowvec = before_highway; g.ldrv = ld_bh;
             }
-            gemm_group({g}, B, T);
+            if (!conv_group({g}, B, T)) return false;
             cur = proj[i & 1];
             ld = D.proj[i].co;
         }
         float *hcur = hw[2];
         if (D.has_dense) {   // hw[2] is not reused by the highway ping-pong, so the debug tap stays valid
-            gemm_group({mk(D.dense, cur, ld, hw[2], D.U, ACT_NONE)}, B, T);
+            if (!conv_group({mk(D.dense, cur, ld, hw[2], D.U, ACT_NONE)}, B, T)) return false;
         } else {
             // widths match: copy through a 1-tap identity is wasteful; read the projection output directly
             hcur = const_cast<float *>(cur);
@@ -715,13 +857,13 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
             GemmProb g = mk(D.highway[i], hcur, D.U, dst, D.U, ACT_NONE);
             g.epi = EPI_HIGHWAY;
             g.R = hcur; g.ldr = D.U;
-            gemm_group({g}, B, T);
+            if (!conv_group({g}, B, T)) return false;
             hcur = dst;
         }
         h->taps[std::string(tag) + "_rnn_in"] = DevBuf{hcur, MM * D.U};
         ConvLayer xl;
         xl.W = D.rnn.Wx; xl.b = D.rnn.bx; xl.k = 1; xl.ci = D.U; xl.co = 6 * D.U;
-        gemm_group({mk(xl, hcur, D.U, xp, 6 * D.U, ACT_NONE)}, B, T);
+        if (!conv_group({mk(xl, hcur, D.U, xp, 6 * D.U, ACT_NONE)}, B, T)) return false;
         RnnParams rp;
         memset(&rp, 0, sizeof(rp));
         rp.XP = xp; rp.Wgh[0] = D.rnn.Wgh[0]; rp.Wgh[1] = D.rnn.Wgh[1]; rp.Wch[0] = D.rnn.Wch[0]; rp.Wch[1] = D.rnn.Wch[1];
@@ -730,15 +872,18 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         rp.w_in_smem = need <= h->smem_optin ? 1 : 0;
         const size_t sm = rp.w_in_smem ? need : (size_t)3 * D.U * sizeof(float);
         const int grid = std::min(2 * B, 2 * h->sm_count);
+        metas.push_back(OpMeta{3.f, 0.f, (float)((double)B * T), (float)D.U, 0.f});
         ops.push_back([h, rp, sm, grid, st]() -> int {
             if (rp.U == 128) taco_bigru_reg_kernel<128><<<grid, 256, 0, st>>>(rp);     // recurrent weights in registers
             else taco_bigru_kernel<<<grid, 256, sm, st>>>(rp);
             h->launches++;
             return cudaGetLastError() == cudaSuccess ? 0 : -1;
         });
+        return true;
     };
 
     // embedding + speaker states
+    metas.push_back(OpMeta{0.f, 0.f, 0.f, 0.f, 0.f});
     ops.push_back([=]() -> int {
         const size_t tot = MT * c.embedding_size;
         taco_embed_kernel<<<(unsigned)std::min<size_t>((tot + 255) / 256, 4096), 256, 0, st>>>(a->ids_dev, h->embedding, (int)MT, c.embedding_size,
@@ -769,7 +914,8 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         ld = h->enc_prenet[i].co;
     }
     h->taps["enc_prenet"] = DevBuf{const_cast<float *>(cur), MT * ld};
-    cbhg(h->enc, cur, N, T_in, before_highway, before_highway ? h->spk_dense[0].co : 0, enc_init, lens_dev, w.e_bank, w.e_proj, w.e_hw, w.e_xp, w.memory, "enc");
+    if (!cbhg(h->enc, cur, N, T_in, before_highway, before_highway ? h->spk_dense[0].co : 0, enc_init, lens_dev, w.e_bank, w.e_proj, w.e_hw, w.e_xp, w.memory, "enc"))
+        return fail(h, TACO_ERR_CUDA, "taco_synthesize: tensor-core plan failed: " + tc_fail);
     gemm_group({mk(h->memory_layer, w.memory, mem, w.keys, A, ACT_NONE)}, N, T_in);
 
     // decoder
@@ -795,6 +941,7 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     add_init(DB_HATT, att_init);
     for (int i = 0; i < c.dec_layer_num; ++i) add_init(DB_H1 + i, dec_init[i]);
     di.state0 = w.state[0]; di.N = N; di.tiles = tiles; di.T_in = T_in; di.dirac = c.attention_type != TACO_ATT_LOC_SEN;
+    metas.push_back(OpMeta{4.f, 0.f, (float)N, (float)S, 0.f});
     ops.push_back([h, dp, di, st, smem, G]() -> int {
         if (cudaMemcpyAsync(h->dp_dev, &dp, sizeof(dp), cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
         if (cudaMemsetAsync(h->barrier_dev, 0, 2 * sizeof(unsigned), st) != cudaSuccess) return -1;
@@ -809,8 +956,9 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
 
     // post-processing net
     if (a->linear_dev) {
-        cbhg(h->post, a->mel_dev, N, Tm, nullptr, 0, nullptr, nullptr, w.p_bank, w.p_proj, w.p_hw, w.p_xp, w.p_out, "post");
-        gemm_group({mk(h->final_dense, w.p_out, 2 * c.post_rnn_size, a->linear_dev, c.num_freq, ACT_NONE)}, N, Tm);
+        if (!cbhg(h->post, a->mel_dev, N, Tm, nullptr, 0, nullptr, nullptr, w.p_bank, w.p_proj, w.p_hw, w.p_xp, w.p_out, "post") ||
+            !conv_group({mk(h->final_dense, w.p_out, 2 * c.post_rnn_size, a->linear_dev, c.num_freq, ACT_NONE)}, N, Tm))
+            return fail(h, TACO_ERR_CUDA, "taco_synthesize: tensor-core plan failed: " + tc_fail);
     }
 
     // upload the problem table, then run
@@ -821,11 +969,38 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
         h->probs_cap = probs.size();
     }
     CK(cudaMemcpyAsync(h->probs_dev, probs.data(), probs.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, st));
-    for (auto &op : ops) {
-        if (op() != 0) {
+    // TACO_TIME_OPS=1: CUDA events around every op of the list; taco_debug_get("op_times") returns rows of
+    // (ms, kind, useful flops, M, N, sum of K) -- scripts/bench_taco.py builds its per-op table and roofline block from it
+    const bool time_ops = getenv("TACO_TIME_OPS") != nullptr && metas.size() == ops.size();
+    std::vector<cudaEvent_t> ev;
+    if (time_ops) {
+        ev.resize(ops.size() + 1);
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        CK(cudaEventRecord(ev[0], st));
+    }
+    for (size_t i = 0; i < ops.size(); ++i) {
+        if (ops[i]() != 0) {
             h->err = std::string("taco_synthesize: launch failed: ") + cudaGetErrorString(cudaGetLastError());
             return TACO_ERR_CUDA;
         }
+        if (time_ops) CK(cudaEventRecord(ev[i + 1], st));
+    }
+    if (time_ops) {
+        CK(cudaStreamSynchronize(st));
+        std::vector<float> rows(ops.size() * 6);
+        for (size_t i = 0; i < ops.size(); ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            rows[i * 6 + 0] = ms; rows[i * 6 + 1] = metas[i].kind; rows[i * 6 + 2] = metas[i].flops; rows[i * 6 + 3] = metas[i].M; rows[i * 6 + 4] = metas[i].N; rows[i * 6 + 5] = metas[i].K;
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+        if (h->op_times_cap < rows.size()) {
+            if (h->op_times_dev) cudaFree(h->op_times_dev);
+            CK(cudaMalloc(&h->op_times_dev, rows.size() * sizeof(float)));
+            h->op_times_cap = rows.size();
+        }
+        CK(cudaMemcpy(h->op_times_dev, rows.data(), rows.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->taps["op_times"] = DevBuf{h->op_times_dev, rows.size()};
     }
     return TACO_OK;
 }
@@ -880,6 +1055,11 @@ int taco_sync_check(taco_handle *h, void *stream) {
     unsigned flags[2] = {0, 0};
     CK(cudaMemcpy(flags, h->barrier_dev, sizeof(flags), cudaMemcpyDeviceToHost));
     if (flags[1]) return fail(h, TACO_ERR_TIMEOUT, "the persistent decoder kernel aborted on its barrier watchdog");
+    if (h->tc_err) {
+        unsigned e = 0;
+        CK(cudaMemcpy(&e, h->tc_err, sizeof(e), cudaMemcpyDeviceToHost));
+        if (e) return fail(h, TACO_ERR_TIMEOUT, "a tensor-core GEMM timed out on a pipeline barrier");
+    }
     return TACO_OK;
 }
 

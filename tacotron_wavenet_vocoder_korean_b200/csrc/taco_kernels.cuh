@@ -9,9 +9,9 @@
 //                       persistent cooperative kernel: weight-stationary column slices in shared memory,
 //                       feature-major activations, grid-wide barrier between dependent phases.
 //
-// Arithmetic is plain fp32 FMA with fixed summation orders and CUDA's accurate expf/tanhf/logf (no fast-math):
-// the 1e-4 tolerance of north_star on float mel outputs leaves no room for bf16/tf32 tensor-core inputs in
-// a 200-step recurrence, and the GEMM-shaped encoder/post work is small (about 0.13 TFLOP for 32 sentences).
+// Arithmetic is plain fp32 FMA with fixed summation orders and CUDA's accurate expf/tanhf/logf (no fast-math).  The large
+// conv / dense contractions of the two CBHG stacks run on the tensor cores instead (taco_gemm_tc.cuh: tcgen05 kind::tf32 with a
+// three-product split that keeps fp32 accuracy); taco_gemm_kernel below serves the small problems and TACO_NO_TC=1.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

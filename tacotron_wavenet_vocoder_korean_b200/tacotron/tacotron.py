@@ -142,6 +142,12 @@ class Tacotron(object):
 
     def debug_tensor(self, name, shape):
         """Test hook over taco_debug_get: an intermediate of the last initialize() as a numpy array."""
+        if any(d < 0 for d in shape):       # one free dimension: ask the library for the size first
+            total = _taco_lib.lib().taco_debug_get(self._h, name.encode(), None, 0)
+            if total < 0:
+                raise RuntimeError("no debug tensor %s" % name)
+            known = int(np.prod([d for d in shape if d >= 0]))
+            shape = tuple(d if d >= 0 else total // max(known, 1) for d in shape)
         out = np.empty(shape, np.float32)
         n = _taco_lib.lib().taco_debug_get(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size)
         if n != out.size:

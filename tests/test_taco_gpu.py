@@ -161,3 +161,41 @@ def test_end_to_end_text_to_wav_tiny():
     wavs2 = tts.synthesize(texts, spk, seed=3)
     # (uniforms are drawn on the device from torch's generator: only shapes/finite-ness are stable across calls)
     assert [len(w) for w in wavs2] == [len(w) for w in wavs]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_tensor_core_conv_path_matches_oracle(name, monkeypatch):
+    """The CBHG convolutions / projections / highway / GRU input GEMMs on tcgen05 with the 3xTF32 split (taco_gemm_tc.cuh):
+    the tiny cases are below the row threshold of that path, so force it (odd channel counts exercise the zero padding to
+    32-channel k-tiles, T < 128 the out-of-bounds rows of the TMA boxes), and compare with the oracle AND with the fp32 SIMT path."""
+    hp, ns, w, ids, lens, spk, steps = case(name)
+    mel, lin, al = TacotronOracle(hp, w, ns).synthesize(ids, lens, spk, max_iters=steps)
+    monkeypatch.setenv('TACO_TC_MIN_ROWS', '1')
+    m = run_cuda(hp, ns, w, ids, lens, spk, steps)
+    assert m.info()['tc_gemm_launches'] >= 8, m.info()
+    check(m, mel, lin, al)
+    monkeypatch.setenv('TACO_NO_TC', '1')
+    s = run_cuda(hp, ns, w, ids, lens, spk, steps)
+    assert s.info()['tc_gemm_launches'] == 0
+    for a_, b_ in ((m.mel_outputs, s.mel_outputs), (m.linear_outputs, s.linear_outputs), (m.alignments, s.alignments)):
+        assert float((a_ - b_).abs().max()) <= 2e-5
+
+
+def test_cfg3_tensor_core_path_is_the_default_and_matches_simt(monkeypatch):
+    """cfg-3 shape (32 sentences, r = 5): every CBHG GEMM group runs on the tensor cores by default; outputs within 5e-5 of the fp32 path."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+    from bench_taco import make_texts
+    from tacotron_wavenet_vocoder_korean_b200.text import text_to_sequence, prepare_inputs
+    hp = dict(synth.TACO_HP)
+    w = synth.make_taco_weights(hp, 2)
+    ids = prepare_inputs([text_to_sequence(t) for t in make_texts(32)])
+    lens = np.array([int(np.argmax(s == 1)) + 1 for s in ids], np.int32)
+    spk = (np.arange(32) % 2).astype(np.int32)
+    m = run_cuda(hp, 2, w, ids, lens, spk, 24)
+    assert m.info()['tc_gemm_launches'] >= 17, m.info()
+    monkeypatch.setenv('TACO_NO_TC', '1')
+    s = run_cuda(hp, 2, w, ids, lens, spk, 24)
+    assert s.info()['tc_gemm_launches'] == 0
+    errs = [float((a_ - b_).abs().max()) for a_, b_ in ((m.mel_outputs, s.mel_outputs), (m.linear_outputs, s.linear_outputs), (m.alignments, s.alignments))]
+    assert max(errs) <= 5e-5, errs       # observed 2.4e-5 on mel after 24 recurrent steps: two fp32-accurate summation orders, north_star allows 1e-4
