@@ -199,3 +199,16 @@ def test_cfg3_tensor_core_path_is_the_default_and_matches_simt(monkeypatch):
     assert s.info()['tc_gemm_launches'] == 0
     errs = [float((a_ - b_).abs().max()) for a_, b_ in ((m.mel_outputs, s.mel_outputs), (m.linear_outputs, s.linear_outputs), (m.alignments, s.alignments))]
     assert max(errs) <= 5e-5, errs       # observed 2.4e-5 on mel after 24 recurrent steps: two fp32-accurate summation orders, north_star allows 1e-4
+
+
+@pytest.mark.parametrize("att,steps,n,t_in", [('bah_mon_norm', 200, 4, 60), ('loc_sen', 120, 3, 50)])
+def test_full_size_model_matches_oracle_over_the_whole_decode(att, steps, n, t_in):
+    """cfg-3's 200 decoder steps (1000 mel frames) against the numpy oracle on the full-size model, and the post-CBHG /
+    linear outputs over all of them: the 30- / 20-step tests above stop before the attention has walked through the sentence."""
+    hp = dict(synth.TACO_HP, attention_type=att)
+    w = synth.make_taco_weights(hp, 2)
+    ids, lens, spk = make_batch(n, t_in, seed=11, min_len=t_in // 2)
+    mel, lin, al = TacotronOracle(hp, w, 2).synthesize(ids, lens, spk, max_iters=steps)
+    m = run_cuda(hp, 2, w, ids, lens, spk, steps)
+    e = check(m, mel, lin, al)
+    assert m.mel_outputs.shape[1] == steps * hp['reduction_factor'], e
