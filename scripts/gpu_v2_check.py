@@ -111,7 +111,7 @@ def main():
         L = 30
         lay = p[:L * 4].reshape(L, 4, 16)
         names = {0: 'wait', 1: 'combine', 2: 'bar1', 3: 'lds+fma+reduce', 4: 'act+zsend', 5: 'bar2', 6: 'dense+send',
-                 11: 'h:early', 7: 'h:wait_full', 8: 'h:ring+zwait', 9: 'h:skip+acc', 10: 'h:pre'}
+                 7: 'h:wait_full', 8: 'h:ring+zwait', 9: 'h:skip+acc', 10: 'h:pre'}
         print('rows=%d layer phases (cycles per row-step)' % rows)
         for sel, tag in ((slice(2, L, 2), 'even layers (LL in, DSMEM out)'), (slice(1, L, 2), 'odd layers (DSMEM in, LL out)')):
             print('   %s:' % tag, {n: int(lay[sel, :, i].mean()) for i, n in names.items()})
@@ -123,8 +123,8 @@ def main():
         print('   per-layer chain busy :', [int(v) for v in lay[:, :, 1:7].sum(axis=2).mean(axis=1)])
         print('   per-layer helper wait:', [int(v) for v in lay[:, :, 7].mean(axis=1)])
         print('   per-layer helper busy:', [int(v) for v in lay[:, :, 8:11].sum(axis=2).mean(axis=1)])
-        print('   layer 0 sampler: pre %d, grain lookups %d, first word %d (rest of the poll + draw + barrier is in combine)' % (lay[0, :, 11].mean(), lay[0, :, 12].mean(), lay[0, :, 13].mean()))
-        print('   per-layer helper early:', [int(v) for v in lay[:, :, 11].mean(axis=1)])
+        print('   layer 0 sampler (chain group, per row-step): noise / forced input from shared %d, poll of the tail partials (4 words per lane per warp) %d, '
+              'barrier %d; partial sum + draw + causal FMA are in combine' % (lay[0, :, 11].mean(), lay[0, :, 12].mean(), lay[0, :, 13].mean()))
         print('   tail wait / busy per CTA:', [int(v) for v in tl[:, 0]], [int(v) for v in tl[:, 1:3].sum(axis=1)])
         if rows >= 1:
             # timeline from the global-timer stamps (ns -> cycles at 1.965 GHz): wake = input complete, send = outputs posted
@@ -139,10 +139,6 @@ def main():
             print('   means: DSMEM hop %.0f, LL hop %.0f, layer wake->send %.0f' % (hop[0::2].mean(), hop[1::2].mean(), comp[:-1].mean()))
             t_w = tl[:, 10].mean() * ghz; t_s = tl[:, 11].mean() * ghz
             print('   layer29 wake -> tail wake %.0f, tail wake->send %.0f' % (t_w - wake[29], t_s - t_w))
-            # layer 0's wake of step t+1 follows the tail's send of step t: the sums differ by the first / last step only
-            step_cyc = None
-            smp = lay[0, :, 13].mean() * ghz       # sample drawn (sum over steps 1..T-1 of step t-1's draw)
-            print('   layer 0: sample drawn -> input ready %.0f cycles (per step, approx)' % ((wake[0] - smp) * T * rows / max(T * rows - rows, 1)))
 
 
 if __name__ == '__main__':

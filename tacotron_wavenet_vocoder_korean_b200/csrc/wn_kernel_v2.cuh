@@ -339,7 +339,6 @@ __device__ __forceinline__ float v2_draw_warp(const WnParams &p, int b, int step
 // One warp of a layer-0 CTA: waits for the Mt partial conv2 outputs of (b, step) from the tail CTAs, adds them left to
 // right onto the bias, writes the logits, draws from the mixture of logistics (wavenet/mixture.py:84-114) and returns
 // the sample in every lane.  Lane o < O owns output o; gum / logistic are precomputed from the step's uniforms.
-__device__ __forceinline__ void pin_ptr(const u64 *&p) { asm volatile("" : "+l"(p)); }
 template <class SH, class PF>
 __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &mb, int b, int step, int lane, bool writer, V2Ab &ab,
                                                 float b2v, float gum, float logistic, PF &pf)
@@ -368,7 +367,6 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
             return base + (w & 255);
         };
         u64 wv[Mt];
-        if (PF::on) { pin_ptr(gb0); pin_ptr(gb1); pin_ptr(gb2); pf.mark(7); }
 #pragma unroll
         for (int i = 0; i < Mt; ++i) wv[i] = ld_relaxed_u64(word(i));
         long long t0 = 0;
@@ -383,7 +381,6 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
                 }
             }
             c2 = fadd(c2, __uint_as_float((unsigned)wv[i]));
-            if (PF::on && i == 0) pf.mark(9);
         }
         if (writer && p.out_logits) p.out_logits[((size_t)b * p.T + step) * O + lane] = c2;
     }
