@@ -53,8 +53,18 @@ def weight_shapes(batch_size=None, dilations=(), filter_width=2, residual_channe
     return shapes
 
 
-def make_weights(seed=1234, bias_scale=0.05, **model_kwargs):
-    """Return {name: float32 ndarray}.  Deterministic in (seed, model_kwargs)."""
+def make_weights(seed=1234, bias_scale=0.05, init='benchmark', **model_kwargs):
+    """Return {name: float32 ndarray}.  Deterministic in (seed, model_kwargs).
+
+    init='benchmark': synthetic weights of a plausible *trained* net (upsample kernels ~ hold filters U(0.3, 0.7), small random biases,
+    log-scale bias shifted) for the generation benchmarks and parity tests.  init='train': what tf.global_variables_initializer gives
+    the reference graph (train_vocoder.py:129-130): Glorot-uniform for every kernel including the conv2d_transpose upsamplers, zero
+    biases, Xavier-normal gc_embedding; pass a fresh seed per run."""
+    if init not in ('benchmark', 'train'):
+        raise ValueError("init must be 'benchmark' or 'train'")
+    train = init == 'train'
+    if train:
+        bias_scale = 0.0
     rng = np.random.RandomState(seed)
     shapes = weight_shapes(**model_kwargs)
     state = {}
@@ -64,7 +74,7 @@ def make_weights(seed=1234, bias_scale=0.05, **model_kwargs):
             w = rng.randn(*shp) * np.sqrt(2.0 / (fan_in + fan_out))
         elif name.endswith('/bias'):
             w = rng.uniform(-bias_scale, bias_scale, shp)
-        elif 'upsample' in name:
+        elif 'upsample' in name and not train:
             # kernels of a trained upsampler are roughly "hold" filters; keep the signal O(1)
             w = rng.uniform(0.3, 0.7, shp)
         else:
@@ -73,7 +83,7 @@ def make_weights(seed=1234, bias_scale=0.05, **model_kwargs):
             lim = np.sqrt(6.0 / (fan_in + fan_out))
             w = rng.uniform(-lim, lim, shp)
         state[name] = w.astype(np.float32)
-    if model_kwargs.get('scalar_input') and model_kwargs.get('use_biases'):
+    if model_kwargs.get('scalar_input') and model_kwargs.get('use_biases') and not train:
         nr = model_kwargs.get('out_channels', 30) // 3
         state['wavenet/conv1d_2/bias'][2 * nr:3 * nr] -= np.float32(3.0)
     return state

@@ -4,6 +4,7 @@ generation path runs as one persistent sm_100a kernel through libwn_b200.so.
 Tensors are torch CUDA tensors; weights are exchanged as a dict keyed by the reference's TF
 variable names.  There is no CPU fallback.
 """
+import os
 import ctypes as C
 
 import numpy as np
@@ -332,10 +333,10 @@ class WaveNetModel(object):
             self._check(_lib.lib().wn_state_reset(self._h, self._inc, self._stream()))
 
     # ------------------------------------------------------------------ training
-    def trainer(self, sample_size, dtype='bf16'):
+    def trainer(self, sample_size, dtype='bf16', init_seed=None):
         """The libwn_train_b200 step for crops of `sample_size` samples, created on first use and seeded with the loaded
-        state dict (or TF-default initialisers: Glorot-uniform kernels, zero biases -- tf.global_variables_initializer,
-        train_vocoder.py:129-130)."""
+        state dict (or TF-default initialisers: Glorot-uniform kernels incl. the upsamplers, zero biases --
+        tf.global_variables_initializer, train_vocoder.py:129-130; `init_seed` None draws a fresh seed per run as TF does)."""
         from .train import WaveNetTrainer
         from .. import synth
         tr = getattr(self, '_trainer', None)
@@ -349,7 +350,10 @@ class WaveNetModel(object):
                       local_condition_channels=self.local_condition_channels, upsample_factor=self.upsample_factor)
             state = tr.state_dict() if tr is not None else getattr(self, '_state', None)
             new = WaveNetTrainer(sample_size, dtype=dtype, device=self.device, **kw)
-            new.load_state_dict(state if state is not None else synth.make_weights(bias_scale=0.0, **kw))
+            if state is None:
+                seed = int(init_seed) if init_seed is not None else int.from_bytes(os.urandom(4), 'little')
+                state = synth.make_weights(seed=seed, init='train', **kw)
+            new.load_state_dict(state)
             if tr is not None:
                 new.global_step = tr.global_step
             self._trainer = new
