@@ -857,15 +857,26 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 pf.mark(2);
                 // 2. current-tap filter/gate column over one K half, from registers; gated activation
                 {
+                    // all 16 LDS.128 of the K half are issued before the first FMA, as volatile asm: left to itself ptxas sometimes
+                    // splits them into two dependent batches of 8 (64 input + 96 weight registers are a tight fit), which costs
+                    // ~120 cycles per layer (profiles/r02_rejected_variants.md: the "slow allocation" of two unrelated edits)
+                    float4 xv[16];
+                    {
+                        const uint32_t xa = smem_u32(xh4);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(xv[i].x), "=f"(xv[i].y), "=f"(xv[i].z), "=f"(xv[i].w)
+                                         : "r"(xa + (uint32_t)i * 16u));
+                    }
                     float acc[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float4 xv = xh4[i];
                         float a = 0.0f;
-                        a = ffma(wfg[i].x, xv.x, a);
-                        a = ffma(wfg[i].y, xv.y, a);
-                        a = ffma(wfg[i].z, xv.z, a);
-                        a = ffma(wfg[i].w, xv.w, a);
+                        a = ffma(wfg[i].x, xv[i].x, a);
+                        a = ffma(wfg[i].y, xv[i].y, a);
+                        a = ffma(wfg[i].z, xv[i].z, a);
+                        a = ffma(wfg[i].w, xv[i].w, a);
                         acc[i] = a;
                     }
 #pragma unroll
