@@ -193,6 +193,7 @@ struct wn_handle {
     DevBuf up_tmp0, up_tmp1;                                  // upsample intermediates
     DevBuf h_forced, h_lc, h_mel, h_unif, h_out, h_logits;    // wn_generate_host staging
     DevBuf g_lc;
+    DevBuf g_noise;                           // cluster path: transformed draw noise of the current launch (wn_noise_prep_kernel)
     DevBuf raw, raw_layers, step_ring_off;                    // TF-layout weights on the device + per-layer pointer table (wn_step)
     std::map<std::string, size_t> raw_off;
     long long step_ring_floats = 0;                                              // wn_generate with mel_dev on a path that materialises the upsampled condition
@@ -325,7 +326,7 @@ void wn_destroy(wn_handle *h)
     if (!h) return;
     DevBuf *bufs[] = {&h->layer_img, &h->tail_img, &h->samp_img, &h->gc_table, &h->wc_onehot, &h->upk, &h->mbox, &h->ring,
                       &h->ring_off, &h->status, &h->prof, &h->mb_tab, &h->up_tmp0, &h->up_tmp1, &h->h_forced, &h->h_lc, &h->h_mel, &h->h_unif,
-                      &h->h_out, &h->h_logits, &h->g_lc, &h->raw, &h->raw_layers, &h->step_ring_off};
+                      &h->h_out, &h->h_logits, &h->g_lc, &h->g_noise, &h->raw, &h->raw_layers, &h->step_ring_off};
     for (DevBuf *b : bufs) b->release();
     if (h->v2_sa) cudaStreamDestroy(h->v2_sa);
     if (h->v2_sb) cudaStreamDestroy(h->v2_sb);
@@ -931,6 +932,18 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
         }
     }
     p.uniforms = a->uniforms_dev;
+    p.noise = nullptr;
+    if (h->v2) {
+        // the draw's noise for every (row, step), transformed once before the launch (see wn_noise_prep_kernel)
+        const int nr = c.out_channels / 3;
+        const long long n = (long long)a->rows * a->T * (nr + 1);
+        CUDA_TRY(h, h->g_noise.ensure((size_t)n * 4));
+        const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)8 * h->sm_count);
+        wn_noise_prep_kernel<<<blocks, 256, 0, st>>>((const float *)a->uniforms_dev, (float *)h->g_noise.p, n, nr);
+        CUDA_TRY(h, cudaGetLastError());
+        p.noise = (const float *)h->g_noise.p;
+        h->launches++;
+    }
     p.out_samples = a->out_samples_dev;
     p.out_logits = a->out_logits_dev;
     // The mailbox / ring strides were laid out for cfg.batch rows; a smaller `rows` only uses a prefix

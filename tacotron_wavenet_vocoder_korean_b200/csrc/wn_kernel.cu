@@ -1039,6 +1039,18 @@ extern "C" __global__ void wn_upsample_stage_kernel(const float *__restrict__ in
 }
 
 // wavenet/ops.py:22-33
+// Noise of the mixture-of-logistics draw (wavenet/mixture.py:96-98, 107-108) for every (row, step): u -> log(-log u) for the nr
+// Gumbel-max values, u -> log u - log(1 - u) for the logistic.  Same pinned log32 as the in-kernel draw; computed once before the
+// launch so that two dependent log32 chains per row-step leave the layer-0 helper group's loop (its slowest stage at 8 rows).
+extern "C" __global__ void wn_noise_prep_kernel(const float *__restrict__ u, float *__restrict__ out, long long n, int nr)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % (nr + 1));
+        const float v = ld_nc_f32(u + i);
+        out[i] = (j < nr) ? wn::log32(-wn::log32(v)) : fsub(wn::log32(v), wn::log32(fsub(1.0f, v)));
+    }
+}
+
 extern "C" __global__ void wn_mu_law_encode_kernel(const float *__restrict__ audio, long long n, float mu, int32_t *__restrict__ out)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {

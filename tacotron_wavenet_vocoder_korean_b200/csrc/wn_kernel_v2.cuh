@@ -551,7 +551,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
             }
             if (l == 0 && has_next && ht <= SH::O / 3 + 1) {
                 constexpr int nr = SH::O / 3;
-                if (ht <= nr) g.su = ld_nc_f32((const float *)p.uniforms + ((size_t)b * p.T + t) * (nr + 1) + ht);
+                if (ht <= nr) g.su = ld_nc_f32(p.noise + ((size_t)b * p.T + t) * (nr + 1) + ht);
                 else if (t + 1 < p.n_forced) g.su = ld_nc_f32(p.forced + (size_t)b * p.n_forced + t + 1);
             }
             return g;
@@ -620,9 +620,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 float sprep = 0.0f;
                 if (l == 0 && has_next && ht <= SH::O / 3 + 1) {
                     constexpr int nr = SH::O / 3;
-                    if (ht < nr) sprep = wn::log32(-wn::log32(cur.su));
-                    else if (ht == nr) sprep = fsub(wn::log32(cur.su), wn::log32(fsub(1.0f, cur.su)));
-                    else sprep = cur.su;
+                    sprep = cur.su;                                      // Gumbel / logistic noise (wn_noise_prep_kernel) or the forced input
                 }
                 pin(oldv); pin(lcv); pin(sprep);
                 hp.mark(6);
@@ -939,11 +937,10 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
             for (int b = 0; b < N; ++b) {
                 const int step = p.T_row[b] - 1;
                 if (step < 0) continue;
-                const float *u = (const float *)p.uniforms + ((size_t)b * p.T + step) * (nr_mix + 1);
+                const float *u = p.noise + ((size_t)b * p.T + step) * (nr_mix + 1);
                 float gum = 0.0f;
-                if (ct < nr_mix) gum = wn::log32(-wn::log32(ld_nc_f32(u + ct)));
-                const float u2 = ld_nc_f32(u + nr_mix);
-                const float logistic = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2)));
+                if (ct < nr_mix) gum = ld_nc_f32(u + ct);
+                const float logistic = ld_nc_f32(u + nr_mix);
                 v2_sample_warp<SH>(p, mb, b, step, ct, true, ab, b2v, gum, logistic, pf);
             }
         }

@@ -91,6 +91,8 @@ struct WnParams {
     int32_t t_mel, n_up, hop;      // hop = prod(F_s)
     int32_t up_f[WN_MAX_UPSAMPLE], up_off[WN_MAX_UPSAMPLE];
     const void *uniforms;
+    const float *noise;            // cluster path, scalar input: the draw's noise per (row, step): nr Gumbel values log(-log u), then the logistic
+                                   // log u - log(1 - u), transformed from `uniforms` by wn_noise_prep_kernel before the launch
     float *out_samples;
     float *out_logits;
     int32_t *status;               // [0] abort flag, [1] cta that raised it, [2] code
