@@ -180,6 +180,18 @@ int wn_mu_law_encode(const float *audio_dev, int64_t n, int quantization_channel
 int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, int quantization,
                      float *out_dev, void *stream);
 
+/* wavenet/mixture.py:84-114 sample_from_discretized_mix_logistic(y, log_scale_min) on device tensors: y_dev (rows, 3*nr_mix)
+ * network outputs [logit | mean | log_scale], uniforms_dev (rows, nr_mix + 1) in (1e-5, 1 - 1e-5) in place of TF's unseeded
+ * tf.random_uniform (nr_mix for the Gumbel-max, one for the logistic) -> out_dev (rows) in [-1, 1].  Same pinned arithmetic
+ * as the draw inside wn_generate / wn_step (bit-identical to the oracle). */
+int wn_mol_sample(const float *y_dev, const float *uniforms_dev, int64_t rows, int nr_mix, float log_scale_min,
+                  float *out_dev, void *stream);
+/* wavenet/mixture.py:27-81 discretized_mix_logistic_loss(y_hat, y, num_class, log_scale_min, reduce), forward value only (the
+ * training step evaluates it fused with its gradient, wn_train_b200.h): y_hat_dev (rows, 3*nr_mix), y_dev (rows) targets in
+ * [-1, 1] -> loss_out_dev (rows) per-step losses (reduce=False) and / or sum_out_dev (one double: reduce=True); either may be NULL. */
+int wn_mol_loss(const float *y_hat_dev, const float *y_dev, int64_t rows, int nr_mix, int num_class, float log_scale_min,
+                float *loss_out_dev, double *sum_out_dev, void *stream);
+
 /* utils/audio.py:69-75 melspectrogram(wav, hparams) ("next-2"): pre-emphasis -> librosa.stft
  * (center, reflect pad, periodic Hann zero-padded to fft_size) -> |D| -> Slaney mel basis -> 20*log10(max(1e-5, .))
  * - ref_level_db -> symmetric normalisation + clip.  Fields are the reference's hparams.py:18-34.

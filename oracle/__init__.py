@@ -69,6 +69,8 @@ def lib():
         L.orc_mu_law_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_mu_law_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_softmax_probs.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_mol_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+        L.orc_mol_sample.restype = None
         L.orc_math_probe.restype = C.c_float
         L.orc_math_probe.argtypes = [C.c_int, C.c_float]
         _LIB = L
@@ -189,6 +191,17 @@ def mu_law_decode(output, quantization_channels, quantization=True):
     a = np.ascontiguousarray(output, dtype=np.float32)
     out = np.empty(a.shape, np.float32)
     lib().orc_mu_law_decode(_ptr(a), a.size, quantization_channels, int(quantization), _ptr(out))
+    return out
+
+
+def mol_sample(y, uniforms):
+    """wavenet/mixture.py:84-114 on (…, 3*nr_mix) logits with (…, nr_mix + 1) uniforms -> (…) samples."""
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    u = np.ascontiguousarray(uniforms, dtype=np.float32)
+    nr = y.shape[-1] // 3
+    assert y.shape[-1] == 3 * nr and u.shape == y.shape[:-1] + (nr + 1,)
+    out = np.empty(y.shape[:-1], np.float32)
+    lib().orc_mol_sample(_ptr(y), _ptr(u), out.size, nr, _ptr(out))
     return out
 
 

@@ -649,6 +649,13 @@ void orc_softmax_probs(const float *c2, int Q, float *probs)
     mulaw_draw(c2, Q, 1.0f, 0.5, probs);
 }
 
+/* mixture.py:84-114 on a tensor of logits: y (rows, 3*nr_mix), u (rows, nr_mix + 1) -> out (rows); the same mol_draw the
+ * generation loop calls, exposed for the test of the product's wn_mol_sample. */
+void orc_mol_sample(const float *y, const float *u, long rows, int nr_mix, float *out)
+{
+    for (long i = 0; i < rows; ++i) out[i] = mol_draw(y + i * 3 * nr_mix, nr_mix, u + i * (nr_mix + 1));
+}
+
 float orc_math_probe(int which, float x)
 {
     switch (which) {

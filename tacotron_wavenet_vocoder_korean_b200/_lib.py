@@ -72,7 +72,7 @@ class WnMelConfig(C.Structure):
 EXPORTS = ["wn_create", "wn_destroy", "wn_last_error", "wn_set_weight", "wn_finalize", "wn_plan_config", "wn_get_plan",
            "wn_get_info", "wn_receptive_field", "wn_upsample", "wn_generate", "wn_sync_check",
            "wn_generate_host", "wn_mu_law_encode", "wn_mu_law_decode", "wn_melspectrogram",
-           "wn_state_create", "wn_state_reset", "wn_state_destroy", "wn_step"]
+           "wn_state_create", "wn_state_reset", "wn_state_destroy", "wn_step", "wn_mol_sample", "wn_mol_loss"]
 
 _lib = None
 
@@ -119,5 +119,7 @@ def lib():
         L.wn_mu_law_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.wn_mu_law_decode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.wn_melspectrogram.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.POINTER(WnMelConfig), C.c_void_p, C.c_void_p]
+        L.wn_mol_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        L.wn_mol_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib

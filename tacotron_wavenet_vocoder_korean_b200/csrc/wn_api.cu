@@ -1323,6 +1323,28 @@ int wn_mu_law_decode(const float *in_dev, int64_t n, int quantization_channels, 
     return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
 }
 
+int wn_mol_sample(const float *y_dev, const float *uniforms_dev, int64_t rows, int nr_mix, float log_scale_min, float *out_dev, void *stream)
+{
+    if (!y_dev || !uniforms_dev || !out_dev || rows < 0 || nr_mix < 1) return WN_ERR_ARG;
+    if (rows == 0) return WN_OK;
+    int blocks = (int)std::min<int64_t>((rows + 127) / 128, 148 * 8);
+    wn_mol_sample_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(y_dev, uniforms_dev, rows, nr_mix, log_scale_min, out_dev);
+    return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+
+int wn_mol_loss(const float *y_hat_dev, const float *y_dev, int64_t rows, int nr_mix, int num_class, float log_scale_min,
+                float *loss_out_dev, double *sum_out_dev, void *stream)
+{
+    if (!y_hat_dev || !y_dev || rows < 0 || nr_mix < 1 || num_class < 2 || (!loss_out_dev && !sum_out_dev)) return WN_ERR_ARG;
+    if (sum_out_dev && cudaMemsetAsync(sum_out_dev, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return WN_ERR_CUDA;
+    if (rows == 0) return WN_OK;
+    int blocks = (int)std::min<int64_t>((rows + 127) / 128, 148 * 8);
+    const float half_bin = (float)(1.0 / (num_class - 1)), log_half = (float)std::log((num_class - 1) / 2.0);
+    wn_mol_loss_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(y_hat_dev, y_dev, rows, nr_mix, log_scale_min, half_bin, log_half,
+                                                                 loss_out_dev, sum_out_dev);
+    return cudaGetLastError() == cudaSuccess ? WN_OK : WN_ERR_CUDA;
+}
+
 }  // extern "C"
 
 /* ---- STFT -> mel (utils/audio.py:69-75) ---------------------------------------------------------------- */

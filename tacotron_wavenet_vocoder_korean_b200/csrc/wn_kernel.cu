@@ -794,6 +794,78 @@ __device__ void sampler_role(const WnParams &p)
     pf.flush();
 }
 
+// wavenet/mixture.py:84-114 sample_from_discretized_mix_logistic on a tensor of logits (rows, 3*nr) with uniforms (rows, nr + 1):
+// the same pinned arithmetic as the in-kernel draw (Gumbel-max over y - log(-log u), first maximum wins like tf.argmax, the
+// selected mean / clamped log-scale, mean + exp(log_scale) * (log u - log(1 - u)), clip to [-1, 1]).  One thread per row.
+extern "C" __global__ void wn_mol_sample_kernel(const float *__restrict__ y, const float *__restrict__ u, long long rows, int nr,
+                                                float log_scale_min, float *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const float *yr = y + i * (3 * nr), *ur = u + i * (nr + 1);
+        int best = 0;
+        float bestv = 0.0f;
+        for (int k = 0; k < nr; ++k) {
+            const float g = fsub(yr[k], wn::log32(-wn::log32(ur[k])));
+            if (k == 0 || g > bestv) { bestv = g; best = k; }
+        }
+        const float mean = yr[nr + best];
+        float ls = yr[2 * nr + best];
+        if (!(ls > log_scale_min)) ls = log_scale_min;
+        const float u2 = ur[nr];
+        const float d = fsub(wn::log32(u2), wn::log32(fsub(1.0f, u2)));
+        float x = fadd(mean, fmul(wn::exp32(ls), d));
+        x = fmaxf(x, -1.0f);
+        x = fminf(x, 1.0f);
+        out[i] = x;
+    }
+}
+
+// wavenet/mixture.py:27-81 discretized_mix_logistic_loss, forward only, on a tensor of network outputs y_hat (rows, 3*nr) and
+// targets y (rows): per-row loss -logsumexp_k(log_prob_k + log_softmax(logit)_k) with the reference's three tf.where branches
+// (y < -0.999: log cdf_plus; y > 0.999: log(1 - cdf_min); else log(max(cdf_delta, 1e-12)) where cdf_delta > 1e-5, the mid-point
+// log-pdf otherwise).  fp32 like the reference's graph; loss_out (rows) and / or sum_out (one double, atomically accumulated).
+extern "C" __global__ void wn_mol_loss_kernel(const float *__restrict__ y_hat, const float *__restrict__ y, long long rows, int nr,
+                                              float log_scale_min, float half_bin, float log_half_classes,
+                                              float *__restrict__ loss_out, double *__restrict__ sum_out)
+{
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const float *yr = y_hat + i * (3 * nr);
+        const float t = y[i];
+        float mx = -INFINITY;
+        for (int k = 0; k < nr; ++k) mx = fmaxf(mx, yr[k]);
+        float se = 0.0f;
+        for (int k = 0; k < nr; ++k) se += expf(yr[k] - mx);
+        const float lse_logits = mx + logf(se);
+        float amax = -INFINITY, asum = 0.0f;              // streaming logsumexp over the components
+        for (int k = 0; k < nr; ++k) {
+            const float ls = fmaxf(yr[2 * nr + k], log_scale_min);
+            const float c = t - yr[nr + k], inv = expf(-ls);
+            const float pin = inv * (c + half_bin), min_ = inv * (c - half_bin), mid = inv * c;
+            float logp;
+            if (t < -0.999f) {
+                logp = pin - (fmaxf(pin, 0.0f) + log1pf(expf(-fabsf(pin))));
+            } else if (t > 0.999f) {
+                logp = -(fmaxf(min_, 0.0f) + log1pf(expf(-fabsf(min_))));
+            } else {
+                const float delta = 1.0f / (1.0f + expf(-pin)) - 1.0f / (1.0f + expf(-min_));
+                if (delta > 1e-5f) logp = logf(fmaxf(delta, 1e-12f));
+                else logp = mid - ls - 2.0f * (fmaxf(mid, 0.0f) + log1pf(expf(-fabsf(mid)))) - log_half_classes;
+            }
+            const float a = logp + (yr[k] - lse_logits);
+            if (a > amax) { asum = asum * expf(amax - a) + 1.0f; amax = a; }
+            else asum += expf(a - amax);
+        }
+        const float loss = -(amax + logf(asum));
+        if (loss_out) loss_out[i] = loss;
+        acc += (double)loss;
+    }
+    if (sum_out) {
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sum_out, acc);
+    }
+}
+
 #include "wn_kernel_static.cuh"
 #include "wn_kernel_ws.cuh"
 #include "wn_kernel_v2.cuh"

@@ -407,6 +407,51 @@ def test_mu_law_codec_on_device():
     np.testing.assert_allclose(dec_c, g['dec_c'], atol=1e-4, rtol=1e-5)
 
 
+def test_mixture_module_sample_and_loss_on_device():
+    """wavenet/mixture.py as tensor-level entry points (wn_mol_sample / wn_mol_loss): the draw is bit-identical to the oracle's
+    mol_draw and within 2e-5 of the reference's own draws on the reference's own logits (ref_mol.npz); the loss follows the fp64
+    numpy evaluation of mixture.py:27-81 in every tf.where branch at the fp32 tolerance of the oracle's own fp32 evaluation."""
+    from oracle import train_oracle as to
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.mixture import sample_from_discretized_mix_logistic, discretized_mix_logistic_loss
+    g = np.load(os.path.join(GOLD, 'ref_mol.npz'))
+    kw = synth.tiny_mol()
+    inp = make_inputs(kw, g['outputs'].shape[1])
+    s = sample_from_discretized_mix_logistic(torch.from_numpy(g['raw_output']).cuda(), uniforms=torch.from_numpy(inp['uniforms']).cuda()).cpu().numpy()
+    assert np.array_equal(s, oracle.mol_sample(g['raw_output'], inp['uniforms']))
+    assert np.abs(s - g['outputs'][:, :, 0]).max() < 2e-5
+    rs = np.random.RandomState(7)
+    B, T, K = 3, 1000, 10
+    y = rs.randn(B, T, 3 * K).astype(np.float32)
+    y[..., 2 * K:] = rs.uniform(-9, 1, (B, T, K))
+    y[0, :50, 2 * K:] = -40.0                                  # below log_scale_min: tf.maximum clamp
+    u = rs.uniform(1e-5, 1 - 1e-5, (B, T, K + 1)).astype(np.float32)
+    u[1, :10, :K], u[2, :10, K] = 1e-5, 1 - 1e-5                # extremes of the uniform range
+    s = sample_from_discretized_mix_logistic(torch.from_numpy(y).cuda(), uniforms=torch.from_numpy(u).cuda()).cpu().numpy()
+    assert np.array_equal(s, oracle.mol_sample(y, u))
+    assert s.min() >= -1.0 and s.max() <= 1.0 and (s == 1.0).any() and (s == -1.0).any()      # the clip is exercised
+    r = sample_from_discretized_mix_logistic(torch.from_numpy(y).cuda())                          # own uniforms: in range, not constant
+    assert r.shape == (B, T) and float(r.min()) >= -1.0 and float(r.max()) <= 1.0 and float(r.std()) > 0.05
+    # loss: the case of tests/test_train_oracle.py::test_mol_loss_matches_float64_numpy_in_every_branch
+    rs = np.random.RandomState(0)
+    B, T = 2, 400
+    y_hat = rs.randn(B, T, 3 * K).astype(np.float32)
+    y_hat[..., 2 * K:] = rs.uniform(-9, -1, (B, T, K))
+    y_hat[0, :40, 2 * K:] = -40.0
+    tgt = rs.uniform(-1, 1, (B, T, 1)).astype(np.float32)
+    tgt[0, :20], tgt[1, :20] = -1.0, 1.0
+    y_hat[1, 100:140, K:2 * K] = 30.0                            # cdf_delta <= 1e-5: log-pdf branch
+    for nc in (256, 65536):
+        ref = to.mol_loss_np(y_hat, tgt, num_class=nc)
+        got = discretized_mix_logistic_loss(torch.from_numpy(y_hat).cuda(), torch.from_numpy(tgt).cuda(), num_class=nc, reduce=False).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=5e-3, atol=1e-3)   # fp32: cdf_plus - cdf_min cancels (same bound as the fp32 oracle)
+        ref32 = to.mol_loss(torch.from_numpy(y_hat), torch.from_numpy(tgt), num_class=nc).numpy()
+        assert np.abs(got - ref).max() <= 3 * np.abs(ref32 - ref).max() + 1e-5          # not noisier than the fp32 oracle itself
+        tot = float(discretized_mix_logistic_loss(torch.from_numpy(y_hat).cuda(), torch.from_numpy(tgt).cuda(), num_class=nc))
+        assert abs(tot - float(got.astype(np.float64).sum())) < 1e-6 * abs(tot)
+    with pytest.raises(AssertionError):
+        sample_from_discretized_mix_logistic(torch.zeros(1, 4, 31).cuda())
+
+
 def test_argument_errors_are_loud():
     kw = synth.tiny_mol()
     net, _ = build(kw)

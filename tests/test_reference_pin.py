@@ -53,6 +53,15 @@ def test_oracle_matches_reference_mol_path():
     assert np.abs(s - g['outputs'][:, :, 0]).max() < 2e-5                                     # mixture.py:84-114 draw
 
 
+def test_oracle_tensor_level_mol_draw_matches_reference_draws():
+    """oracle.mol_sample (mixture.py:84-114 on a tensor of logits) fed the REFERENCE's own logits reproduces the reference's draws."""
+    g = np.load(os.path.join(GOLD, 'ref_mol.npz'))
+    kw = synth.tiny_mol()
+    inp = make_inputs(kw, g['outputs'].shape[1])
+    s = oracle.mol_sample(g['raw_output'], inp['uniforms'])
+    assert np.abs(s - g['outputs'][:, :, 0]).max() < 2e-5
+
+
 def test_oracle_matches_reference_mulaw_path():
     g = np.load(os.path.join(GOLD, 'ref_mulaw.npz'))
     kw = MULAW_LC

@@ -68,6 +68,44 @@ def test_intermediate_stages_match_oracle():
         assert err <= TOL, "%s: max |err| %.3g" % (cname, err)
 
 
+def test_host_buffer_entry_point_equals_device_path():
+    """taco_synthesize_host (ids in, mel / linear / alignments out through HOST buffers, copies inside): bit-identical to the
+    device path, on reused buffers, with and without the linear output; the pinned staging slots are shrunk to 1.25 MB so that
+    the 5.7 MB linear output crosses them in several pipelined chunks with a partial last one (and the 1 MB threaded-copy split)."""
+    import ctypes as C
+    from tacotron_wavenet_vocoder_korean_b200 import _taco_lib
+    hp, ns, w, ids, lens, spk, steps = case('tiny_mon_norm')
+    reps = 24
+    ids, lens, spk = np.tile(ids, (reps, 1)), np.tile(lens, reps), np.tile(spk, reps)
+    steps = 160
+    m = run_cuda(hp, ns, w, ids, lens, spk, steps)
+    os.environ['TACO_STAGE_BYTES'] = str(5 << 18)          # read when the handle first allocates its staging ring
+    N, T_in = ids.shape
+    r, nm, nf = hp['reduction_factor'], hp['num_mels'], hp['num_freq']
+    L = _taco_lib.lib()
+    ids_c = np.ascontiguousarray(ids, np.int32)
+    lens_c, spk_c = np.ascontiguousarray(lens, np.int32), np.ascontiguousarray(spk, np.int32)
+    for want_linear in (True, False, True):
+        mel_h = np.full((N, steps * r, nm), np.nan, np.float32)
+        lin_h = np.full((N, steps * r, nf), np.nan, np.float32)
+        al_h = np.full((N, T_in, steps), np.nan, np.float32)
+        a = _taco_lib.TacoSynthArgs()
+        a.N, a.T_in, a.n_steps = N, T_in, steps
+        a.ids_dev = ids_c.ctypes.data
+        a.lengths = lens_c.ctypes.data_as(C.POINTER(C.c_int32))
+        a.speaker_ids = spk_c.ctypes.data_as(C.POINTER(C.c_int32))
+        a.mel_dev, a.alignments_dev = mel_h.ctypes.data, al_h.ctypes.data
+        a.linear_dev = lin_h.ctypes.data if want_linear else None
+        assert L.taco_synthesize_host(m._h, C.byref(a)) == 0, L.taco_last_error(m._h)
+        assert np.array_equal(mel_h, m.mel_outputs.cpu().numpy())
+        assert np.array_equal(al_h, m.alignments.cpu().numpy())
+        if want_linear:
+            assert np.array_equal(lin_h, m.linear_outputs.cpu().numpy())
+        else:
+            assert np.isnan(lin_h).all()
+    del os.environ['TACO_STAGE_BYTES']
+
+
 def test_manual_alignments_override():
     hp, ns, w, ids, lens, spk, steps = case('tiny_mon_norm')
     N, T_in = ids.shape

@@ -32,22 +32,6 @@ def test_mol_loss_matches_float64_numpy_in_every_branch():
     np.testing.assert_allclose(got32, ref, rtol=5e-3, atol=1e-3)   # fp32: cdf_plus - cdf_min cancels
 
 
-def test_product_mixture_loss_entry_point_matches_numpy():
-    """wavenet.mixture.discretized_mix_logistic_loss (tensor-level entry point of the reference module)."""
-    from tacotron_wavenet_vocoder_korean_b200.wavenet.mixture import discretized_mix_logistic_loss
-    rs = np.random.RandomState(2)
-    y_hat = rs.randn(2, 50, 30).astype(np.float32)
-    y_hat[..., 20:] = rs.uniform(-8, -1, (2, 50, 10))
-    y = rs.uniform(-1, 1, (2, 50, 1)).astype(np.float32)
-    y[0, :5], y[1, :5] = -1.0, 1.0
-    for nc in (256, 65536):
-        ref = to.mol_loss_np(y_hat, y, num_class=nc)
-        got = discretized_mix_logistic_loss(torch.from_numpy(y_hat).double(), torch.from_numpy(y).double(), num_class=nc, reduce=False).numpy()
-        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9)
-        tot = float(discretized_mix_logistic_loss(torch.from_numpy(y_hat).double(), torch.from_numpy(y).double(), num_class=nc))
-        assert abs(tot - ref.sum()) < 1e-7 * abs(ref.sum())
-
-
 def test_training_graph_equals_incremental_generation_under_teacher_forcing():
     """Without local conditioning (the training graph aligns lc per layer) the training logits at
     position j are the incremental graph's output after it has consumed samples [0, rf-1+j]."""
