@@ -116,6 +116,33 @@ def cpu_port_throughput(steps, threads):
     return ROWS * steps / dt
 
 
+def cpu_best_effort_throughput(steps, threads):
+    """BASELINE.md section 3 "B-cpu": oracle/wn_cpu_best.h -- the same arithmetic as the port (bit-identical output), organised
+    like the GPU path: every thread keeps a packed column slice of all weights in its own cache, all rows advance together,
+    two spin barriers per layer.  Returns samples/s."""
+    import oracle
+    kw, w, mel, uniforms, x0, gc = make_job(0)
+    om = oracle.OracleModel(**kw)
+    om.set_weights(w)
+    lc = om.upsample(mel[:, :(steps + 299) // 300])
+    t0 = time.perf_counter()
+    om.generate(steps, x0, uniforms[:, :steps], lc_up=lc, gc_ids=np.asarray(gc, np.int32), best_effort_threads=threads)
+    return ROWS * steps / (time.perf_counter() - t0)
+
+
+def best_effort_thread_counts():
+    """Column slices are whole 8-float vectors of the 128 gated channels: at most 16 threads, powers of two."""
+    cores = os.cpu_count() or 1
+    return [n for n in (16, 8, 4, 2, 1) if n <= cores][:2] or [1]
+
+
+def cpu_best_effort(steps):
+    """Best thread count of a short trial, then the bounded sample.  Returns (samples/s, threads)."""
+    trials = {n: cpu_best_effort_throughput(60, n) for n in best_effort_thread_counts()}
+    n = max(trials, key=trials.get)
+    return cpu_best_effort_throughput(steps, n), n
+
+
 def cpu_reference_structure_throughput(steps):
     """SURVEY.md 8(d) "reference-structure" baseline: the numpy restatement driven by the same per-sample Python loop as
     generate.py:202-233, every queue shifted by a full copy per step (model.py:122,125,145), numpy's BLAS threads as they
@@ -142,10 +169,19 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     threads = min(cores, ROWS)
     sample_steps = CPU_SAMPLE_STEPS
-    for _ in range(args.warmup):
-        cpu_port_throughput(60, threads)
+    # two organisations of the same arithmetic (bit-identical outputs): rows over threads (the plain port) and weight-stationary
+    # threads (wn_cpu_best.h, BASELINE.md "B-cpu"); the warm-up picks the faster one on this host, the timed steps run it
+    trial = {("port", threads): 0.0}
+    for n in best_effort_thread_counts():
+        trial[("best_effort", n)] = 0.0
+    for _ in range(max(1, args.warmup)):
+        for (kind, n) in trial:
+            v = cpu_port_throughput(60, n) if kind == "port" else cpu_best_effort_throughput(60, n)
+            trial[(kind, n)] = max(trial[(kind, n)], v)
+    (impl_kind, threads) = max(trial, key=trial.get)
+    run = (lambda st: cpu_port_throughput(st, threads)) if impl_kind == "port" else (lambda st: cpu_best_effort_throughput(st, threads))
     t0 = time.perf_counter()
-    vals = [cpu_port_throughput(sample_steps, threads) for _ in range(args.steps)]
+    vals = [run(sample_steps) for _ in range(args.steps)]
     dt = time.perf_counter() - t0
     # each step's throughput is timed around the generation loop only (as generate.py:199 does); the
     # wall time per step additionally contains building the oracle model and the upsampling
@@ -155,11 +191,16 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "steps_per_row": T_STEPS},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
-                             "host_cores": cores, "sample": "%d rows x %d steps of the workload per bench step, rows over %d host threads "
-                                       "(oracle/wn_oracle.c; the TF 1.x reference is not installable)" % (ROWS, sample_steps, threads),
-                             "note": "a stated baseline, not the target: the C port streams the 21 MB of weights per row and step and is built "
-                                     "with -ffp-contract=off so that it stays bit-comparable; it is not a tuned 'best-effort CPU' implementation "
-                                     "(BASELINE.md section 3 B-cpu) and a GPU/CPU ratio says nothing about kernel quality -- roofline.frac does"},
+                             "host_cores": cores, "organisation": impl_kind,
+                             "sample": "%d rows x %d steps of the workload per bench step on %d host threads: %s "
+                                       "(the TF 1.x reference is not installable)" % (
+                                           ROWS, sample_steps, threads,
+                                           "oracle/wn_cpu_best.h, weight-stationary threads, all rows together (BASELINE.md B-cpu)"
+                                           if impl_kind == "best_effort" else "oracle/wn_oracle.c, rows over threads"),
+                             "warmup_trials_samples_per_sec": {"%s/%d threads" % k: x for k, x in trial.items()},
+                             "note": "a stated baseline, not the target: the faster of the two CPU organisations of the oracle's arithmetic on this "
+                                     "host (both bit-identical to the oracle, built with -ffp-contract=off, AVX2 + FMA); a GPU/CPU ratio says "
+                                     "nothing about kernel quality -- roofline.frac does"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "per_step_values": vals}
     print(json.dumps(line))
@@ -573,8 +614,11 @@ def main():
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "cpu_model": cpu_model_name(),
                "host_cores": os.cpu_count(), "sample": "%d rows x %d steps of the same workload, rows over %d host threads (oracle/wn_oracle.c, plain-C "
                          "restatement; the TF 1.x reference cannot be installed)" % (ROWS, CPU_SAMPLE_STEPS, threads),
-               "note": "a stated baseline, not the target (not a tuned best-effort CPU implementation: every row re-streams the 21 MB of "
-                       "weights, built with -ffp-contract=off for bit-comparability)",
+               "note": "a stated baseline, not the target (rows over threads: every row re-streams the 21 MB of weights; built with "
+                       "-ffp-contract=off for bit-comparability); best_effort is the B-cpu organisation of BASELINE.md section 3",
+               "best_effort": (lambda r: {"value": r[0], "unit": "samples/s", "cores": r[1], "sample": "%d rows x %d steps, oracle/wn_cpu_best.h: "
+                               "weight-stationary threads with packed column slices, all rows together, 2 spin barriers per layer; "
+                               "output bit-identical to the port" % (ROWS, CPU_SAMPLE_STEPS)})(cpu_best_effort(CPU_SAMPLE_STEPS)),
                "reference_structure": {"value": cpu_reference_structure_throughput(300), "unit": "samples/s",
                                        "sample": "%d rows x 300 steps, numpy restatement in the per-sample Python loop of "
                                                  "generate.py:202-233 with full queue copies per step (oracle/np_oracle.py)" % ROWS}}

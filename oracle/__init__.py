@@ -45,7 +45,7 @@ class OrcPlan(C.Structure):
 def build(force=False):
     """Compile liborc.so in place (gcc, a second or two)."""
     so = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, f) for f in ("wn_oracle.c", "wn_math_ref.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("wn_oracle.c", "wn_math_ref.h", "wn_cpu_best.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so
@@ -65,6 +65,7 @@ def lib():
         L.orc_generate.argtypes = [C.c_void_p, C.POINTER(OrcPlan), C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p]
+        L.orc_generate_best.argtypes = L.orc_generate.argtypes + [C.c_int]
         L.orc_receptive_field.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_mu_law_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_mu_law_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -150,7 +151,7 @@ class OracleModel:
         return out
 
     def generate(self, T, forced, uniforms, lc_up=None, lc_shift=0, gc_ids=None, temperature=1.0,
-                 plan=None, want_logits=False):
+                 plan=None, want_logits=False, best_effort_threads=0):
         """Run T steps per batch row.  forced: (N, n_forced) fp32, n_forced>=1.
         uniforms: (N,T,nr_mix+1) fp32 for scalar input, (N,T) fp64 for mu-law."""
         n = self.cfg.batch
@@ -169,9 +170,15 @@ class OracleModel:
         out = np.empty((n, T), np.float32)
         logits = np.empty((n, T, self.out_dim), np.float32) if want_logits else None
         plan = plan or OrcPlan.natural()
-        self._check(lib().orc_generate(self._h, C.byref(plan), T, forced.shape[1], _ptr(forced), _ptr(lc_up),
-                                       t_lc, lc_shift, _ptr(gc), _ptr(uniforms), float(temperature),
-                                       _ptr(out), _ptr(logits)))
+        if best_effort_threads:
+            # wn_cpu_best.h: weight-stationary threads, all rows together; bit-identical to orc_generate for the same plan
+            self._check(lib().orc_generate_best(self._h, C.byref(plan), T, forced.shape[1], _ptr(forced), _ptr(lc_up),
+                                                t_lc, lc_shift, _ptr(gc), _ptr(uniforms), float(temperature),
+                                                _ptr(out), _ptr(logits), int(best_effort_threads)))
+        else:
+            self._check(lib().orc_generate(self._h, C.byref(plan), T, forced.shape[1], _ptr(forced), _ptr(lc_up),
+                                           t_lc, lc_shift, _ptr(gc), _ptr(uniforms), float(temperature),
+                                           _ptr(out), _ptr(logits)))
         return (out, logits) if want_logits else out
 
 

@@ -667,3 +667,6 @@ float orc_math_probe(int which, float x)
     default: return (float)orc_exp64((double)x);
     }
 }
+
+/* the "best-effort CPU" baseline (BASELINE.md section 3, B-cpu): same structures, same arithmetic, weight-stationary threads */
+#include "wn_cpu_best.h"

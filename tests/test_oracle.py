@@ -202,3 +202,25 @@ def test_oracle_errors():
         om.set_weights({'wavenet/nonsense': np.zeros(3, np.float32)})
     with pytest.raises(RuntimeError):
         om.generate(4, np.zeros((2, 1), np.float32), np.full((2, 4, 11), 0.5, np.float32))   # no weights
+
+
+@pytest.mark.parametrize('threads', [1, 3, 4])
+def test_best_effort_cpu_organisation_is_bit_identical_to_the_port(threads):
+    """oracle/wn_cpu_best.h (BASELINE.md B-cpu: weight-stationary threads, all rows together) against orc_generate: same samples and
+    logits bit for bit, for the natural plan and a chunked one, MoL and mu-law heads, with and without conditioning, for
+    thread counts that do and do not divide the channel counts."""
+    from tacotron_wavenet_vocoder_korean_b200 import synth
+    from tests.helpers import make_inputs, oracle_model
+    mulaw_lc = dict(synth.tiny_mulaw(), local_condition_channels=20, upsample_factor=[2, 3], global_condition_channels=8,
+                    global_condition_cardinality=3)
+    chunked = oracle.OrcPlan.natural()
+    chunked.M, chunked.Mt, chunked.t_cur, chunked.t_old, chunked.t_dense, chunked.t_skip, chunked.t_post1 = 2, 2, 4, 2, 2, 4, 4
+    for kw, T, plan in ((synth.tiny_mol(), 120, None), (synth.tiny_mol(), 60, chunked), (synth.tiny_mulaw(), 80, None), (mulaw_lc, 60, None),
+                        (synth.cfg2(5), 12, None)):
+        om = oracle_model(kw, synth.make_weights(**kw))
+        inp = make_inputs(kw, T)
+        lc = om.upsample(inp['mel']) if 'mel' in inp else None
+        forced = inp['forced_full'][:, :7]                      # a primed start, then free running
+        a = om.generate(T, forced, inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True, plan=plan)
+        b = om.generate(T, forced, inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True, plan=plan, best_effort_threads=threads)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
