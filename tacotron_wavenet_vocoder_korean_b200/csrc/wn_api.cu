@@ -1440,14 +1440,27 @@ int wn_melspectrogram(const float *wav_dev, int rows, int64_t n, const wn_mel_co
     p.min_level = (float)std::exp(mc->min_level_db / 20.0 * std::log(10.0));
     p.ref_level_db = mc->ref_level_db; p.min_level_db = mc->min_level_db; p.max_abs = mc->max_abs_value;
     p.out = out_dev;
-    const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 8 + 16;    // FFT buffer + two magnitude spectra
-    if (cudaFuncSetAttribute(wn_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");
+    const long long items = (long long)rows * ((p.frames + 1) / 2);        // one CTA iteration = one PAIR of frames
+    static const bool radix2 = getenv("WN_MEL_RADIX2") != nullptr;         // A/B: the round-1 radix-2 kernel
+    if (p.n_fft <= 4096 && !radix2) {
+        // Stockham radix-8 passes through a padded ping-pong buffer (2 x 9/8 x n_fft double2); the magnitudes reuse the free half
+        const size_t smem = (size_t)2 * (p.n_fft + (p.n_fft >> 3)) * 16;
+        if (cudaFuncSetAttribute(wn_mel_kernel_s8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");
+        }
+        const int per_sm = std::max(1, std::min(2, (int)((size_t)(220 << 10) / smem)));
+        const int grid = (int)std::min<long long>(items, 148LL * per_sm);
+        wn_mel_kernel_s8<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 8 + 16;    // FFT buffer + two magnitude spectra
+        if (cudaFuncSetAttribute(wn_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");
+        }
+        const int grid = (int)std::min<long long>(items, 148LL * 16);
+        wn_mel_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     }
-    const long long items = (long long)rows * p.frames;
-    const int grid = (int)std::min<long long>(items, 148LL * 16);
-    wn_mel_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     if (cudaGetLastError() != cudaSuccess) return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: launch failed");
     return WN_OK;
 }

@@ -67,3 +67,23 @@ def test_gpu_melspectrogram_batch_edges_errors():
     assert float(loud.max()) <= 4.0
     with pytest.raises(RuntimeError):
         audio.melspectrogram(torch.zeros(500), hparams)                      # shorter than fft_size / 2: cannot reflect-pad
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fft_size,win_size,hop', [(2048, 1200, 300), (512, 400, 100), (1024, 1024, 256), (4096, 2400, 600), (8192, 4800, 1200), (64, 64, 16)])
+def test_gpu_melspectrogram_fft_sizes_and_radix_paths(fft_size, win_size, hop):
+    """Every factorisation the Stockham kernel takes (8*8*8*4, 8*8*8, 8*8*8*2, 8^4, 8*8) and the radix-2 kernel (n_fft 8192, and
+    WN_MEL_RADIX2 for the default size) against the oracle within 1e-4; odd frame counts leave the last pair half empty."""
+    import copy
+    import os
+    from tacotron_wavenet_vocoder_korean_b200 import audio
+    hp = copy.copy(hparams)
+    hp.fft_size, hp.win_size, hp.hop_size = fft_size, win_size, hop
+    if fft_size == 64:
+        hp.num_mels = 8
+    for n in (24000 + 77, hop * 20):                       # 1 + n // hop frames: even and odd counts
+        x = mo.synthetic_speech(n, seed=1)
+        ref = mo.melspectrogram(x, fft_size=fft_size, win_size=win_size, hop_size=hop, num_mels=hp.num_mels)
+        got = audio.melspectrogram(torch.from_numpy(x), hp).cpu().numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-4, np.abs(got - ref).max()
