@@ -1445,13 +1445,16 @@ int wn_melspectrogram(const float *wav_dev, int rows, int64_t n, const wn_mel_co
     if (p.n_fft <= 4096 && !radix2) {
         // Stockham radix-8 passes through a padded ping-pong buffer (2 x 9/8 x n_fft double2); the magnitudes reuse the free half
         const size_t smem = (size_t)2 * (p.n_fft + (p.n_fft >> 3)) * 16;
-        if (cudaFuncSetAttribute(wn_mel_kernel_s8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        static const int want_ctas = getenv("WN_MEL_CTAS") ? atoi(getenv("WN_MEL_CTAS")) : 3;     // A/B: 2 = the 122-register build
+        const int fit = std::max(1, (int)((size_t)(226 << 10) / (smem + 1024)));               // CTAs per SM that fit in shared memory
+        const int per_sm = std::min(fit, want_ctas >= 3 ? 3 : 2);
+        auto kern = per_sm >= 3 ? wn_mel_kernel_s8<3> : wn_mel_kernel_s8<2>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
             return fail(nullptr, WN_ERR_CUDA, "wn_melspectrogram: shared memory request failed");
         }
-        const int per_sm = std::max(1, std::min(2, (int)((size_t)(220 << 10) / smem)));
         const int grid = (int)std::min<long long>(items, 148LL * per_sm);
-        wn_mel_kernel_s8<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+        kern<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
     } else {
         const size_t smem = (size_t)p.n_fft * 16 + (size_t)p.n_bins * 8 + 16;    // FFT buffer + two magnitude spectra
         if (cudaFuncSetAttribute(wn_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

@@ -92,7 +92,9 @@ __device__ __forceinline__ void mel_pass(const double2 *__restrict__ x, double2 
     }
 }
 
-extern "C" __global__ void __launch_bounds__(256, 2) wn_mel_kernel_s8(const WnMelParams p)
+// CTAS = resident CTAs per SM the register allocation is bounded for: 2 -> 122 registers, 3 -> 80 registers (24 bytes of spill)
+template <int CTAS>
+__global__ void __launch_bounds__(256, CTAS) wn_mel_kernel_s8(const WnMelParams p)
 {
     extern __shared__ __align__(16) unsigned char mel_smem[];
     const int padded = p.n_fft + (p.n_fft >> 3);
