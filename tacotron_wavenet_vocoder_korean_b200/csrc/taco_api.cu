@@ -71,6 +71,7 @@ struct taco_handle {
     DecParams *dp_dev = nullptr;
     long long *prof_dev = nullptr;            // in-kernel phase profile of the last decoder launch (TACO_PROFILE=1)
     float *dec_img = nullptr;
+    float *dec_p0_init = nullptr;             // relu(b1) of the first decoder prenet layer: its activation for the zero <GO> frame (fused plan)
     int dec_grid = 0, dec_smem = 0, dec_maxK = 0, dec_dyn_max = 0;
     unsigned *barrier_dev = nullptr;
     size_t smem_optin = 0;
@@ -282,13 +283,30 @@ int build_decoder(taco_handle *h) {
         }
         if (ks != K) { h->err = "decoder: segment widths do not add up for " + kname; return false; }
         ph.out_buf = out_buf; ph.h_buf = h_buf; ph.res_in = res_in; ph.res_out = res_out; ph.U = U;
+        ph.N1 = N; ph.epi2 = DE_LINEAR; ph.out_buf2 = -1;
         h->dec_maxK = std::max(h->dec_maxK, K);
         return true;
     };
+    // Fused plan (default; TACO_NO_FUSE=1 keeps one phase per layer): the output projection is linear and the first prenet layer
+    // reads its last frame (helpers.py:39-41), so  relu(W1 . (Wout_last . o + bout_last) + b1) = relu((Wout_last W1) . o + (bout_last W1 + b1))
+    // is evaluated BY THE OUTPUT PHASE ITSELF as extra columns of its matrix (product formed once in fp64): one grid barrier
+    // less per decoder step.  The step loop is rotated accordingly -- prenet layers 2.., attention, decoder cells, then
+    // [output projection | first prenet layer of the NEXT step] -- and the first step's prenet activation relu(b1) (the <GO>
+    // frame is zero) is written by the init kernel.
+    const bool fuse_out = getenv("TACO_NO_FUSE") == nullptr;
+    h->dec_p0_init = nullptr;
     int ci = nm, prev = DB_X;
     for (int i = 0; i < c.n_dec_prenet; ++i) {
         const std::string s = D + "decoder_prenet/dense_" + std::to_string(i + 1);
-        if (!add_dense(s + "/kernel", s + "/bias", ci, c.dec_prenet_sizes[i], DE_RELU, {{prev, ci}}, DB_P0 + i, -1, -1, -1, 0)) return TACO_ERR_STATE;
+        if (i == 0 && fuse_out) {
+            auto b1 = find_w(h, s + "/bias", c.dec_prenet_sizes[0]);
+            if (!b1) return TACO_ERR_STATE;
+            std::vector<float> r0(*b1);
+            for (auto &v : r0) v = std::max(v, 0.f);
+            h->dec_p0_init = upload(h, r0.data(), r0.size());
+            if (!h->dec_p0_init) return fail(h, TACO_ERR_CUDA, "uploading the decoder prenet init failed");
+            h->n_params -= (int64_t)r0.size();
+        } else if (!add_dense(s + "/kernel", s + "/bias", ci, c.dec_prenet_sizes[i], DE_RELU, {{prev, ci}}, DB_P0 + i, -1, -1, -1, 0)) return TACO_ERR_STATE;
         prev = DB_P0 + i;
         ci = c.dec_prenet_sizes[i];
     }
@@ -314,6 +332,35 @@ int build_decoder(taco_handle *h) {
     }
     if (!add_dense(D + "output_projection/kernel", D + "output_projection/bias", R, OD, DE_OUT, {{DB_O0 + c.dec_layer_num, R}}, DB_X, -1, -1, -1, 0))
         return TACO_ERR_STATE;
+    if (fuse_out) {
+        const int P0 = c.dec_prenet_sizes[0];
+        const std::string s1 = D + "decoder_prenet/dense_1";
+        auto W1 = find_w(h, s1 + "/kernel", (size_t)nm * P0), b1 = find_w(h, s1 + "/bias", P0);
+        if (!W1 || !b1) return TACO_ERR_STATE;
+        DenseSrc &so = srcs.back();                        // (R, OD) + (OD)
+        DenseSrc f;
+        f.W.assign((size_t)R * (OD + P0), 0.f);
+        f.b.assign(OD + P0, 0.f);
+        for (int k = 0; k < R; ++k) {
+            for (int col = 0; col < OD; ++col) f.W[(size_t)k * (OD + P0) + col] = so.W[(size_t)k * OD + col];
+            for (int j = 0; j < P0; ++j) {
+                double acc = 0.0;
+                for (int m = 0; m < nm; ++m) acc += (double)so.W[(size_t)k * OD + (OD - nm + m)] * (double)(*W1)[(size_t)m * P0 + j];
+                f.W[(size_t)k * (OD + P0) + OD + j] = (float)acc;
+            }
+        }
+        for (int col = 0; col < OD; ++col) f.b[col] = so.b[col];
+        for (int j = 0; j < P0; ++j) {
+            double acc = (double)(*b1)[j];
+            for (int m = 0; m < nm; ++m) acc += (double)so.b[OD - nm + m] * (double)(*W1)[(size_t)m * P0 + j];
+            f.b[OD + j] = (float)acc;
+        }
+        srcs.back() = std::move(f);
+        DecPhase &ph = dp.ph[np - 1];
+        ph.N = OD + P0; ph.N1 = OD; ph.epi2 = DE_RELU; ph.out_buf2 = DB_P0;
+        ph.ncp = (ph.N + G - 1) / G;
+        ph.pad = ph.ncp <= 2 ? ph.ncp : ((ph.ncp + 3) & ~3);
+    }
     dp.n_phases = np;
 
     // which input slots were final before the previous phase started (staged while waiting at the barrier)
@@ -327,6 +374,7 @@ int build_decoder(taco_handle *h) {
             if (ph.epi == DE_RELU || ph.epi == DE_LINEAR) writer[ph.out_buf] = i;
             if (ph.epi == DE_CAND) { writer[ph.out_buf] = i; if (ph.res_out >= 0) writer[ph.res_out] = i; }
             if (ph.epi == DE_OUT) writer[DB_X] = i;
+            if (ph.N1 < ph.N && ph.out_buf2 >= 0) writer[ph.out_buf2] = i;
         }
         for (int i = 1; i < np; ++i) {
             DecPhase &ph = dp.ph[i];
@@ -949,8 +997,11 @@ int taco_synthesize(taco_handle *h, const taco_synth_args *a, void *stream_) {
     DecInit di;
     memset(&di, 0, sizeof(di));
     di.n = 0;
-    auto add_init = [&](int b, const float *src) { di.dst[di.n] = w.db[b]; di.src[di.n] = src; di.width[di.n] = db_width[b]; di.n++; };
+    auto add_init = [&](int b, const float *src, const float *vec = nullptr) {
+        di.dst[di.n] = w.db[b]; di.src[di.n] = src; di.vec[di.n] = vec; di.width[di.n] = db_width[b]; di.n++;
+    };
     add_init(DB_X, nullptr);
+    if (h->dec_p0_init) add_init(DB_P0, nullptr, h->dec_p0_init);
     add_init(DB_CTX, nullptr);
     add_init(DB_HATT, att_init);
     for (int i = 0; i < c.dec_layer_num; ++i) add_init(DB_H1 + i, dec_init[i]);

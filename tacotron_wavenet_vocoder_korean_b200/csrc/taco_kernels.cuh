@@ -399,6 +399,8 @@ struct DecPhase {
     int h_buf;                // GATES: state h (r*h -> DB_RH, u -> DB_U)
     int res_in, res_out;      // CAND: o_out = o_in + h' (ResidualWrapper), -1 = none
     int U;                    // GATES: units
+    int N1;                   // columns [0, N1) take the epilogue above; [N1, N) a second one (fused phases); N1 == N: one part
+    int epi2, out_buf2;       // second part: DE_RELU / DE_LINEAR into out_buf2 (N - N1 features)
 };
 
 struct DecParams {
@@ -616,12 +618,16 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
                                 for (int w = 0; w < DEC_WARPS; ++w) v += red[(w * 4 + warp) * 32 + lane];
                                 v += bs[cl];
                                 const size_t ti = (size_t)tile * 32 + lane;   // padded sentence index
-                                switch (ph.epi) {
+                                // fused phases (two matrices that read the same input side by side): the columns from N1 on
+                                // belong to the second matrix and take its epilogue
+                                int epi = ph.epi, ecol = col, eN = ph.N1, eout = ph.out_buf;
+                                if (col >= ph.N1) { epi = ph.epi2; ecol = col - ph.N1; eN = ph.N - ph.N1; eout = ph.out_buf2; }
+                                switch (epi) {
                                     case DE_RELU:
-                                        P.buf[ph.out_buf][((size_t)tile * ph.N + col) * 32 + lane] = fmaxf(v, 0.f);
+                                        P.buf[eout][((size_t)tile * eN + ecol) * 32 + lane] = fmaxf(v, 0.f);
                                         break;
                                     case DE_LINEAR:
-                                        P.buf[ph.out_buf][((size_t)tile * ph.N + col) * 32 + lane] = v;
+                                        P.buf[eout][((size_t)tile * eN + ecol) * 32 + lane] = v;
                                         break;
                                     case DE_QUERY:
                                         P.q_row[ti * ph.N + col] = v;
@@ -853,9 +859,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) taco_decoder_kernel(const DecP
 // Decoder prologue: transposes the initial states into feature-major tiles, zeroes the <GO> frame, the context
 // and the attention state (dirac at position 0 for monotonic attention, zeros for loc_sen).
 struct DecInit {
-    float *dst[3 + 4];
-    const float *src[3 + 4];   // (N, width) row-major or null (= zeros)
-    int width[3 + 4];
+    float *dst[4 + 4];
+    const float *src[4 + 4];   // (N, width) row-major or null (= zeros)
+    const float *vec[4 + 4];   // (width) one vector for every sentence (takes precedence), or null
+    int width[4 + 4];
     int n;
     float *state0;
     int N, tiles, T_in, dirac;
@@ -869,7 +876,7 @@ __global__ void taco_dec_init_kernel(const DecInit d) {
             const size_t fk = i >> 5;
             const int tile = (int)(fk / d.width[b]), f = (int)(fk - (size_t)tile * d.width[b]);
             const int n = tile * 32 + r;
-            d.dst[b][i] = (d.src[b] && n < d.N) ? d.src[b][(size_t)n * d.width[b] + f] : 0.0f;
+            d.dst[b][i] = d.vec[b] ? d.vec[b][f] : (d.src[b] && n < d.N) ? d.src[b][(size_t)n * d.width[b] + f] : 0.0f;
         }
     }
     for (size_t i = gt; i < (size_t)d.N * d.T_in; i += gs) d.state0[i] = (d.dirac && (i % d.T_in) == 0) ? 1.0f : 0.0f;
