@@ -23,6 +23,7 @@
 namespace {
 
 constexpr int kManyRows = 10;
+constexpr int kSharedRingRows = 16;    // cluster path: from this many rows on the layer kernel uses one shared ring per layer (wn_kernel_v2.cuh, SR); measured break-even
 constexpr int kMaxDynSmem = 232448 - 2048;   // 227 KB opt-in limit minus static/reserved slack
 
 std::string g_create_error;
@@ -178,6 +179,7 @@ struct wn_handle {
     bool v2_planned = false, v2 = false;
     const void *kernel_v2_layers = nullptr, *kernel_v2_layers_prof = nullptr, *kernel_v2_tail = nullptr;
     const void *kernel_v2_layers16 = nullptr, *kernel_v2_layers16_prof = nullptr;
+    const void *kernel_v2_layers_sr = nullptr, *kernel_v2_layers16_sr = nullptr;      // shared-ring builds (launches with >= kSharedRingRows rows)
     int v2_n16 = 0;                        // > 0: layers [0, 4*n16) run in n16 clusters of 16, the rest in clusters of 8 (second launch)
     cudaStream_t v2_sc = nullptr;
     cudaEvent_t v2_join_c = nullptr;
@@ -727,12 +729,15 @@ int wn_finalize(wn_handle *h)
         h->kernel_v2_layers_prof = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true, 8> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true, 8>;
         h->kernel_v2_layers16 = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false, 16> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false, 16>;
         h->kernel_v2_layers16_prof = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, true, 16> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, true, 16>;
+        h->kernel_v2_layers_sr = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false, 8, true> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false, 8, true>;
+        h->kernel_v2_layers16_sr = fa ? (const void *)wn_layers_kernel_v2<ShapeCfg2, true, false, 16, true> : (const void *)wn_layers_kernel_v2<ShapeCfg2, false, false, 16, true>;
         h->kernel_v2_tail = (const void *)wn_tail_kernel_v2<ShapeCfg2>;
         cudaError_t e = cudaSuccess;
-        const void *ks[4] = {h->kernel_v2_layers, h->kernel_v2_layers_prof, h->kernel_v2_layers16, h->kernel_v2_layers16_prof};
-        for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+        const void *ks[6] = {h->kernel_v2_layers, h->kernel_v2_layers_prof, h->kernel_v2_layers_sr, h->kernel_v2_layers16, h->kernel_v2_layers16_prof,
+                             h->kernel_v2_layers16_sr};
+        for (int i = 0; i < 6 && e == cudaSuccess; ++i) {
             e = cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_layers);
-            if (e == cudaSuccess && i >= 2) e = cudaFuncSetAttribute(ks[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e == cudaSuccess && i >= 3) e = cudaFuncSetAttribute(ks[i], cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         }
         if (e == cudaSuccess) e = cudaFuncSetAttribute(h->kernel_v2_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, h->v2_smem_tail);
         auto max_clusters = [&](const void *k, int cs, int *n) -> cudaError_t {
@@ -953,7 +958,12 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
     for (int b = a->rows; b < c.batch; ++b) { p.T_row[b] = 0; p.gc_id[b] = 0; }
 
     CUDA_TRY(h, cudaMemsetAsync(h->mbox.p, 0, h->mbox_bytes, st));
-    if (h->ring_bytes && !h->v2) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));      // the cluster path reads the rings only once they hold data
+    // Shared-ring builds of the layer kernel (one tagged ring per layer instead of four private copies, wn_kernel_v2.cuh) from
+    // kSharedRingRows rows on, where the private copies overflow the L2; WN_SHARED_RING=0 / 1 forces either build for A/B runs.
+    const int sr_env = getenv("WN_SHARED_RING") ? atoi(getenv("WN_SHARED_RING")) : -1;
+    const bool shared_ring = h->v2 && !h->prof_on && p.T < (1 << 30) && (sr_env >= 0 ? sr_env != 0 : a->rows >= kSharedRingRows);
+    // the cluster path reads the private rings only once they hold data; the shared ring's tags must start at zero
+    if (h->ring_bytes && (!h->v2 || shared_ring)) CUDA_TRY(h, cudaMemsetAsync(h->ring.p, 0, h->ring_bytes, st));
     CUDA_TRY(h, cudaMemsetAsync(h->status.p, 0, 32, st));
     p.prof = nullptr;
     if (h->prof_on) {
@@ -973,23 +983,23 @@ int wn_generate(wn_handle *h, const wn_generate_args *a, void *stream)
             // layers [0, 4*n16) in clusters of 16, then the rest in clusters of 8 on a second stream, then the tail
             const int split = 4 * h->v2_n16;
             p.layer_base = 0; p.layer_end = split;
-            CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers16_prof : h->kernel_v2_layers16, dim3(16 * h->v2_n16), dim3(V2_NT), args,
-                                         (size_t)h->v2_smem_layers, h->v2_sa));
+            CUDA_TRY(h, cudaLaunchKernel(shared_ring ? h->kernel_v2_layers16_sr : h->prof_on ? h->kernel_v2_layers16_prof : h->kernel_v2_layers16,
+                                         dim3(16 * h->v2_n16), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
             if (split < p.L) {
                 WnParams p2 = p;
                 p2.layer_base = split; p2.layer_end = p.L; p2.claim_slot = 6;
                 void *args2[] = {&p2};
                 CUDA_TRY(h, cudaStreamWaitEvent(h->v2_sc, h->v2_fork, 0));
-                CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(((p.L - split + 1) / 2) * V2_CS), dim3(V2_NT),
-                                             args2, (size_t)h->v2_smem_layers, h->v2_sc));
+                CUDA_TRY(h, cudaLaunchKernel(shared_ring ? h->kernel_v2_layers_sr : h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers,
+                                             dim3(((p.L - split + 1) / 2) * V2_CS), dim3(V2_NT), args2, (size_t)h->v2_smem_layers, h->v2_sc));
                 CUDA_TRY(h, cudaEventRecord(h->v2_join_c, h->v2_sc));
                 CUDA_TRY(h, cudaStreamWaitEvent(st, h->v2_join_c, 0));
                 h->launches++;
             }
         } else {
             p.layer_base = 0; p.layer_end = p.L;
-            CUDA_TRY(h, cudaLaunchKernel(h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers, dim3(h->v2_grid_layers), dim3(V2_NT), args,
-                                         (size_t)h->v2_smem_layers, h->v2_sa));
+            CUDA_TRY(h, cudaLaunchKernel(shared_ring ? h->kernel_v2_layers_sr : h->prof_on ? h->kernel_v2_layers_prof : h->kernel_v2_layers,
+                                         dim3(h->v2_grid_layers), dim3(V2_NT), args, (size_t)h->v2_smem_layers, h->v2_sa));
         }
         CUDA_TRY(h, cudaLaunchKernel(h->kernel_v2_tail, dim3(p.Mt), dim3(WN_NT), args, (size_t)h->v2_smem_tail, h->v2_sb));
         CUDA_TRY(h, cudaEventRecord(h->v2_join_a, h->v2_sa));

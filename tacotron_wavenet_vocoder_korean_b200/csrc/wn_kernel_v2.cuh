@@ -388,7 +388,13 @@ __device__ __forceinline__ float v2_sample_warp(const WnParams &p, const MBox &m
     return v2_draw_warp<SH>(p, b, step, lane, writer, c2, gum, logistic);
 }
 
-template <class SH, bool FAST, bool PROF, int CS>
+// SR ("shared ring", launches with >= 16 rows): ONE dilation ring per layer instead of one private copy per sibling CTA.  The
+// four copies (1.59 MB x 4 per row) overflow the L2 from about 10 rows on (profiles/r02_ncu_range_16x12000.csv: 3.9 GB of DRAM
+// traffic per launch at 16 rows) and put HBM round trips into the helper groups' taps.  Every sibling holds the full layer input, so
+// sibling m pushes only its quarter of x; the ring holds 8-byte {value, step tag} words (the LL mailbox protocol) and a reader
+// that finds an older tag re-reads until the sibling's push has landed -- no ordering between the siblings is assumed.  The ring is
+// zeroed per launch (tag 0 is never expected).  SR = false is the unchanged round-2 code: the 8-row headline path keeps its SASS.
+template <class SH, bool FAST, bool PROF, int CS, bool SR>
 __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const int l_local)
 {
     using Cur = typename SH::Cur;        // packed for 256 slots: col = slot / 4, chunk = slot % 4, 8 float4
@@ -477,6 +483,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
 
     const int d = p.dil[l];
     float *ring_cta = p.ring + p.ring_off[l] + (size_t)m * N * d * R;
+    u64 *ring_sh = reinterpret_cast<u64 *>(p.ring + p.ring_off[l]);            // SR: (N, d, R) tagged words = half of the layer's region
     V2Ab ab{p.status, 0};
     const MBox mb = make_mbox(p);
     const size_t rowx = (size_t)L * M * R, rowa = (size_t)L * M * Sm;
@@ -539,12 +546,14 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
         // Global loads of an item (dilated tap from the ring, materialised lc row, layer 0: the draw's uniforms / forced input).
         // They are issued one item AHEAD (while the current item waits and computes): in a train of rows the helper is the
         // busiest group of a CTA, and 600-1000 cycles of exposed L2 / DRAM latency per item would be added to its service time.
-        struct GLoad { float oldv, lcraw, su; };
+        struct GLoad { float oldv, lcraw, su; u64 oldw; };
         auto gload = [&](int t, int b) -> GLoad {
-            GLoad g{0.0f, 0.0f, 0.0f};
+            GLoad g{0.0f, 0.0f, 0.0f, 0ull};
             const bool has_next = (t + 1 < p.T_row[b]);
-            if (has_next && d >= 2 && t + 1 >= d && ht < R)
-                g.oldv = v2_ld_cg_f32(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);       // x_l(t+1-d); the queue starts at zero (model.py:64)
+            if (has_next && d >= 2 && t + 1 >= d && ht < R) {
+                if constexpr (SR) g.oldw = ld_relaxed_u64(ring_sh + ((size_t)b * d + ((t + 1) % d)) * R + ht);
+                else g.oldv = v2_ld_cg_f32(ring_cta + ((size_t)b * d + ((t + 1) % d)) * R + ht);       // x_l(t+1-d); the queue starts at zero (model.py:64)
+            }
             if (SH::HAS_LC && !fold_lc && has_next && ht < SH::C && p.lc_up != nullptr) {
                 const long idx = (long)t - p.lc_shift;
                 if (idx >= 0 && idx < p.t_lc) g.lcraw = ld_nc_f32(p.lc_up + ((size_t)b * p.t_lc + idx) * SH::C + ht);
@@ -556,7 +565,7 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
             }
             return g;
         };
-        GLoad pref{0.0f, 0.0f, 0.0f};
+        GLoad pref{0.0f, 0.0f, 0.0f, 0ull};
         int pref_t = -1, pref_b = -1;
 
         for (int t = 0; t < p.T; ++t) {
@@ -585,6 +594,24 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                     if (hn && bn != b) { pref = gload(tn, bn); pref_t = tn; pref_b = bn; }
                 }
                 float oldv = cur.oldv, lcv = cur.lcraw;
+                if constexpr (SR) {
+                    if (has_next && d >= 2 && t + 1 >= d && ht < R) {
+                        // x_l(t+1-d) was pushed with tag (t+1-d) + 1 by the sibling that owns channel ht
+                        const unsigned want = (unsigned)(t + 2 - d);
+                        const u64 *pw = ring_sh + ((size_t)b * d + ((t + 1) % d)) * R + ht;
+                        u64 wv = cur.oldw;
+                        unsigned spins = 0;
+                        long long t0 = 0;
+                        while ((unsigned)(wv >> 32) != want && !ab.dead) {
+                            if (((++spins) & 0x3ffu) == 0) {
+                                t0 = v2_watchdog(ab.status, t0);
+                                if (t0 < 0) { ab.dead = 1; break; }
+                            }
+                            wv = ld_relaxed_u64(pw);
+                        }
+                        oldv = __uint_as_float((unsigned)wv);
+                    }
+                }
                 bool mel_last = false;
                 int mel_next = 0;
                 if (SH::HAS_LC && has_next && ht < SH::C) {
@@ -629,7 +656,11 @@ __device__ void layer_role_v2(const WnParams &p, const int l, const int m, const
                 hp.mark(7);
                 if (ht < R) {
                     const float xme = rb[LY::R_XRAW + ht];
-                    if (d >= 2) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + ht, xme);
+                    if constexpr (SR) {
+                        if (d >= 2 && ht / (R / M) == m) ll_store(ring_sh + ((size_t)b * d + (t % d)) * R + ht, xme, seq);
+                    } else {
+                        if (d >= 2) __stcg(ring_cta + ((size_t)b * d + (t % d)) * R + ht, xme);
+                    }
                     if (d == 1) oldv = xme;
                     xs_old[xp_x] = oldv;
                 }
@@ -1062,7 +1093,7 @@ __device__ void tail_role_v2(const WnParams &p, int mt)
 // chain crosses the die boundary once on its way down instead of wherever the hardware put the clusters.
 // Launch shapes (wn_api.cu): 15 clusters of 8 for the whole stack, or 7 clusters of 16 (layers 0..27) plus one cluster of 8
 // (layers 28, 29) as two concurrent launches -- 16-CTA clusters halve the number of L2 hops but only 7 are co-resident.
-template <class SH, bool FAST, bool PROF, int CS>
+template <class SH, bool FAST, bool PROF, int CS, bool SR = false>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers_kernel_v2(const __grid_constant__ WnParams p)
 {
     __shared__ int s_crole;
@@ -1084,7 +1115,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(V2_NT, 1) wn_layers
     const int l_local = (int)(crank >> 2), m = (int)(crank & 3u);
     const int l = p.layer_base + crole * LPC + l_local;
     if (l < p.layer_end) {
-        layer_role_v2<SH, FAST, PROF, CS>(p, l, m, l_local);
+        layer_role_v2<SH, FAST, PROF, CS, SR>(p, l, m, l_local);
     } else {
         v2_cluster_sync();
         __syncthreads();

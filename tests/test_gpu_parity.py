@@ -270,6 +270,43 @@ def test_many_rows_variant_bit_exact(cluster):
         assert np.array_equal(s[r, :tr], so[r, :tr])
 
 
+def test_shared_ring_build_equals_private_rings():
+    """From 16 rows on the cluster path keeps ONE tagged dilation ring per layer (wn_kernel_v2.cuh, SR) instead of one private copy
+    per sibling CTA.  Same bits as the private-ring build on the same 16-row job past the d = 512 wrap, in both directions on
+    one handle (the shared ring is zeroed per launch, the private rings are written before they are read), and when forced at 8 rows."""
+    kw = synth.cfg2(16)
+    net, w = build(kw)
+    T = 700
+    inp = make_inputs(kw, T)
+    lc = net.create_upsample(inp['mel'])
+
+    def run(rows, flag):
+        if flag is None:
+            os.environ.pop('WN_SHARED_RING', None)
+        else:
+            os.environ['WN_SHARED_RING'] = flag
+        try:
+            return net.generate(T, inp['x0'][:rows], inp['uniforms'][:rows], lc_up=lc[:rows], gc_ids=inp['gc_ids'][:rows], want_logits=True)
+        finally:
+            os.environ.pop('WN_SHARED_RING', None)
+    shared = run(16, None)                  # default at 16 rows: shared ring
+    private = run(16, '0')
+    again = run(16, '1')
+    assert torch.equal(shared[0], private[0]) and torch.equal(shared[1], private[1])
+    assert torch.equal(shared[0], again[0]) and torch.equal(shared[1], again[1])
+    eight = run(8, None)                    # default at 8 rows: private rings (the benchmark path)
+    eight_sr = run(8, '1')
+    assert torch.equal(eight[0], eight_sr[0]) and torch.equal(eight[1], eight_sr[1])
+    assert torch.equal(eight[0], shared[0][:8])
+    om = oracle_model(kw, w)
+    _oracle_threads(8)
+    try:
+        so = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc.cpu().numpy(), gc_ids=inp['gc_ids'], plan=plan_from_dict(net.plan()))
+    finally:
+        _oracle_threads(1)
+    assert np.array_equal(so, shared[0].cpu().numpy())
+
+
 def test_hparams_default_model_bit_exact():
     # the reference's own defaults (hparams.py:59-79): 50 layers, R=D=32, scalar input, lc + gc
     _, _, _, got, exp, _ = run_both(synth.cfg_hparams_default(2), 400)
