@@ -215,8 +215,10 @@ def test_best_effort_cpu_organisation_is_bit_identical_to_the_port(threads):
                     global_condition_cardinality=3)
     chunked = oracle.OrcPlan.natural()
     chunked.M, chunked.Mt, chunked.t_cur, chunked.t_old, chunked.t_dense, chunked.t_skip, chunked.t_post1 = 2, 2, 4, 2, 2, 4, 4
+    from tacotron_wavenet_vocoder_korean_b200.wavenet.model import plan_config
+    kernel_plan = plan_from_dict(plan_config(148, **synth.cfg2(5))[0])          # the evaluation plan the B200 kernels report for cfg-2
     for kw, T, plan in ((synth.tiny_mol(), 120, None), (synth.tiny_mol(), 60, chunked), (synth.tiny_mulaw(), 80, None), (mulaw_lc, 60, None),
-                        (synth.cfg2(5), 12, None)):
+                        (synth.cfg2(5), 12, None), (synth.cfg2(5), 8, kernel_plan)):
         om = oracle_model(kw, synth.make_weights(**kw))
         inp = make_inputs(kw, T)
         lc = om.upsample(inp['mel']) if 'mel' in inp else None
