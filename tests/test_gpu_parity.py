@@ -305,6 +305,17 @@ def test_shared_ring_build_equals_private_rings():
     finally:
         _oracle_threads(1)
     assert np.array_equal(so, shared[0].cpu().numpy())
+    # ragged rows (some finished early, one never started) through both builds
+    T_row = [700, 3, 0, 77, 700, 513, 9, 700, 650, 1, 700, 60, 700, 512, 700, 300]
+    outs = []
+    for flag in ('1', '0'):
+        os.environ['WN_SHARED_RING'] = flag
+        try:
+            outs.append(net.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], T_row=T_row).cpu().numpy())
+        finally:
+            os.environ.pop('WN_SHARED_RING', None)
+    for r, tr in enumerate(T_row):
+        assert np.array_equal(outs[0][r, :tr], so[r, :tr]) and np.array_equal(outs[1][r, :tr], so[r, :tr])
 
 
 def test_hparams_default_model_bit_exact():
