@@ -66,6 +66,8 @@ def lib():
                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p]
         L.orc_generate_best.argtypes = L.orc_generate.argtypes + [C.c_int]
+        L.orc_gate_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_gate_probe.restype = None
         L.orc_receptive_field.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_mu_law_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_mu_law_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -210,6 +212,15 @@ def mol_sample(y, uniforms):
     out = np.empty(y.shape[:-1], np.float32)
     lib().orc_mol_sample(_ptr(y), _ptr(u), out.size, nr, _ptr(out))
     return out
+
+
+def gate_probe(f, g):
+    """z = tanh32(f) * sigmoid32(g) by the 8-lane path of wn_cpu_best.h and by the scalar pinned functions."""
+    f = np.ascontiguousarray(f, dtype=np.float32)
+    g = np.ascontiguousarray(g, dtype=np.float32)
+    zv, zs = np.empty(f.shape, np.float32), np.empty(f.shape, np.float32)
+    lib().orc_gate_probe(_ptr(f), _ptr(g), f.size, _ptr(zv), _ptr(zs))
+    return zv, zs
 
 
 def softmax_probs(logits_row):

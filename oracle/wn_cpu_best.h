@@ -76,6 +76,26 @@ static inline void orcb_chain8x4(const float *wc, int stride, const float *x, in
     _mm256_storeu_ps(dst, a0); _mm256_storeu_ps(dst + rs, a1); _mm256_storeu_ps(dst + 2 * rs, a2); _mm256_storeu_ps(dst + 3 * rs, a3);
 }
 
+/* eight rows of an 8-column strip: 8 independent chains (with four, the 4-cycle fma latency leaves half of the issue slots empty) */
+static inline void orcb_chain8x8(const float *wc, int stride, const float *x, int ldx, int ch, float *dst, size_t rs)
+{
+    __m256 a0 = _mm256_setzero_ps(), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+    const float *x0 = x, *x1 = x + ldx, *x2 = x1 + ldx, *x3 = x2 + ldx, *x4 = x3 + ldx, *x5 = x4 + ldx, *x6 = x5 + ldx, *x7 = x6 + ldx;
+    for (int i = 0; i < ch; ++i) {
+        const __m256 w0 = _mm256_loadu_ps(wc + (size_t)i * stride);
+        a0 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x0 + i), a0);
+        a1 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x1 + i), a1);
+        a2 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x2 + i), a2);
+        a3 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x3 + i), a3);
+        a4 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x4 + i), a4);
+        a5 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x5 + i), a5);
+        a6 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x6 + i), a6);
+        a7 = _mm256_fmadd_ps(w0, _mm256_broadcast_ss(x7 + i), a7);
+    }
+    _mm256_storeu_ps(dst, a0); _mm256_storeu_ps(dst + rs, a1); _mm256_storeu_ps(dst + 2 * rs, a2); _mm256_storeu_ps(dst + 3 * rs, a3);
+    _mm256_storeu_ps(dst + 4 * rs, a4); _mm256_storeu_ps(dst + 5 * rs, a5); _mm256_storeu_ps(dst + 6 * rs, a6); _mm256_storeu_ps(dst + 7 * rs, a7);
+}
+
 /* scratch block of a strip: [N][t][nc] */
 static void mvb_chains(const float *W, int stride, const float *X, int ldx, int N, int K, int t, float *scratch, int nc)
 {
@@ -86,8 +106,10 @@ static void mvb_chains(const float *W, int stride, const float *X, int ldx, int 
         int b = 0;
         if (nc == 16)
             for (; b + 4 <= N; b += 4) orcb_chain16x4(wc, stride, X + (size_t)b * ldx + c * ch, ldx, ch, scratch + ((size_t)b * t + c) * nc, rs);
-        else if (nc == 8)
+        else if (nc == 8) {
+            for (; b + 8 <= N; b += 8) orcb_chain8x8(wc, stride, X + (size_t)b * ldx + c * ch, ldx, ch, scratch + ((size_t)b * t + c) * nc, rs);
             for (; b + 4 <= N; b += 4) orcb_chain8x4(wc, stride, X + (size_t)b * ldx + c * ch, ldx, ch, scratch + ((size_t)b * t + c) * nc, rs);
+        }
         for (; b < N; ++b) {
             const float *x = X + (size_t)b * ldx + c * ch;
             float *restrict a = scratch + ((size_t)b * t + c) * nc;
@@ -129,6 +151,58 @@ static void mvb(const float *W, int stride, int c0, int c1, const float *X, int 
         }
         o0 += sw;
     }
+}
+
+/* The pinned activation (wn_math_ref.h: orc_exp32 / orc_tanh32 / orc_sigmoid32) for eight lanes at once: the same IEEE operations
+ * in the same order per lane (fma, correctly rounded division, exponent add), so z = tanh32(f) * sigmoid32(g) is bit-identical to
+ * the scalar functions -- tests/test_oracle.py compares them on edge values and random inputs. */
+static inline __m256 orcb_exp32x8(__m256 x)
+{
+    const __m256 lt = _mm256_cmp_ps(x, _mm256_set1_ps(-87.0f), _CMP_LT_OQ);                   /* x < -87 -> +0 */
+    x = _mm256_blendv_ps(x, _mm256_set1_ps(88.0f), _mm256_cmp_ps(x, _mm256_set1_ps(88.0f), _CMP_GT_OQ));
+    const __m256 magic = _mm256_set1_ps(12582912.0f);
+    const __m256 t = _mm256_fmadd_ps(x, _mm256_set1_ps(1.44269504088896341f), magic);
+    const __m256 n = _mm256_sub_ps(t, magic);
+    __m256 r = _mm256_fmadd_ps(n, _mm256_set1_ps(-0.693359375f), x);
+    r = _mm256_fmadd_ps(n, _mm256_set1_ps(2.12194440e-4f), r);
+    __m256 p = _mm256_set1_ps(1.9875691500e-4f);
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(1.3981999507e-3f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(8.3334519073e-3f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(4.1665795894e-2f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(1.6666665459e-1f));
+    p = _mm256_fmadd_ps(p, r, _mm256_set1_ps(5.0000001201e-1f));
+    const __m256 r2 = _mm256_mul_ps(r, r);
+    const __m256 e = _mm256_add_ps(_mm256_fmadd_ps(p, r2, r), _mm256_set1_ps(1.0f));
+    const __m256i ni = _mm256_cvttps_epi32(n);
+    const __m256 res = _mm256_castsi256_ps(_mm256_add_epi32(_mm256_castps_si256(e), _mm256_slli_epi32(ni, 23)));
+    return _mm256_andnot_ps(lt, res);
+}
+static inline __m256 orcb_gate8(__m256 f, __m256 g)
+{
+    const __m256 sign = _mm256_castsi256_ps(_mm256_set1_epi32((int)0x80000000u));
+    const __m256 one = _mm256_set1_ps(1.0f);
+    /* sigmoid32(g) = 1 / (1 + exp32(-g)) */
+    const __m256 sg = _mm256_div_ps(one, _mm256_add_ps(one, orcb_exp32x8(_mm256_xor_ps(g, sign))));
+    /* tanh32(f) = copysign(|f| > 44 ? 1 : 1 - 2 / (exp32(2|f|) + 1), f) */
+    const __m256 af = _mm256_andnot_ps(sign, f);
+    const __m256 e = orcb_exp32x8(_mm256_add_ps(af, af));
+    __m256 r = _mm256_sub_ps(one, _mm256_div_ps(_mm256_set1_ps(2.0f), _mm256_add_ps(e, one)));
+    r = _mm256_blendv_ps(r, one, _mm256_cmp_ps(af, _mm256_set1_ps(44.0f), _CMP_GT_OQ));
+    const __m256 th = _mm256_or_ps(_mm256_andnot_ps(sign, r), _mm256_and_ps(sign, f));
+    return _mm256_mul_ps(th, sg);
+}
+/* z[i] = tanh32(f[i]) * sigmoid32(g[i]), i < n (model.py:86) */
+static void orcb_gate(const float *f, const float *g, float *z, int n)
+{
+    int i = 0;
+    for (; i + 8 <= n; i += 8) _mm256_storeu_ps(z + i, orcb_gate8(_mm256_loadu_ps(f + i), _mm256_loadu_ps(g + i)));
+    for (; i < n; ++i) z[i] = orc_tanh32(f[i]) * orc_sigmoid32(g[i]);
+}
+/* test hook: vector path (whole vectors + scalar tail) and the scalar functions on the same inputs */
+void orc_gate_probe(const float *f, const float *g, int n, float *z_vec, float *z_scalar)
+{
+    orcb_gate(f, g, z_vec, n);
+    for (int i = 0; i < n; ++i) z_scalar[i] = orc_tanh32(f[i]) * orc_sigmoid32(g[i]);
 }
 
 /* A thread's private, contiguous copy of the column slice [c0, c1) of a (K, stride) matrix: its share of the weights is then
@@ -285,9 +359,8 @@ static void *orcb_worker(void *arg_)
                 ORCB_ADD(f, pk[l].wf1, x, R, R, p.t_cur);
                 ORCB_ADD(gg, pk[l].wg1, x, R, R, p.t_cur);
 #undef ORCB_ADD
-                for (int b = 0; b < N; ++b)
-                    for (int o = d0; o < d1; ++o)
-                        g->z[(size_t)b * D + o] = orc_tanh32(f[(size_t)b * D + o]) * orc_sigmoid32(gg[(size_t)b * D + o]);   /* model.py:86 */
+                for (int b = 0; b < N; ++b)                                                    /* model.py:86 */
+                    orcb_gate(f + (size_t)b * D + d0, gg + (size_t)b * D + d0, g->z + (size_t)b * D + d0, nd);
             }
             orcb_wait(&g->bar, &sense);          /* z complete; every thread has read the ring slot and x */
             /* queue push (model.py:145), skip 1x1 + running sum (model.py:157), dense 1x1 + residual */

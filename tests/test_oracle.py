@@ -226,3 +226,30 @@ def test_best_effort_cpu_organisation_is_bit_identical_to_the_port(threads):
         a = om.generate(T, forced, inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True, plan=plan)
         b = om.generate(T, forced, inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True, plan=plan, best_effort_threads=threads)
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+def test_best_effort_vector_gate_is_the_pinned_scalar_gate():
+    """The 8-lane tanh32 * sigmoid32 of oracle/wn_cpu_best.h against the scalar pinned functions: identical bits on the range
+    edges of exp32 (-87, 88, +-44 for tanh), zeros of both signs, denormals, infinities, and two million random inputs."""
+    edge = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 43.999, 44.0, 44.00001, -44.0, -44.00001, 87.0, -87.0, 87.00001, -87.00001,
+                     88.0, 88.5, -88.5, 100.0, -100.0, np.inf, -np.inf, 0.5, -0.5, 1.0, -1.0, 20.0, -20.0, 3e-8, -3e-8], np.float32)
+    f, g = np.meshgrid(edge, edge)
+    rs = np.random.RandomState(0)
+    f = np.concatenate([f.ravel(), rs.randn(1000003).astype(np.float32) * 4, rs.uniform(-100, 100, 1000000).astype(np.float32)])
+    g = np.concatenate([g.ravel(), rs.randn(1000003).astype(np.float32) * 4, rs.uniform(-100, 100, 1000000).astype(np.float32)])
+    zv, zs = oracle.gate_probe(f, g)
+    assert np.array_equal(zv.view(np.uint32), zs.view(np.uint32))
+
+
+def test_best_effort_cpu_sixteen_threads_eight_column_slices():
+    """16 threads on cfg-2: every thread owns 8 gated channels (one AVX2 vector), the 8-rows-at-a-time kernel plus a remainder row."""
+    from tacotron_wavenet_vocoder_korean_b200 import synth
+    from tests.helpers import make_inputs, oracle_model
+    kw = synth.cfg2(9)
+    om = oracle_model(kw, synth.make_weights(**kw))
+    T = 6
+    inp = make_inputs(kw, T)
+    lc = om.upsample(inp['mel'])
+    a = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True)
+    b = om.generate(T, inp['x0'], inp['uniforms'], lc_up=lc, gc_ids=inp['gc_ids'], want_logits=True, best_effort_threads=16)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
